@@ -1,0 +1,191 @@
+// extern "C" surface of libdmdqn_b200.so (include/dmdqn_b200.h): argument validation and
+// dispatch only; the kernels live in featurize.cu, act.cu, replay.cu and learn.cu.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace dmdqn {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int validate_dims(const dmdqn_dims* d) {
+    DMDQN_CHECK_ARG(d != nullptr, "dims is NULL");
+    DMDQN_CHECK_ARG(d->n_agents >= 1, "n_agents=%d must be >= 1", d->n_agents);
+    DMDQN_CHECK_ARG(d->n_nets == d->n_agents || d->n_nets == 1,
+                    "n_nets=%d must be n_agents (independent) or 1 (shared)", d->n_nets);
+    DMDQN_CHECK_ARG(d->obs_dim >= 1 && d->obs_stride >= d->obs_dim && d->obs_stride % 16 == 0 &&
+                        d->obs_stride <= 128,
+                    "obs_dim=%d obs_stride=%d: stride must be a multiple of 16 in [obs_dim, 128]",
+                    d->obs_dim, d->obs_stride);
+    DMDQN_CHECK_ARG(d->hidden == 64 || d->hidden == 128 || d->hidden == 256 || d->hidden == 512,
+                    "hidden=%d: supported widths are 64, 128, 256, 512 (nn_layers=[H,H])", d->hidden);
+    DMDQN_CHECK_ARG(d->n_actions >= 1 && d->n_actions <= DMDQN_MAX_ACTIONS, "n_actions=%d must be in [1,4]",
+                    d->n_actions);
+    DMDQN_CHECK_ARG(d->batch >= 1 && d->batch <= 4096, "batch=%d must be in [1,4096]", d->batch);
+    DMDQN_CHECK_ARG(d->capacity >= 1, "capacity=%d must be >= 1", d->capacity);
+    DMDQN_CHECK_ARG((int64_t)d->n_agents * d->capacity < (int64_t)1 << 31,
+                    "n_agents*capacity=%lld overflows the int32 row id",
+                    (long long)d->n_agents * d->capacity);
+    return DMDQN_OK;
+}
+
+static int check_workspace(const dmdqn_dims* dims, void* ws, size_t bytes, Workspace* out) {
+    int rc = validate_dims(dims);
+    if (rc) return rc;
+    *out = make_workspace(*dims);
+    DMDQN_CHECK_ARG(ws != nullptr, "workspace is NULL");
+    if (bytes < out->total) {
+        set_error("workspace has %zu bytes, %zu needed", bytes, out->total);
+        return DMDQN_ERR_WORKSPACE;
+    }
+    return DMDQN_OK;
+}
+
+}  // namespace dmdqn
+
+using namespace dmdqn;
+
+extern "C" {
+
+const char* dmdqn_last_error(void) { return g_error; }
+int dmdqn_abi_version(void) { return DMDQN_ABI_VERSION; }
+
+int dmdqn_param_layout(const dmdqn_dims* dims, dmdqn_layout* out) {
+    int rc = validate_dims(dims);
+    if (rc) return rc;
+    DMDQN_CHECK_ARG(out != nullptr, "out is NULL");
+    const Layout l = make_layout(dims->obs_stride, dims->hidden);
+    out->w1 = l.w1; out->b1 = l.b1; out->w2 = l.w2; out->b2 = l.b2;
+    out->w3 = l.w3; out->b3 = l.b3; out->stride = l.stride;
+    return DMDQN_OK;
+}
+
+int dmdqn_workspace_bytes(const dmdqn_dims* dims, size_t* out_bytes) {
+    int rc = validate_dims(dims);
+    if (rc) return rc;
+    DMDQN_CHECK_ARG(out_bytes != nullptr, "out_bytes is NULL");
+    *out_bytes = make_workspace(*dims).total;
+    return DMDQN_OK;
+}
+
+int dmdqn_featurize(int32_t n, const int32_t* halting, const int32_t* phase, const double* next_switch,
+                    const double* phase_dur, double sim_time, const uint8_t* signal_valid,
+                    const int32_t* nbr_idx, const int32_t* phase_lut, const double* snapshot,
+                    double local_weight, double global_weight, double* own_out, float* obs_out,
+                    int32_t obs_out_stride, double* reward_out, double* global_out, int64_t* scratch,
+                    void* stream) {
+    DMDQN_CHECK_ARG(n >= 1, "n=%d must be >= 1", n);
+    DMDQN_CHECK_ARG(halting && phase && next_switch && phase_dur && signal_valid && nbr_idx && phase_lut,
+                    "featurize: NULL input");
+    DMDQN_CHECK_ARG(obs_out && reward_out && global_out && scratch, "featurize: NULL output");
+    DMDQN_CHECK_ARG(obs_out_stride >= DMDQN_OBS_DIM, "obs_out_stride=%d must be >= 89", obs_out_stride);
+    return launch_featurize(n, halting, phase, next_switch, phase_dur, sim_time, signal_valid, nbr_idx,
+                            phase_lut, snapshot, local_weight, global_weight, own_out, obs_out,
+                            obs_out_stride, reward_out, global_out, scratch, (cudaStream_t)stream);
+}
+
+int dmdqn_act(const dmdqn_dims* dims, const dmdqn_nets* nets, const float* obs, int32_t obs_in_stride,
+              const double* eps, const uint32_t* w_explore, const uint32_t* w_action, int32_t* actions_out,
+              float* q_out, void* stream) {
+    int rc = validate_dims(dims);
+    if (rc) return rc;
+    DMDQN_CHECK_ARG(nets && nets->theta && obs && eps && w_explore && w_action && actions_out, "act: NULL argument");
+    DMDQN_CHECK_ARG(obs_in_stride >= dims->obs_dim, "obs_in_stride=%d < obs_dim=%d", obs_in_stride, dims->obs_dim);
+    return launch_act(*dims, *nets, obs, obs_in_stride, eps, w_explore, w_action, actions_out, q_out,
+                      (cudaStream_t)stream);
+}
+
+int dmdqn_push(const dmdqn_dims* dims, const dmdqn_replay* replay, const float* obs, const int32_t* act,
+               const double* rew, const float* next_obs, const uint8_t* done, int32_t in_stride,
+               const uint8_t* mask, void* stream) {
+    int rc = validate_dims(dims);
+    if (rc) return rc;
+    DMDQN_CHECK_ARG(replay && replay->obs && replay->next_obs && replay->act && replay->rew && replay->done &&
+                        replay->n_written, "push: NULL replay pointer");
+    DMDQN_CHECK_ARG(obs && act && rew && next_obs && done, "push: NULL transition pointer");
+    DMDQN_CHECK_ARG(in_stride >= dims->obs_dim, "in_stride=%d < obs_dim=%d", in_stride, dims->obs_dim);
+    return launch_push(*dims, *replay, obs, act, rew, next_obs, done, in_stride, mask, (cudaStream_t)stream);
+}
+
+static int check_learn_args(const dmdqn_hparams* hp, const dmdqn_replay* replay, const dmdqn_nets* nets,
+                            const void* draws) {
+    DMDQN_CHECK_ARG(hp && replay && nets && draws, "NULL argument");
+    DMDQN_CHECK_ARG(replay->obs && replay->next_obs && replay->act && replay->rew && replay->done &&
+                        replay->n_written, "NULL replay pointer");
+    DMDQN_CHECK_ARG(nets->theta && nets->theta_tgt && nets->adam_m && nets->adam_v && nets->learn_step,
+                    "NULL network pointer");
+    DMDQN_CHECK_ARG(hp->sample_mode >= 0 && hp->sample_mode <= 2, "sample_mode=%d", hp->sample_mode);
+    DMDQN_CHECK_ARG(hp->loss == DMDQN_LOSS_MSE || hp->loss == DMDQN_LOSS_HUBER, "loss=%d", hp->loss);
+    DMDQN_CHECK_ARG(hp->precision == DMDQN_PRECISION_FP32, "precision=%d: only fp32 is built", hp->precision);
+    return DMDQN_OK;
+}
+
+int dmdqn_sample(const dmdqn_dims* dims, const dmdqn_hparams* hp, const dmdqn_replay* replay,
+                 const dmdqn_nets* nets, const void* draws, const uint8_t* learn_mask, int32_t advance_step,
+                 void* workspace, size_t workspace_bytes, void* stream) {
+    Workspace w;
+    int rc = check_workspace(dims, workspace, workspace_bytes, &w);
+    if (rc) return rc;
+    rc = check_learn_args(hp, replay, nets, draws);
+    if (rc) return rc;
+    return launch_sample(*dims, *hp, *replay, *nets, draws, learn_mask, advance_step, (char*)workspace, w,
+                         (cudaStream_t)stream);
+}
+
+int dmdqn_gather(const dmdqn_dims* dims, const dmdqn_replay* replay, const void* workspace,
+                 size_t workspace_bytes, float* states, int32_t* actions, float* rewards, float* next_states,
+                 float* dones, int32_t* active_out, void* stream) {
+    Workspace w;
+    int rc = check_workspace(dims, const_cast<void*>(workspace), workspace_bytes, &w);
+    if (rc) return rc;
+    DMDQN_CHECK_ARG(replay && replay->obs && replay->next_obs, "gather: NULL replay pointer");
+    DMDQN_CHECK_ARG(states && actions && rewards && next_states && dones, "gather: NULL output");
+    return launch_gather(*dims, *replay, (const char*)workspace, w, states, actions, rewards, next_states, dones,
+                         active_out, (cudaStream_t)stream);
+}
+
+int dmdqn_learn(const dmdqn_dims* dims, const dmdqn_hparams* hp, const dmdqn_replay* replay,
+                const dmdqn_nets* nets, const void* draws, const uint8_t* learn_mask, float* metrics_out,
+                void* workspace, size_t workspace_bytes, void* stream) {
+    Workspace w;
+    int rc = check_workspace(dims, workspace, workspace_bytes, &w);
+    if (rc) return rc;
+    rc = check_learn_args(hp, replay, nets, draws);
+    if (rc) return rc;
+    rc = launch_sample(*dims, *hp, *replay, *nets, draws, learn_mask, 1, (char*)workspace, w, (cudaStream_t)stream);
+    if (rc) return rc;
+    return launch_learn(*dims, *hp, *replay, *nets, metrics_out, (char*)workspace, w, (cudaStream_t)stream);
+}
+
+int dmdqn_debug(const dmdqn_dims* dims, void* workspace, size_t workspace_bytes, dmdqn_debug_views* out) {
+    Workspace w;
+    int rc = check_workspace(dims, workspace, workspace_bytes, &w);
+    if (rc) return rc;
+    DMDQN_CHECK_ARG(out != nullptr, "out is NULL");
+    char* ws = (char*)workspace;
+    out->y = (const float*)(ws + w.y);
+    out->q_all = (const float*)(ws + w.q_all);
+    out->q_next = (const float*)(ws + w.q_next);
+    out->tq_all = (const float*)(ws + w.tq_all);
+    out->rows = (const int32_t*)(ws + w.rows);
+    out->r_hat = (const float*)(ws + w.r_hat);
+    out->active = (const int32_t*)(ws + w.active);
+    return DMDQN_OK;
+}
+
+int dmdqn_sync_target(const dmdqn_dims* dims, const dmdqn_nets* nets, const uint8_t* mask, double tau,
+                      void* stream) {
+    int rc = validate_dims(dims);
+    if (rc) return rc;
+    DMDQN_CHECK_ARG(nets && nets->theta && nets->theta_tgt, "sync_target: NULL network pointer");
+    return launch_sync_target(*dims, *nets, mask, tau, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,226 @@
+// K1 -- device-resident ring replay buffer: push, sample (index draw + reward z-score), gather.
+//
+// Replaces ReplayBuffer.add / sample / __len__ and DQNAgent.remember / store_experience
+// (reference src/agents/dqn_agent.py:27-89,306-325).  The ring keeps deque(maxlen=C)
+// semantics: logical index j (0 = oldest) lives in slot (n_written - size + j) mod C.
+// Rows are padded to obs_stride floats (89 -> 96: three whole 128-byte lines) so that every
+// gather in K3/K4 is made of aligned 16-byte accesses.
+#include "common.cuh"
+
+namespace dmdqn {
+
+namespace {
+
+// ---------------------------------------------------------------- push ------------------
+__global__ void __launch_bounds__(64)
+push_kernel(dmdqn_dims d, dmdqn_replay rp, const float* __restrict__ obs, const int32_t* __restrict__ act,
+            const double* __restrict__ rew, const float* __restrict__ next_obs,
+            const uint8_t* __restrict__ done, int in_stride, const uint8_t* __restrict__ mask) {
+    const int a = blockIdx.x;
+    if (mask && !mask[a]) return;
+    const long long nw = rp.n_written[a];
+    const size_t row = (size_t)a * d.capacity + (size_t)(nw % d.capacity);  // overwrite the oldest
+    float* dst_s = rp.obs + row * d.obs_stride;
+    float* dst_n = rp.next_obs + row * d.obs_stride;
+    for (int c = threadIdx.x; c < d.obs_stride; c += blockDim.x) {
+        const bool in = c < d.obs_dim;
+        dst_s[c] = in ? obs[(size_t)a * in_stride + c] : 0.f;
+        dst_n[c] = in ? next_obs[(size_t)a * in_stride + c] : 0.f;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        rp.act[row] = act[a];
+        rp.rew[row] = rew[a];
+        rp.done[row] = done[a] ? 1 : 0;
+        rp.n_written[a] = nw + 1;
+    }
+}
+
+// ---------------------------------------------------------------- sample ----------------
+constexpr int kEmpty = -1;
+
+__device__ __forceinline__ unsigned hash_slot(int key, int log2t) {
+    return ((unsigned)key * 2654435761u) >> (32 - log2t);
+}
+
+// Canonical float64 tree sum over a batch held in shared memory: lane l adds elements
+// l, l+32, ... in order, then an xor butterfly (16,8,4,2,1).  oracle/replay.py
+// zscore_canonical restates exactly this, so the z-score is bit-comparable.
+template <typename F>
+__device__ __forceinline__ double tree_sum(int n, int lane, F elem) {
+    double acc = 0.0;
+    for (int i = lane; i < n; i += 32) acc = __dadd_rn(acc, elem(i));
+    for (int off = 16; off; off >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, off));
+    return acc;
+}
+
+// One warp per network.  smem: keys[T] vals[T] (sparse Fisher-Yates pool), words[B], rs[B].
+__global__ void __launch_bounds__(32)
+sample_kernel(dmdqn_dims d, dmdqn_hparams hp, dmdqn_replay rp, int32_t* __restrict__ learn_step,
+              const uint32_t* __restrict__ draws, const uint8_t* __restrict__ learn_mask, int advance,
+              int32_t* __restrict__ rows, float* __restrict__ r_hat, int32_t* __restrict__ act_b,
+              float* __restrict__ done_b, int32_t* __restrict__ active, int32_t* __restrict__ step_t,
+              int log2t) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int B = d.batch, T = 1 << log2t;
+    int* keys = reinterpret_cast<int*>(smem_raw);
+    int* vals = keys + T;
+    int* words = vals + T;                         // draws in, logical indices out
+    double* rs = reinterpret_cast<double*>(words + ((B + 1) & ~1));
+    const int g = blockIdx.x, lane = threadIdx.x;
+    const bool shared_net = d.n_nets == 1 && d.n_agents > 1;
+
+    // Population: this agent's ring, or (shared parameters) all rings of this GPU, which the
+    // host keeps equally filled, concatenated agent-major.
+    const long long nw0 = rp.n_written[shared_net ? 0 : g];
+    const int size0 = (int)(nw0 < d.capacity ? nw0 : d.capacity);
+    const long long pop = shared_net ? (long long)size0 * d.n_agents : size0;
+    const bool on = (learn_mask == nullptr || learn_mask[g]) && pop >= B;  // dqn_agent.py:61-62
+    if (lane == 0) {
+        active[g] = on ? 1 : 0;
+        int t = learn_step[g];
+        if (on && advance) learn_step[g] = ++t;    // dqn_agent.py:359
+        step_t[g] = t;
+    }
+    if (!on) return;
+
+    for (int i = lane; i < B; i += 32) words[i] = (int)draws[(size_t)g * B + i];
+    if (hp.sample_mode == DMDQN_SAMPLE_FISHER_YATES) {
+        for (int i = lane; i < T; i += 32) keys[i] = kEmpty;
+        __syncwarp();
+        if (lane == 0) {
+            // CPython random.sample pool path with randbelow(m) := (w*m) >> 32:
+            //   j = randbelow(n-i); result[i] = pool[j]; pool[j] = pool[n-i-1]
+            // pool is the identity except for <= B displaced entries kept in the hash map.
+            for (int i = 0; i < B; ++i) {
+                const unsigned m = (unsigned)(pop - i);
+                const int j = (int)__umulhi((unsigned)words[i], m);
+                const int t = (int)m - 1;
+                unsigned sj = hash_slot(j, log2t), st = hash_slot(t, log2t);
+                int vj = j, vt = t;
+                for (;; sj = (sj + 1) & (T - 1)) {      // lookup j; remember its slot for the put
+                    const int k = keys[sj];
+                    if (k == j) { vj = vals[sj]; break; }
+                    if (k == kEmpty) break;
+                }
+                for (;; st = (st + 1) & (T - 1)) {
+                    const int k = keys[st];
+                    if (k == t) { vt = vals[st]; break; }
+                    if (k == kEmpty) break;
+                }
+                words[i] = vj;
+                keys[sj] = j;                           // sj is j's slot, or the first empty one
+                vals[sj] = vt;
+            }
+        }
+        __syncwarp();
+    } else if (hp.sample_mode == DMDQN_SAMPLE_REPLACEMENT) {
+        for (int i = lane; i < B; i += 32) words[i] = (int)__umulhi((unsigned)words[i], (unsigned)pop);
+        __syncwarp();
+    } else {                                            // explicit logical indices, clamped
+        for (int i = lane; i < B; i += 32) {
+            const int v = words[i];
+            words[i] = v < 0 ? 0 : (v >= pop ? (int)pop - 1 : v);
+        }
+        __syncwarp();
+    }
+
+    for (int i = lane; i < B; i += 32) {
+        const int logical = words[i];
+        const int agent = shared_net ? logical / size0 : g;
+        const int lj = shared_net ? logical % size0 : logical;
+        const long long nw = rp.n_written[agent];
+        const long long sz = nw < d.capacity ? nw : d.capacity;
+        const int slot = (int)((nw - sz + lj) % d.capacity);
+        const int row = agent * d.capacity + slot;
+        rows[(size_t)g * B + i] = row;
+        act_b[(size_t)g * B + i] = rp.act[row];
+        done_b[(size_t)g * B + i] = rp.done[row] ? 1.f : 0.f;
+        rs[i] = rp.rew[row];
+    }
+    __syncwarp();
+    if (hp.normalize_rewards) {                         // dqn_agent.py:66-69, float64
+        const double mean = __ddiv_rn(tree_sum(B, lane, [&](int i) { return rs[i]; }), (double)B);
+        const double var = __ddiv_rn(tree_sum(B, lane, [&](int i) {
+                                         const double dv = __dsub_rn(rs[i], mean);
+                                         return __dmul_rn(dv, dv);
+                                     }), (double)B);
+        const double denom = __dadd_rn(__dsqrt_rn(var), 1e-8);
+        for (int i = lane; i < B; i += 32)
+            r_hat[(size_t)g * B + i] = (float)__ddiv_rn(__dsub_rn(rs[i], mean), denom);
+    } else {
+        for (int i = lane; i < B; i += 32) r_hat[(size_t)g * B + i] = (float)rs[i];
+    }
+}
+
+// ---------------------------------------------------------------- gather ----------------
+// One warp per sampled transition: 2 x obs_stride floats in (whole 128-byte lines), dense out.
+__global__ void __launch_bounds__(128)
+gather_kernel(dmdqn_dims d, dmdqn_replay rp, const int32_t* __restrict__ rows, const float* __restrict__ r_hat,
+              const int32_t* __restrict__ act_b, const float* __restrict__ done_b,
+              const int32_t* __restrict__ active, float* __restrict__ states, int32_t* __restrict__ actions,
+              float* __restrict__ rewards, float* __restrict__ next_states, float* __restrict__ dones,
+              int32_t* __restrict__ active_out) {
+    const int lane = threadIdx.x & 31;
+    const long long r = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const long long total = (long long)d.n_nets * d.batch;
+    if (r >= total) return;
+    const int g = (int)(r / d.batch);
+    if (active_out && (r % d.batch) == 0 && lane == 0) active_out[g] = active[g];
+    if (!active[g]) return;
+    const size_t src = (size_t)rows[r] * d.obs_stride;
+    for (int c = lane; c < d.obs_dim; c += 32) {
+        states[r * d.obs_dim + c] = rp.obs[src + c];
+        next_states[r * d.obs_dim + c] = rp.next_obs[src + c];
+    }
+    if (lane == 0) {
+        actions[r] = act_b[r];
+        rewards[r] = r_hat[r];
+        dones[r] = done_b[r];
+    }
+}
+
+}  // namespace
+
+int launch_push(const dmdqn_dims& d, const dmdqn_replay& rp, const float* obs, const int32_t* act,
+                const double* rew, const float* next_obs, const uint8_t* done, int32_t in_stride,
+                const uint8_t* mask, cudaStream_t s) {
+    push_kernel<<<d.n_agents, 64, 0, s>>>(d, rp, obs, act, rew, next_obs, done, in_stride, mask);
+    DMDQN_CUDA(cudaGetLastError());
+    return DMDQN_OK;
+}
+
+int launch_sample(const dmdqn_dims& d, const dmdqn_hparams& hp, const dmdqn_replay& rp, const dmdqn_nets& nets,
+                  const void* draws, const uint8_t* learn_mask, int advance, char* ws, const Workspace& w,
+                  cudaStream_t s) {
+    int log2t = 1;
+    while ((1 << log2t) < 2 * d.batch) ++log2t;
+    const size_t smem = (size_t)(2 << log2t) * 4 + (size_t)((d.batch + 1) & ~1) * 4 + (size_t)d.batch * 8;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        DMDQN_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    sample_kernel<<<d.n_nets, 32, smem, s>>>(
+        d, hp, rp, nets.learn_step, static_cast<const uint32_t*>(draws), learn_mask, advance,
+        reinterpret_cast<int32_t*>(ws + w.rows), reinterpret_cast<float*>(ws + w.r_hat),
+        reinterpret_cast<int32_t*>(ws + w.act_b), reinterpret_cast<float*>(ws + w.done_b),
+        reinterpret_cast<int32_t*>(ws + w.active), reinterpret_cast<int32_t*>(ws + w.step_t), log2t);
+    DMDQN_CUDA(cudaGetLastError());
+    return DMDQN_OK;
+}
+
+int launch_gather(const dmdqn_dims& d, const dmdqn_replay& rp, const char* ws, const Workspace& w,
+                  float* states, int32_t* actions, float* rewards, float* next_states, float* dones,
+                  int32_t* active_out, cudaStream_t s) {
+    const long long total = (long long)d.n_nets * d.batch;
+    gather_kernel<<<(unsigned)((total + 3) / 4), 128, 0, s>>>(
+        d, rp, reinterpret_cast<const int32_t*>(ws + w.rows), reinterpret_cast<const float*>(ws + w.r_hat),
+        reinterpret_cast<const int32_t*>(ws + w.act_b), reinterpret_cast<const float*>(ws + w.done_b),
+        reinterpret_cast<const int32_t*>(ws + w.active), states, actions, rewards, next_states, dones,
+        active_out);
+    DMDQN_CUDA(cudaGetLastError());
+    return DMDQN_OK;
+}
+
+}  // namespace dmdqn

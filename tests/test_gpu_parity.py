@@ -1,0 +1,400 @@
+"""GPU parity: the CUDA path (through the C ABI, via AgentGroup) against the CPU oracle.
+
+Bit-exact for indices, gathered transitions, rewards (fp64), z-scores and greedy actions;
+<= 1e-5 relative (tolerance written at each assert) for fp32 Q-values, TD targets, losses,
+post-Adam weights and Adam moments.  Run on the B200 box:  pytest -m gpu
+"""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+RTOL = 1e-5          # BASELINE.json: "within 1e-5 relative for fp32 Q-values, losses and post-Adam weights"
+
+
+def _group(*a, **k):
+    from dmdqn_b200.group import AgentGroup
+    return AgentGroup(*a, **k)
+
+
+def close(got, ref, rtol=RTOL, scale=None, what=""):
+    """|got-ref| <= rtol * max(|ref| elementwise, typical magnitude of the tensor)."""
+    got = np.asarray(got, np.float64)
+    ref = np.asarray(ref, np.float64)
+    mag = float(np.abs(ref).max()) if scale is None else scale
+    tol = rtol * np.maximum(np.abs(ref), mag if mag > 0 else 1.0)
+    bad = np.abs(got - ref) > tol
+    assert not bad.any(), f"{what}: {bad.sum()} / {bad.size} off, worst {np.abs(got - ref).max():.3e} (mag {mag:.3e})"
+
+
+# ------------------------------------------------------------------ K0 featurise ------------
+@pytest.mark.parametrize("tag", ["shipped", "live"])
+def test_featurize_matches_reference_fixture(tag):
+    from oracle import featurize as F
+    z = np.load(os.path.join(G, "ref_featurize.npz"))
+    grp = _group(16, {"nn_layers": [64, 64], "replay_buffer_size": 8, "batch_size": 4})
+    nbr = F.grid_neighbors(4, 4)
+    for c in range(z[f"{tag}_halting"].shape[0]):
+        obs, own, rew, glob = grp.featurize(z[f"{tag}_halting"][c], z[f"{tag}_phase"][c], z[f"{tag}_next_switch"][c],
+                                            z[f"{tag}_phase_dur"][c], float(z[f"{tag}_sim_time"][c]),
+                                            z[f"{tag}_signal_valid"], nbr)
+        assert np.array_equal(own.cpu().numpy(), z[f"{tag}_own"][c])
+        assert np.array_equal(obs.cpu().numpy()[:, :89], z[f"{tag}_obs"][c].astype(np.float32))
+        assert np.all(obs.cpu().numpy()[:, 89:] == 0)
+        r_ref, g_ref = F.rewards(z[f"{tag}_own"][c])
+        assert np.array_equal(rew.cpu().numpy(), r_ref) and float(glob.item()) == g_ref
+
+
+@pytest.mark.parametrize("tag", ["shipped", "live"])
+def test_featurize_reproduces_reference_train_loop_trace(tag):
+    z = np.load(os.path.join(G, f"ref_episode_{tag}.npz"))
+    from oracle import featurize as F
+    nbr = F.grid_neighbors(3, 3)
+    grp = _group(9, {"nn_layers": [64, 64], "replay_buffer_size": 8, "batch_size": 4})
+    t_steps = z["s"].shape[1]
+    for t in range(t_steps + 1):
+        obs, own, rew, _ = grp.featurize(z["halting"][t], z["phase"][t], z["next_switch"][t], z["phase_dur"][t],
+                                         float(z["sim_time"][t]), z["signal_valid"], nbr)
+        o = obs.cpu().numpy()[:, :89]
+        if t < t_steps:
+            assert np.array_equal(o, z["s"][:, t]) and np.array_equal(rew.cpu().numpy(), z["r"][:, t])
+        if t > 0:
+            assert np.array_equal(o, z["s2"][:, t - 1])
+
+
+def test_featurize_large_grid_and_snapshot():
+    from oracle import featurize as F
+    rng = np.random.default_rng(0)
+    rows = cols = 64
+    n = rows * cols
+    grp = _group(n, {"nn_layers": [64, 64], "replay_buffer_size": 2, "batch_size": 1})
+    nbr = F.grid_neighbors(rows, cols)
+    halting = rng.integers(-1, 30, (n, 12)).astype(np.int32)
+    phase = rng.integers(0, 12, n).astype(np.int32)
+    nsw = rng.uniform(0, 100, n); dur = rng.uniform(5, 60, n); valid = (rng.random(n) < 0.7).astype(np.uint8)
+    own_ref = F.own_state(halting, phase, nsw, dur, 41.5, valid)
+    snap = own_ref + 1.0
+    for snapshot in (None, snap):
+        obs, own, rew, glob = grp.featurize(halting, phase, nsw, dur, 41.5, valid, nbr, snapshot=snapshot)
+        assert np.array_equal(own.cpu().numpy(), own_ref)
+        assert np.array_equal(obs.cpu().numpy()[:, :89], F.build_obs(own_ref, nbr, snapshot))
+        r_ref, g_ref = F.rewards(own_ref)
+        assert np.array_equal(rew.cpu().numpy(), r_ref) and float(glob.item()) == g_ref
+
+
+# ------------------------------------------------------------------ K1 replay ---------------
+def _fill(grp, ring, n_push, rng, d=89):
+    n = grp.n_agents
+    for t in range(n_push):
+        s = rng.integers(0, 20, (n, d)).astype(np.float32)
+        s[:, 0] = t
+        s2 = rng.integers(0, 20, (n, d)).astype(np.float32)
+        a = rng.integers(0, 4, n).astype(np.int32)
+        r = -0.3 * rng.integers(0, 200, n) - 0.7 * rng.integers(0, 5000, n)
+        dn = rng.random(n) < 0.05
+        grp.push(s, a, r, s2, dn)
+        ring.push(s, a, r, s2, dn)
+
+
+@pytest.mark.parametrize("cap,n_push,batch", [(50, 20, 16), (50, 50, 50), (37, 120, 32), (300, 1000, 256)])
+def test_push_sample_bit_exact_fisher_yates(cap, n_push, batch):
+    from oracle import replay as R
+    rng = np.random.default_rng(cap + n_push)
+    n = 5
+    grp = _group(n, {"nn_layers": [64, 64], "replay_buffer_size": cap, "batch_size": batch})
+    ring = R.RingReplay(n, cap, 89)
+    _fill(grp, ring, n_push, rng)
+    assert np.array_equal(grp.n_written.cpu().numpy(), ring.n_written)
+    assert np.array_equal(grp.obs.cpu().numpy()[:, :, :89], ring.obs)
+    assert np.array_equal(grp.rew_ring.cpu().numpy(), ring.rew)
+    assert np.all(grp.obs.cpu().numpy()[:, :, 89:] == 0)
+    words = rng.integers(0, 2**32, (n, batch), dtype=np.uint64).astype(np.uint32)
+    s, a, r, s2, d, active = grp.sample(words, sample_mode="fisher_yates")
+    size = min(n_push, cap)
+    assert active.cpu().numpy().tolist() == [int(size >= batch)] * n
+    if size < batch:
+        return
+    rows = grp.debug_views()["rows"].cpu().numpy()
+    for i in range(n):
+        idx = R.fisher_yates_indices(words[i], size)
+        assert len(set(idx.tolist())) == batch                        # without replacement
+        assert np.array_equal(rows[i], i * cap + ring.logical_to_slot(i, idx))
+        es, ea, er, es2, ed = ring.gather(i, idx, canonical=True)
+        assert np.array_equal(s[i].cpu().numpy(), es) and np.array_equal(s2[i].cpu().numpy(), es2)
+        assert np.array_equal(a[i].cpu().numpy(), ea) and np.array_equal(d[i].cpu().numpy(), ed)
+        assert np.array_equal(r[i].cpu().numpy(), er)                  # fp64 z-score, same tree: bit-exact
+        np.testing.assert_allclose(r[i].cpu().numpy(), ring.gather(i, idx, canonical=False)[2], rtol=0, atol=1e-6)
+
+
+def test_sample_modes_replacement_and_constant_rewards():
+    from oracle import replay as R
+    rng = np.random.default_rng(9)
+    n, cap, batch = 3, 64, 32
+    grp = _group(n, {"nn_layers": [64, 64], "replay_buffer_size": cap, "batch_size": batch})
+    ring = R.RingReplay(n, cap, 89)
+    for t in range(100):
+        s = rng.random((n, 89)).astype(np.float32)
+        grp.push(s, np.zeros(n), np.full(n, -12.5), s, np.zeros(n))
+        ring.push(s, np.zeros(n, np.int32), np.full(n, -12.5), s, np.zeros(n))
+    words = rng.integers(0, 2**32, (n, batch), dtype=np.uint64).astype(np.uint32)
+    s, a, r, s2, d, _ = grp.sample(words, sample_mode="replacement")
+    assert np.all(r.cpu().numpy() == 0)                                # std == 0 -> r_hat == 0
+    for i in range(n):
+        idx = R.replacement_indices(words[i], cap)
+        assert np.array_equal(s[i].cpu().numpy(), ring.gather(i, idx)[0])
+
+
+@pytest.mark.parametrize("tag", ["pool", "set", "wrap", "exact", "short", "const"])
+def test_facade_replay_buffer_matches_reference_fixture(tag):
+    """ReplayBuffer facade under random.seed == the reference's own add/sample outputs."""
+    from dmdqn_b200.agent import ReplayBuffer
+    z = np.load(os.path.join(G, "ref_replay.npz"))
+    cap, n_add, batch, seed = (int(x) for x in z[f"{tag}_meta"])
+    buf = ReplayBuffer(cap, batch_size=batch)
+    s = z[f"{tag}_in_s"].astype(np.float32); s2 = z[f"{tag}_in_s2"].astype(np.float32)
+    for i in range(n_add):
+        buf.add((s[i][None], int(z[f"{tag}_in_a"][i]), float(z[f"{tag}_in_r"][i]), s2[i][None], bool(z[f"{tag}_in_d"][i])))
+    assert len(buf) == int(z[f"{tag}_len"])
+    random.seed(seed)
+    out = buf.sample(batch)
+    if f"{tag}_none" in z:
+        assert out is None
+        return
+    got = [t.cpu().numpy() for t in out]
+    for name, arr in zip(("s", "a", "r", "s2", "d"), got):
+        ref = z[f"{tag}_out_{name}"]
+        if name == "r":
+            np.testing.assert_allclose(arr, ref, rtol=0, atol=1e-6)    # numpy's pairwise order vs fixed tree
+        else:
+            assert arr.dtype == ref.dtype and np.array_equal(arr, ref), name
+
+
+# ------------------------------------------------------------------ K2 act ------------------
+def _load_oracle_weights(grp, stk):
+    for i in range(grp.n_nets):
+        grp.set_weights(i, [p[i] for p in stk.online], "online")
+        grp.set_weights(i, [p[i] for p in stk.target], "target")
+
+
+@pytest.mark.parametrize("h,n", [(64, 7), (128, 16), (256, 256), (512, 5)])
+def test_act_q_values_and_greedy_actions(h, n):
+    from oracle.dqn import StackedOracle
+    from oracle.replay import explore_decision, random_action
+    rng = np.random.default_rng(h + n)
+    stk = StackedOracle(n, 89, [h, h], 4, seed0=10)
+    for k in (1, 3, 5):
+        stk.online[k] += torch.as_tensor(rng.standard_normal(stk.online[k].shape).astype(np.float32)) * 0.1
+    grp = _group(n, {"nn_layers": [h, h], "replay_buffer_size": 4, "batch_size": 2})
+    _load_oracle_weights(grp, stk)
+    obs = rng.integers(-1, 20, (n, 89)).astype(np.float32)
+    q_ref = stk.q_values(obs).numpy()
+    actions, q = grp.act(obs, return_q=True)
+    close(q.cpu().numpy(), q_ref, what="Q(s)")
+    top2 = np.sort(q_ref, axis=1)[:, -2:]
+    gap_ok = (top2[:, 1] - top2[:, 0]) > 1e-4 * np.abs(q_ref).max()
+    assert gap_ok.mean() > 0.95                                        # near-ties are the rare exception
+    assert np.array_equal(actions.cpu().numpy()[gap_ok], q_ref.argmax(1)[gap_ok])
+    # epsilon mask with supplied draws: bit-exact decisions and random actions
+    eps = rng.choice([0.0, 0.3, 1.0], n)
+    w1 = rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32)
+    w2 = rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32)
+    a2, q2 = grp.act(obs, eps, w1, w2, return_q=True)
+    ex = explore_decision(w1, eps)
+    a2 = a2.cpu().numpy()
+    assert np.array_equal(a2[ex], random_action(w2, 4)[ex])
+    assert np.array_equal(a2[~ex & gap_ok], q_ref.argmax(1)[~ex & gap_ok])
+    assert np.isnan(q2.cpu().numpy()[ex]).all()                        # no forward pass when exploring
+    assert (eps == 1.0).sum() == 0 or ex[eps == 1.0].all()
+
+
+def test_act_argmax_tie_picks_lowest_index():
+    grp = _group(2, {"nn_layers": [64, 64], "replay_buffer_size": 4, "batch_size": 2})
+    zero = [np.zeros((89, 64)), np.zeros(64), np.zeros((64, 64)), np.zeros(64), np.zeros((64, 4)), np.array([0.5, 0.7, 0.7, 0.1])]
+    grp.set_weights(0, zero); grp.set_weights(1, zero[:5] + [np.array([0.2, 0.2, 0.2, 0.2])])
+    a = grp.act(np.ones((2, 89), np.float32)).cpu().numpy()
+    assert a.tolist() == [1, 0]
+
+
+# ------------------------------------------------------------------ K3/K4 learn -------------
+def _learn_case(h, n, batch, cap, steps, loss="mse", tau=None, freq=3, double_dqn=True, adam_form="keras", seed=0):
+    from oracle import replay as R
+    from oracle.dqn import StackedOracle
+    rng = np.random.default_rng(seed + h + batch)
+    cfg = {"nn_layers": [h, h], "replay_buffer_size": cap, "batch_size": batch, "learning_rate": 5e-4,
+           "gamma": 0.99, "target_update_frequency": freq, "loss": loss, "tau": tau, "double_dqn": double_dqn,
+           "adam_form": adam_form}
+    grp = _group(n, cfg)
+    stk = StackedOracle(n, 89, [h, h], 4, gamma=0.99, learning_rate=5e-4, loss=loss, tau=tau,
+                        target_update_frequency=freq, double_dqn=double_dqn, adam_form=adam_form, seed0=50)
+    for k in (1, 3, 5):   # non-zero biases so every term of the backward pass is exercised
+        stk.online[k] += torch.as_tensor(rng.standard_normal(stk.online[k].shape).astype(np.float32)) * 0.05
+        stk.target[k].copy_(stk.online[k])
+    _load_oracle_weights(grp, stk)
+    ring = R.RingReplay(n, cap, 89)
+    for t in range(cap + 7):
+        s = rng.integers(-1, 20, (n, 89)).astype(np.float32)
+        s2 = rng.integers(-1, 20, (n, 89)).astype(np.float32)
+        a = rng.integers(0, 4, n).astype(np.int32)
+        r = -0.3 * rng.integers(0, 200, n) - 0.7 * rng.integers(0, 5000, n)
+        dn = rng.random(n) < 0.1
+        grp.push(s, a, r, s2, dn); ring.push(s, a, r, s2, dn)
+    for step in range(steps):
+        words = rng.integers(0, 2**32, (n, batch), dtype=np.uint64).astype(np.uint32)
+        metrics = grp.learn(words, sample_mode="fisher_yates").cpu().numpy()
+        dbg = {k: v.cpu().numpy() for k, v in grp.debug_views().items()}
+        batches = [ring.gather(i, R.fisher_yates_indices(words[i], cap)) for i in range(n)]
+        S, A_, Rw, S2, D = (np.stack([b[k] for b in batches]) for k in range(5))
+        assert np.array_equal(dbg["r_hat"], Rw)
+        out = stk.learn_on_batch(S, A_, Rw, S2, D)
+        # a near-tie in argmax_a online(s') may legitimately flip: exclude those rows (counted)
+        qn = np.sort(out["q_next"], axis=2)
+        tie = (qn[..., -1] - qn[..., -2]) < 1e-5 * np.abs(out["q_next"]).max()
+        assert tie.mean() < 0.01
+        close(dbg["q_next"], out["q_next"], what=f"step {step} online Q(s')")
+        close(dbg["tq_all"], out["tq_all"], what=f"step {step} target Q(s')")
+        close(dbg["q_all"], out["q_all"], what=f"step {step} online Q(s)")
+        close(dbg["y"][~tie], out["y"][~tie], what=f"step {step} TD target")
+        if not tie.any():
+            close(metrics[:, 0], out["loss"], what=f"step {step} loss")
+            q_mean = out["q_all"].reshape(n, -1).mean(1); q_std = out["q_all"].reshape(n, -1).std(1)
+            close(metrics[:, 1], q_mean, rtol=1e-4, what="q_mean"); close(metrics[:, 2], q_std, rtol=1e-4, what="q_std")
+            hist = np.stack([np.bincount(A_[i], minlength=4) for i in range(n)])
+            assert np.array_equal(metrics[:, 3:7], hist) and np.all(metrics[:, 7] == 1)
+            for i in range(n):
+                got = grp.get_weights(i, "online"); gm = grp.get_weights(i, "m"); gv = grp.get_weights(i, "v")
+                gt = grp.get_weights(i, "target")
+                for k in range(6):
+                    close(got[k].numpy(), stk.online[k][i].numpy(), what=f"step {step} net {i} theta[{k}]")
+                    close(gt[k].numpy(), stk.target[k][i].numpy(), what=f"step {step} net {i} theta_tgt[{k}]")
+                    close(gm[k].numpy(), stk.adam_m[k][i].numpy(), rtol=1e-4, what=f"step {step} net {i} adam_m[{k}]")
+                    close(gv[k].numpy(), stk.adam_v[k][i].numpy(), rtol=1e-4, what=f"step {step} net {i} adam_v[{k}]")
+        else:   # keep the two trajectories together after a flipped tie
+            _load_oracle_weights(grp, stk)
+            for i in range(n):
+                grp.set_weights(i, [p[i] for p in stk.adam_m], "m"); grp.set_weights(i, [p[i] for p in stk.adam_v], "v")
+    assert np.array_equal(grp.learn_step.cpu().numpy(), stk.learn_step)
+    assert np.array_equal(grp.learn_step_host, stk.learn_step)
+    # pad rows of W1 (obs columns 89..95) never move
+    L = grp.layout
+    w1 = grp.theta[:, L.w1:L.w1 + grp.obs_stride * h].view(n, grp.obs_stride, h)
+    assert torch.all(w1[:, 89:] == 0)
+
+
+@pytest.mark.parametrize("h,n,batch,cap", [(64, 3, 32, 64), (64, 2, 48, 100), (128, 3, 64, 128), (256, 4, 64, 128),
+                                           (256, 2, 100, 200), (256, 2, 256, 300), (512, 2, 64, 100)])
+def test_learn_matches_oracle_mse_hard_sync(h, n, batch, cap):
+    _learn_case(h, n, batch, cap, steps=7)
+
+
+def test_learn_matches_oracle_huber_polyak():
+    _learn_case(128, 3, 64, 128, steps=5, loss="huber", tau=0.01)
+
+
+def test_learn_matches_oracle_vanilla_target_torch_adam():
+    _learn_case(64, 3, 32, 64, steps=5, double_dqn=False, adam_form="torch")
+
+
+def test_learn_skips_short_buffers_and_masked_agents():
+    n, batch = 4, 16
+    grp = _group(n, {"nn_layers": [64, 64], "replay_buffer_size": 64, "batch_size": batch})
+    rng = np.random.default_rng(0)
+    theta0 = grp.theta.clone()
+    for t in range(batch - 1):
+        s = rng.random((n, 89)).astype(np.float32)
+        grp.push(s, np.zeros(n), -rng.random(n), s, np.zeros(n))
+    m = grp.learn().cpu().numpy()                      # len < batch: learn() is a no-op (dqn_agent.py:333-335)
+    assert np.all(m == 0) and torch.equal(grp.theta, theta0) and grp.learn_step.sum().item() == 0
+    s = rng.random((n, 89)).astype(np.float32)
+    grp.push(s, np.zeros(n), -rng.random(n), s, np.zeros(n), mask=[1, 1, 0, 1])   # agent 2 stays short
+    m = grp.learn(mask=[1, 0, 1, 1]).cpu().numpy()
+    assert m[:, 7].tolist() == [1, 0, 0, 1]
+    assert grp.learn_step.cpu().numpy().tolist() == [1, 0, 0, 1] and grp.learn_step_host.tolist() == [1, 0, 0, 1]
+    changed = [not torch.equal(grp.theta[i], theta0[i]) for i in range(n)]
+    assert changed == [True, False, False, True]
+
+
+def test_facade_agent_matches_oracle_agent_under_same_seeds():
+    """Drop-in DQNAgent vs the faithful oracle agent: same python-random stream -> same sampled
+    transitions; losses within 1e-5 (dqn_agent.py API, train.py:274-292 call pattern)."""
+    from dmdqn_b200.agent import DQNAgent
+    from oracle.dqn import OracleDQNAgent
+    cfg = {"nn_layers": [64, 64], "replay_buffer_size": 200, "batch_size": 32, "learning_rate": 1e-3,
+           "target_update_frequency": 5}
+    ag = DQNAgent(89, 4, "J_0_0", cfg)
+    orc = OracleDQNAgent(89, 4, "J_0_0", cfg, rng=None)
+    ag.online_network.set_weights([p.numpy() for p in orc.online]); ag.update_target_network()
+    rng = np.random.default_rng(1)
+    random.seed(123); st_a = random.getstate()
+    losses_a, losses_o = [], []
+    for t in range(60):
+        s = rng.integers(0, 20, (1, 89)).astype(np.float32); s2 = rng.integers(0, 20, (1, 89)).astype(np.float32)
+        a, r, d = int(rng.integers(0, 4)), float(-rng.integers(0, 300)) * 0.7, bool(t % 17 == 0)
+        ag.remember(s, a, r, s2, d); orc.remember(s, a, r, s2, d)
+        random.setstate(st_a); la = ag.replay(); st_after = random.getstate()
+        random.setstate(st_a); lo = orc.replay(); st_a = st_after
+        losses_a.append(float(la)); losses_o.append(float(lo))
+    assert losses_a[:31] == [0] * 31 and losses_o[:31] == [0] * 31    # replay() -> 0 while short (:431-432)
+    close(np.array(losses_a[31:]), np.array(losses_o[31:]), rtol=5e-5, what="facade losses")
+    assert ag.learn_step_counter == orc.learn_step_counter == 29
+    q = ag.online_network(s).cpu().numpy(); close(q, orc.q_values(s).numpy(), rtol=1e-4, what="facade Q")
+    assert ag.select_greedy_action(s) == int(np.argmax(q))
+    np.random.seed(0); ag.global_step_count = 0
+    np.random.seed(0); u = np.random.rand(); expect = np.random.randint(0, 4)
+    np.random.seed(0)
+    assert ag.select_action(s) == expect and ag.get_epsilon() == 1.0 and u < 1.0
+
+
+# ------------------------------------------------------------------ full-size properties ----
+def test_cfg3_full_size_properties():
+    """BASELINE cfg3 (256 agents, B=256, H=256, C=30000): size-independent properties plus
+    an oracle spot check of 3 agents."""
+    from oracle import replay as R
+    from oracle.dqn import StackedOracle
+    n, b, h, cap = 256, 256, 256, 30000
+    grp = _group(n, {"nn_layers": [h, h], "replay_buffer_size": cap, "batch_size": b, "learning_rate": 5e-4,
+                     "target_update_frequency": 1000})
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    grp.obs[:, :, :89] = torch.randint(0, 20, (n, cap, 89), device="cuda", generator=gen).float()
+    grp.next_obs[:, :, :89] = torch.randint(0, 20, (n, cap, 89), device="cuda", generator=gen).float()
+    grp.act_ring.copy_(torch.randint(0, 4, (n, cap), device="cuda", generator=gen).int())
+    grp.rew_ring.copy_(-torch.randint(0, 5000, (n, cap), device="cuda", generator=gen).double() * 0.7)
+    grp.done_ring.copy_((torch.rand((n, cap), device="cuda", generator=gen) < 1 / 240).to(torch.uint8))
+    grp.n_written.fill_(cap + 12345); grp.n_written_host[:] = cap + 12345
+    theta0 = grp.theta.clone()
+    words = grp.draw_words((n, b))
+    m = grp.learn(words).cpu().numpy()
+    dbg = grp.debug_views()
+    rows = dbg["rows"].cpu().numpy()
+    assert np.all(rows // cap == np.arange(n)[:, None])                 # every agent samples its own ring
+    assert all(len(set(r.tolist())) == b for r in rows)                 # distinct (no replacement)
+    assert np.isfinite(m).all() and np.all(m[:, 7] == 1) and np.all(m[:, 3:7].sum(1) == b)
+    r_hat = dbg["r_hat"].cpu().numpy().astype(np.float64)
+    assert np.abs(r_hat.mean(1)).max() < 1e-6 and np.abs(r_hat.std(1) - 1).max() < 1e-5   # z-score
+    assert not torch.equal(grp.theta, theta0) and torch.equal(grp.theta_tgt, theta0)
+    w = words.cpu().numpy().view(np.uint32)
+    stk = StackedOracle(3, 89, [h, h], 4, learning_rate=5e-4, seed0=0)
+    picks = [0, 117, 255]
+    L = grp.layout
+    for j, i in enumerate(picks):
+        ws = grp.unpack(theta0[i])
+        for k in range(6):
+            stk.online[k][j].copy_(ws[k]); stk.target[k][j].copy_(ws[k])
+    batches = []
+    for i in picks:
+        idx = R.fisher_yates_indices(w[i], cap)
+        slot = R.ring_physical(cap + 12345, cap, idx)
+        assert np.array_equal(rows[i], i * cap + slot)
+        rr = R.zscore_canonical(grp.rew_ring[i].cpu().numpy()[slot]).astype(np.float32)
+        batches.append((grp.obs[i].cpu().numpy()[slot][:, :89], grp.act_ring[i].cpu().numpy()[slot], rr,
+                        grp.next_obs[i].cpu().numpy()[slot][:, :89], grp.done_ring[i].cpu().numpy()[slot].astype(np.float32)))
+    out = stk.learn_on_batch(*(np.stack([bt[k] for bt in batches]) for k in range(5)))
+    close(m[picks, 0], out["loss"], what="cfg3 loss")
+    for j, i in enumerate(picks):
+        got = grp.get_weights(i)
+        for k in range(6):
+            close(got[k].numpy(), stk.online[k][j].numpy(), what=f"cfg3 agent {i} theta[{k}]")

@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- agent-updates/s of the Double-DQN learn step (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg3]
+
+A "step" is one learn sweep: every agent of the workload runs one ``learn()`` (sample B
+transitions from its ring, target + online forward, backward, Adam, target sync).
+Workloads (BASELINE.json configs; synthetic replay, observation-shaped integers, rings full):
+  cfg2  16 agents,  B=64,  H=256      cfg3  256 agents, B=256, H=256  (default, per GPU)
+  cfg4  512 agents, B=512, H=256 per GPU (4096 over 8 GPUs)
+N>1 shards agents across ranks with no collective (independent networks): weak scaling,
+every rank holds the per-GPU workload.  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import random
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "cfg2": dict(agents=16, batch=64, hidden=256, capacity=30000, grid="4x4"),
+    "cfg3": dict(agents=256, batch=256, hidden=256, capacity=30000, grid="16x16"),
+    "cfg4": dict(agents=512, batch=512, hidden=256, capacity=30000, grid="64x64 city grid / 8 GPUs"),
+}
+D, A = 89, 4
+
+
+def agent_cfg(w):
+    return {"learning_rate": 5e-4, "gamma": 0.99, "replay_buffer_size": w["capacity"], "batch_size": w["batch"],
+            "target_update_frequency": 1000, "nn_layers": [w["hidden"], w["hidden"]]}   # config/agent_config.yaml
+
+
+def flops_bytes(w):
+    """Algorithmic work per agent-update (SURVEY.md section 8 D-roofline)."""
+    b, h = w["batch"], w["hidden"]
+    m = D * h + h * h + h * A
+    p = m + h + h + A
+    k = {"target": dict(flops=2 * 2 * b * m, bytes=b * (D + 2) * 4 + 8 * p),
+         "online": dict(flops=2 * b * m + 2 * b * (h * h + h * A), bytes=b * (D + 1) * 4 + 4 * p),
+         "wgrad_adam": dict(flops=2 * b * m, bytes=12 * p),
+         "sample": dict(flops=0, bytes=b * 13 + b * 16)}
+    return {"flops": 2 * b * (4 * m + h * h + h * A), "bytes": b * (2 * D + 3) * 4 + 24 * p, "params": p, "kernels": k}
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons every 200 ms while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        import subprocess
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(r[0]) for r in self.rows]
+        reasons = [n for i, n in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), 3)
+                   if any(r[i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(self.rows[0][1]), "samples": len(sm),
+                "power_w_max": max(float(r[2]) for r in self.rows), "reasons": reasons}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return {"hbm_gbs": j["hbm_gbs"], "bf16_tflops": j["bf16_tflops"], "bf16_tflops_sustained": j["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------
+def synth_fill(grp, seed):
+    """Full rings of featuriser-shaped data: queue counts 0..19 as floats, -1 padding,
+    rewards 0.3*local + 0.7*global (float64), dones ~ 1/240 (SURVEY.md D-inputs)."""
+    n, c = grp.n_agents, grp.capacity
+    gen = torch.Generator(device=grp.device).manual_seed(seed)
+    chunk = max(1, (1 << 28) // (c * D))
+    for a0 in range(0, n, chunk):
+        a1 = min(n, a0 + chunk)
+        for ring in (grp.obs, grp.next_obs):
+            v = torch.randint(-1, 20, (a1 - a0, c, D), device=grp.device, generator=gen).float()
+            ring[a0:a1, :, :D] = v
+    grp.act_ring.copy_(torch.randint(0, A, (n, c), device=grp.device, generator=gen).int())
+    loc = torch.randint(0, 240, (n, c), device=grp.device, generator=gen).double()
+    glob = torch.randint(0, 240 * 256, (1, c), device=grp.device, generator=gen).double()
+    grp.rew_ring.copy_(-0.3 * loc - 0.7 * glob)
+    grp.done_ring.copy_((torch.rand((n, c), device=grp.device, generator=gen) < 1 / 240).to(torch.uint8))
+    grp.n_written.fill_(c + 777)
+    grp.n_written_host[:] = c + 777
+
+
+def run_ours(args):
+    from dmdqn_b200 import _native as N
+    from dmdqn_b200.group import AgentGroup
+    import ctypes as C
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    w = WORKLOADS[args.workload]
+    fb = flops_bytes(w)
+    grp = AgentGroup(w["agents"], agent_cfg(w), D, A, seed=1000 * rank)
+    synth_fill(grp, seed=rank)
+    n, b = grp.n_agents, grp.batch_size
+    K, W = args.steps, args.warmup
+    draws = grp.draw_words((K + W, n, b))
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput: K learn sweeps, inputs already in HBM ----------------
+    for i in range(W):
+        grp.learn(draws[i])
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(K):
+        grp.learn(draws[W + i])
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+
+    # ---- per-kernel durations: same sweep, one stage per call, events in between ----------
+    stage_names = ["sample", "target", "online", "wgrad_adam"]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(K)]
+    lib = grp.lib
+    for i in range(K):
+        d = draws[W + i]
+        for s in range(4):
+            evs[i][s].record(stream)
+            N.check(lib.dmdqn_learn_stages(C.byref(grp.dims), C.byref(grp.hp), C.byref(grp.replay), C.byref(grp.nets),
+                                           d.data_ptr(), None, grp.metrics.data_ptr(), grp.workspace.data_ptr(),
+                                           grp.workspace.numel(), 1 << s, stream.cuda_stream))
+        evs[i][4].record(stream)
+    torch.cuda.synchronize()
+    grp.learn_step_host += K
+    stage_ms = {nm: statistics.mean(evs[i][s].elapsed_time(evs[i][s + 1]) for i in range(K)) for s, nm in enumerate(stage_names)}
+
+    # ---- end to end: host transitions + draws in, losses out, every step ------------------
+    pin = lambda t: t.pin_memory()
+    h_obs, h_next = pin(torch.randint(0, 20, (n, D)).float()), pin(torch.randint(0, 20, (n, D)).float())
+    h_act, h_rew = pin(torch.randint(0, A, (n,), dtype=torch.int32)), pin(-torch.rand(n, dtype=torch.float64) * 100)
+    h_done = pin(torch.zeros(n, dtype=torch.uint8))
+    h_draws = pin(torch.randint(0, 2**31, (n, b), dtype=torch.int32))
+    h_metrics = pin(torch.empty((n, N.METRICS_STRIDE), dtype=torch.float32))
+    d_obs, d_next = torch.empty((n, D), device=grp.device), torch.empty((n, D), device=grp.device)
+    d_act = torch.empty(n, dtype=torch.int32, device=grp.device); d_rew = torch.empty(n, dtype=torch.float64, device=grp.device)
+    d_done = torch.empty(n, dtype=torch.uint8, device=grp.device); d_draws = torch.empty((n, b), dtype=torch.int32, device=grp.device)
+    h2d = sum(t.numel() * t.element_size() for t in (h_obs, h_next, h_act, h_rew, h_done, h_draws))
+    d2h = h_metrics.numel() * h_metrics.element_size()
+
+    def e2e_step():
+        for dst, src in ((d_obs, h_obs), (d_next, h_next), (d_act, h_act), (d_rew, h_rew), (d_done, h_done), (d_draws, h_draws)):
+            dst.copy_(src, non_blocking=True)
+        grp.push(d_obs, d_act, d_rew, d_next, d_done)          # remember (train.py:275)
+        m = grp.learn(d_draws)                                 # replay   (train.py:282)
+        h_metrics.copy_(m, non_blocking=True)
+        stream.synchronize()                                   # the caller reads the losses
+        return float(h_metrics[0, 0])
+    for _ in range(W):
+        e2e_step()
+    barrier()
+    e0.record(stream)
+    for _ in range(K):
+        e2e_step()
+    e1.record(stream)
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=grp.device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    total_agents = n * world
+    value = total_agents * K / (ms / 1e3)
+    pk = peaks()
+    dom = max(("target", "online", "wgrad_adam"), key=lambda k_: stage_ms[k_])
+    kf = fb["kernels"][dom]
+    ach_tf = n * kf["flops"] / (stage_ms[dom] / 1e3) / 1e12
+    ffma_peak = 148 * 128 * 2 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e12
+    out = {
+        "metric": "agent-updates/sec", "value": value, "unit": "agent-updates/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic replay (observation-shaped integers, full rings), random-init weights",
+        "config": {"workload": f"{args.workload}: {w['agents']} agents/GPU ({w['grid']}), batch {w['batch']}, hidden "
+                               f"[{w['hidden']},{w['hidden']}], obs 89, actions 4, replay capacity {w['capacity']}, "
+                               f"independent networks, fp32 FFMA path",
+                   "agents_total": total_agents, "sharding": "agent ranges, no collectives" if world > 1 else "single GPU",
+                   "l2_policy": "working set (replay ring 5.9 GB, theta/m/v 368 MB, scratch 200 MB at cfg3) exceeds the 126 MB L2",
+                   "sample_mode": "fisher_yates (device draws)"},
+        "e2e": {"value": total_agents * K / (ms_e2e / 1e3), "unit": "agent-updates/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K,
+                "what": "pinned host transition+draws -> push -> learn -> losses to host, synchronised every step"},
+        "gpu_launches": 4 * K,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": dom, "achieved": ach_tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": ach_tf / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"],
+                     "note": "fp32 FFMA kernel (1e-5 parity path): fraction of the fp32 FFMA peak at the sampled clock = "
+                             f"{ach_tf / ffma_peak:.3f} of {ffma_peak:.1f} TFLOP/s"},
+        "kernels": {k_: {"ms": stage_ms[k_], "tflops": n * fb["kernels"][k_]["flops"] / (stage_ms[k_] / 1e3) / 1e12,
+                         "gbs": n * fb["kernels"][k_]["bytes"] / (stage_ms[k_] / 1e3) / 1e9} for k_ in stage_names},
+        "step": {"flops_per_agent_update": fb["flops"], "bytes_per_agent_update": fb["bytes"],
+                 "tflops": n * fb["flops"] / (ms / K / 1e3) / 1e12, "hbm_gbs_algorithmic": n * fb["bytes"] / (ms / K / 1e3) / 1e9,
+                 "hbm_frac": n * fb["bytes"] / (ms / K / 1e3) / 1e9 / pk["hbm_gbs"]},
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(w, budget_s=args.cpu_budget)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------
+def build_oracle_agents(w, n_agents, seed=0):
+    """Faithful per-agent oracle objects with full deque buffers (reference structure:
+    one DQNAgent per intersection, train.py:109-127)."""
+    from oracle.dqn import OracleDQNAgent
+    rng = np.random.default_rng(seed)
+    agents = []
+    c = w["capacity"]
+    for i in range(n_agents):
+        ag = OracleDQNAgent(D, A, f"J_{i}", dict(agent_cfg(w), seed=i))
+        s = rng.integers(-1, 20, (c, 1, D)).astype(np.float32); s2 = rng.integers(-1, 20, (c, 1, D)).astype(np.float32)
+        a = rng.integers(0, A, c); r = -0.3 * rng.integers(0, 240, c) - 0.7 * rng.integers(0, 240 * 256, c)
+        dn = rng.random(c) < 1 / 240
+        for t in range(c):
+            ag.replay_buffer.buffer.append((s[t, 0], int(a[t]), float(r[t]), s2[t, 0], bool(dn[t])))
+        agents.append(ag)
+    return agents
+
+
+def cpu_baseline(w, budget_s=15.0, sample_agents=None):
+    """The oracle's sequential per-agent learn loop (train.py:274-292 + dqn_agent.py:328-380)
+    on this box's host cores, bounded to ~budget_s of CPU work."""
+    sample_agents = sample_agents or min(w["agents"], 16)
+    random.seed(0)
+    agents = build_oracle_agents(w, sample_agents)
+    for ag in agents[:2]:
+        ag.replay()                                   # warm-up
+    t0 = time.perf_counter(); sweeps = 0
+    while True:
+        for ag in agents:
+            ag.replay()
+        sweeps += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or sweeps >= 200:
+            break
+    return {"value": sample_agents * sweeps / el, "unit": "agent-updates/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{sample_agents} of {w['agents']} agents (full {w['capacity']}-deep deque buffers), {sweeps} learn sweeps, "
+                      f"{el:.1f} s; sequential per-agent loop of the CPU PyTorch oracle (reference is TensorFlow: not installable)",
+            "host_cpus": os.cpu_count()}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; oracle/_ref does not exist because
+    TensorFlow/Keras cannot be installed) on the host cores, same workload/metric."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    sample_agents = min(w["agents"], 16)
+    random.seed(0)
+    agents = build_oracle_agents(w, sample_agents)
+    K, W = args.steps, args.warmup
+    for _ in range(min(W, 3)):
+        for ag in agents:
+            ag.replay()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        for ag in agents:
+            ag.replay()
+    el = time.perf_counter() - t0
+    v = sample_agents * K / el
+    sample = (f"each step = one learn sweep over {sample_agents} of {w['agents']} agents (full {w['capacity']}-deep deque buffers); "
+              "sequential per-agent loop")
+    print(json.dumps({
+        "impl": "reference", "metric": "agent-updates/sec", "value": v, "unit": "agent-updates/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": K, "warmup": W, "ms_per_step": el / K * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic replay",
+        "config": {"workload": f"{args.workload}: {w['agents']} agents ({w['grid']}), batch {w['batch']}, hidden "
+                               f"[{w['hidden']},{w['hidden']}], obs 89, actions 4, replay capacity {w['capacity']}"},
+        "cpu_baseline": {"value": v, "unit": "agent-updates/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "agent-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

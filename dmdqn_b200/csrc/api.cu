@@ -151,17 +151,26 @@ int dmdqn_gather(const dmdqn_dims* dims, const dmdqn_replay* replay, const void*
                          active_out, (cudaStream_t)stream);
 }
 
-int dmdqn_learn(const dmdqn_dims* dims, const dmdqn_hparams* hp, const dmdqn_replay* replay,
-                const dmdqn_nets* nets, const void* draws, const uint8_t* learn_mask, float* metrics_out,
-                void* workspace, size_t workspace_bytes, void* stream) {
+int dmdqn_learn_stages(const dmdqn_dims* dims, const dmdqn_hparams* hp, const dmdqn_replay* replay,
+                       const dmdqn_nets* nets, const void* draws, const uint8_t* learn_mask, float* metrics_out,
+                       void* workspace, size_t workspace_bytes, int32_t stages, void* stream) {
     Workspace w;
     int rc = check_workspace(dims, workspace, workspace_bytes, &w);
     if (rc) return rc;
     rc = check_learn_args(hp, replay, nets, draws);
     if (rc) return rc;
-    rc = launch_sample(*dims, *hp, *replay, *nets, draws, learn_mask, 1, (char*)workspace, w, (cudaStream_t)stream);
-    if (rc) return rc;
-    return launch_learn(*dims, *hp, *replay, *nets, metrics_out, (char*)workspace, w, (cudaStream_t)stream);
+    if (stages & DMDQN_STAGE_SAMPLE) {
+        rc = launch_sample(*dims, *hp, *replay, *nets, draws, learn_mask, 1, (char*)workspace, w, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return launch_learn(*dims, *hp, *replay, *nets, metrics_out, (char*)workspace, w, stages, (cudaStream_t)stream);
+}
+
+int dmdqn_learn(const dmdqn_dims* dims, const dmdqn_hparams* hp, const dmdqn_replay* replay,
+                const dmdqn_nets* nets, const void* draws, const uint8_t* learn_mask, float* metrics_out,
+                void* workspace, size_t workspace_bytes, void* stream) {
+    return dmdqn_learn_stages(dims, hp, replay, nets, draws, learn_mask, metrics_out, workspace, workspace_bytes,
+                              DMDQN_STAGE_SAMPLE | DMDQN_STAGE_TARGET | DMDQN_STAGE_ONLINE | DMDQN_STAGE_WGRAD, stream);
 }
 
 int dmdqn_debug(const dmdqn_dims* dims, void* workspace, size_t workspace_bytes, dmdqn_debug_views* out) {

@@ -616,7 +616,7 @@ __global__ void sync_target_kernel(int64_t stride, const float* __restrict__ the
 }
 
 template <int H>
-int launch_learn_h(const LearnArgs& A, cudaStream_t s) {
+int launch_learn_h(const LearnArgs& A, int stages, cudaStream_t s) {
     using T = Tile<H>;
     const size_t smem = Smem<H>::bytes(A.d.obs_stride);
     const size_t smem_w = sizeof(float) * 2 * T::KC * ((T::BM + 4) + T::LDW);
@@ -628,20 +628,26 @@ int launch_learn_h(const LearnArgs& A, cudaStream_t s) {
         configured = smem;
     }
     const int grid = A.d.n_nets * A.tiles;
-    target_kernel<H><<<grid, T::NT, smem, s>>>(A);
-    DMDQN_CUDA(cudaGetLastError());
-    online_kernel<H><<<grid, T::NT, smem, s>>>(A);
-    DMDQN_CUDA(cudaGetLastError());
-    const int per_net = H / T::BM + (A.d.obs_stride + T::BM - 1) / T::BM + 1;
-    wgrad_adam_kernel<H><<<A.d.n_nets * per_net, T::NT, smem_w, s>>>(A);
-    DMDQN_CUDA(cudaGetLastError());
+    if (stages & DMDQN_STAGE_TARGET) {
+        target_kernel<H><<<grid, T::NT, smem, s>>>(A);
+        DMDQN_CUDA(cudaGetLastError());
+    }
+    if (stages & DMDQN_STAGE_ONLINE) {
+        online_kernel<H><<<grid, T::NT, smem, s>>>(A);
+        DMDQN_CUDA(cudaGetLastError());
+    }
+    if (stages & DMDQN_STAGE_WGRAD) {
+        const int per_net = H / T::BM + (A.d.obs_stride + T::BM - 1) / T::BM + 1;
+        wgrad_adam_kernel<H><<<A.d.n_nets * per_net, T::NT, smem_w, s>>>(A);
+        DMDQN_CUDA(cudaGetLastError());
+    }
     return DMDQN_OK;
 }
 
 }  // namespace
 
 int launch_learn(const dmdqn_dims& d, const dmdqn_hparams& hp, const dmdqn_replay& rp, const dmdqn_nets& nets,
-                 float* metrics, char* ws, const Workspace& w, cudaStream_t s) {
+                 float* metrics, char* ws, const Workspace& w, int stages, cudaStream_t s) {
     LearnArgs A;
     A.d = d;
     A.L = make_layout(d.obs_stride, d.hidden);
@@ -674,10 +680,10 @@ int launch_learn(const dmdqn_dims& d, const dmdqn_hparams& hp, const dmdqn_repla
     A.part_b1 = reinterpret_cast<float*>(ws + w.part_b1);
     A.metrics = metrics;
     switch (d.hidden) {
-        case 64: return launch_learn_h<64>(A, s);
-        case 128: return launch_learn_h<128>(A, s);
-        case 256: return launch_learn_h<256>(A, s);
-        case 512: return launch_learn_h<512>(A, s);
+        case 64: return launch_learn_h<64>(A, stages, s);
+        case 128: return launch_learn_h<128>(A, stages, s);
+        case 256: return launch_learn_h<256>(A, stages, s);
+        case 512: return launch_learn_h<512>(A, stages, s);
     }
     set_error("unsupported hidden width %d", d.hidden);
     return DMDQN_ERR_ARG;

@@ -207,6 +207,17 @@ int dmdqn_learn(const dmdqn_dims* dims, const dmdqn_hparams* hp, const dmdqn_rep
                 const dmdqn_nets* nets, const void* draws, const uint8_t* learn_mask,
                 float* metrics_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same step, one stage per call, so a caller can bracket each kernel with CUDA events
+ * (bench.py roofline): stages is a bit mask of DMDQN_STAGE_*; all four in order == dmdqn_learn. */
+#define DMDQN_STAGE_SAMPLE 1   /* K1b */
+#define DMDQN_STAGE_TARGET 2   /* K3  */
+#define DMDQN_STAGE_ONLINE 4   /* K4a */
+#define DMDQN_STAGE_WGRAD  8   /* K4b */
+int dmdqn_learn_stages(const dmdqn_dims* dims, const dmdqn_hparams* hp, const dmdqn_replay* replay,
+                       const dmdqn_nets* nets, const void* draws, const uint8_t* learn_mask,
+                       float* metrics_out, void* workspace, size_t workspace_bytes, int32_t stages,
+                       void* stream);
+
 /* Debug / parity views into the workspace after dmdqn_learn (device pointers into it):
  * y[n_nets][B], q_all[n_nets][B][4] (online Q of s), q_next[n_nets][B][4] (online Q of s'),
  * tq_all[n_nets][B][4] (target Q of s'), rows int32[n_nets][B] (agent*C + slot). */

@@ -14,22 +14,12 @@ import torch
 pytestmark = pytest.mark.gpu
 
 G = os.path.join(os.path.dirname(__file__), "golden")
-RTOL = 1e-5          # BASELINE.json: "within 1e-5 relative for fp32 Q-values, losses and post-Adam weights"
+from parity_util import RTOL, adam_close, close  # noqa: E402
 
 
 def _group(*a, **k):
     from dmdqn_b200.group import AgentGroup
     return AgentGroup(*a, **k)
-
-
-def close(got, ref, rtol=RTOL, scale=None, what=""):
-    """|got-ref| <= rtol * max(|ref| elementwise, typical magnitude of the tensor)."""
-    got = np.asarray(got, np.float64)
-    ref = np.asarray(ref, np.float64)
-    mag = float(np.abs(ref).max()) if scale is None else scale
-    tol = rtol * np.maximum(np.abs(ref), mag if mag > 0 else 1.0)
-    bad = np.abs(got - ref) > tol
-    assert not bad.any(), f"{what}: {bad.sum()} / {bad.size} off, worst {np.abs(got - ref).max():.3e} (mag {mag:.3e})"
 
 
 # ------------------------------------------------------------------ K0 featurise ------------
@@ -223,7 +213,7 @@ def test_act_argmax_tie_picks_lowest_index():
 # ------------------------------------------------------------------ K3/K4 learn -------------
 def _learn_case(h, n, batch, cap, steps, loss="mse", tau=None, freq=3, double_dqn=True, adam_form="keras", seed=0):
     from oracle import replay as R
-    from oracle.dqn import StackedOracle
+    from oracle.dqn import StackedOracle, adam_scalars
     rng = np.random.default_rng(seed + h + batch)
     cfg = {"nn_layers": [h, h], "replay_buffer_size": cap, "batch_size": batch, "learning_rate": 5e-4,
            "gamma": 0.99, "target_update_frequency": freq, "loss": loss, "tau": tau, "double_dqn": double_dqn,
@@ -250,7 +240,11 @@ def _learn_case(h, n, batch, cap, steps, loss="mse", tau=None, freq=3, double_dq
         batches = [ring.gather(i, R.fisher_yates_indices(words[i], cap)) for i in range(n)]
         S, A_, Rw, S2, D = (np.stack([b[k] for b in batches]) for k in range(5))
         assert np.array_equal(dbg["r_hat"], Rw)
+        th0 = [p.clone() for p in stk.online]; m0 = [p.clone() for p in stk.adam_m]; v0 = [p.clone() for p in stk.adam_v]
+        tg0 = [p.clone() for p in stk.target]
         out = stk.learn_on_batch(S, A_, Rw, S2, D)
+        alpha, eps = adam_scalars(int(stk.learn_step[0]), 5e-4, adam_form)
+        synced = tau is None and int(stk.learn_step[0]) % freq == 0
         # a near-tie in argmax_a online(s') may legitimately flip: exclude those rows (counted)
         qn = np.sort(out["q_next"], axis=2)
         tie = (qn[..., -1] - qn[..., -2]) < 1e-5 * np.abs(out["q_next"]).max()
@@ -269,10 +263,19 @@ def _learn_case(h, n, batch, cap, steps, loss="mse", tau=None, freq=3, double_dq
                 got = grp.get_weights(i, "online"); gm = grp.get_weights(i, "m"); gv = grp.get_weights(i, "v")
                 gt = grp.get_weights(i, "target")
                 for k in range(6):
-                    close(got[k].numpy(), stk.online[k][i].numpy(), what=f"step {step} net {i} theta[{k}]")
-                    close(gt[k].numpy(), stk.target[k][i].numpy(), what=f"step {step} net {i} theta_tgt[{k}]")
-                    close(gm[k].numpy(), stk.adam_m[k][i].numpy(), rtol=1e-4, what=f"step {step} net {i} adam_m[{k}]")
-                    close(gv[k].numpy(), stk.adam_v[k][i].numpy(), rtol=1e-4, what=f"step {step} net {i} adam_v[{k}]")
+                    adam_close(got[k].numpy(), th0[k][i], m0[k][i], v0[k][i], out["grads"][k][i], alpha, eps,
+                               what=f"step {step} net {i} theta[{k}]")
+                    if synced:      # hard copy of the just-updated online weights (dqn_agent.py:376-377)
+                        assert torch.equal(gt[k], got[k])
+                    elif tau is None:
+                        assert torch.equal(gt[k], tg0[k][i])
+                    else:
+                        close(gt[k].numpy(), stk.target[k][i].numpy(), what=f"step {step} net {i} theta_tgt[{k}]")
+                    close(gm[k].numpy(), stk.adam_m[k][i].numpy(), what=f"step {step} net {i} adam_m[{k}]")
+                    close(gv[k].numpy(), stk.adam_v[k][i].numpy(), what=f"step {step} net {i} adam_v[{k}]")
+                # keep the trajectories bit-identical so later steps test the kernel, not drift
+                grp.set_weights(i, [p[i] for p in stk.online], "online"); grp.set_weights(i, [p[i] for p in stk.target], "target")
+                grp.set_weights(i, [p[i] for p in stk.adam_m], "m"); grp.set_weights(i, [p[i] for p in stk.adam_v], "v")
         else:   # keep the two trajectories together after a flipped tie
             _load_oracle_weights(grp, stk)
             for i in range(n):
@@ -392,9 +395,13 @@ def test_cfg3_full_size_properties():
         rr = R.zscore_canonical(grp.rew_ring[i].cpu().numpy()[slot]).astype(np.float32)
         batches.append((grp.obs[i].cpu().numpy()[slot][:, :89], grp.act_ring[i].cpu().numpy()[slot], rr,
                         grp.next_obs[i].cpu().numpy()[slot][:, :89], grp.done_ring[i].cpu().numpy()[slot].astype(np.float32)))
+    th0 = [p.clone() for p in stk.online]
     out = stk.learn_on_batch(*(np.stack([bt[k] for bt in batches]) for k in range(5)))
     close(m[picks, 0], out["loss"], what="cfg3 loss")
+    from oracle.dqn import adam_scalars
+    alpha, eps = adam_scalars(1, 5e-4, "keras")
     for j, i in enumerate(picks):
         got = grp.get_weights(i)
         for k in range(6):
-            close(got[k].numpy(), stk.online[k][j].numpy(), what=f"cfg3 agent {i} theta[{k}]")
+            z = torch.zeros_like(th0[k][j])
+            adam_close(got[k].numpy(), th0[k][j], z, z, out["grads"][k][j], alpha, eps, what=f"cfg3 agent {i} theta[{k}]")

@@ -163,7 +163,8 @@ int dmdqn_learn_stages(const dmdqn_dims* dims, const dmdqn_hparams* hp, const dm
         rc = launch_sample(*dims, *hp, *replay, *nets, draws, learn_mask, 1, (char*)workspace, w, (cudaStream_t)stream);
         if (rc) return rc;
     }
-    return launch_learn(*dims, *hp, *replay, *nets, metrics_out, (char*)workspace, w, stages, (cudaStream_t)stream);
+    return launch_learn(*dims, *hp, *replay, *nets, metrics_out, (char*)workspace, w, stages, nullptr, 0, nullptr,
+                        (cudaStream_t)stream);
 }
 
 int dmdqn_learn(const dmdqn_dims* dims, const dmdqn_hparams* hp, const dmdqn_replay* replay,
@@ -171,6 +172,34 @@ int dmdqn_learn(const dmdqn_dims* dims, const dmdqn_hparams* hp, const dmdqn_rep
                 void* workspace, size_t workspace_bytes, void* stream) {
     return dmdqn_learn_stages(dims, hp, replay, nets, draws, learn_mask, metrics_out, workspace, workspace_bytes,
                               DMDQN_STAGE_SAMPLE | DMDQN_STAGE_TARGET | DMDQN_STAGE_ONLINE | DMDQN_STAGE_WGRAD, stream);
+}
+
+int dmdqn_learn_grads(const dmdqn_dims* dims, const dmdqn_hparams* hp, const dmdqn_replay* replay,
+                      const dmdqn_nets* nets, const void* draws, const uint8_t* learn_mask, int32_t global_batch,
+                      float* grads_out, float* metrics_out, void* workspace, size_t workspace_bytes, void* stream) {
+    Workspace w;
+    int rc = check_workspace(dims, workspace, workspace_bytes, &w);
+    if (rc) return rc;
+    rc = check_learn_args(hp, replay, nets, draws);
+    if (rc) return rc;
+    DMDQN_CHECK_ARG(grads_out != nullptr, "grads_out is NULL");
+    DMDQN_CHECK_ARG(global_batch >= dims->batch, "global_batch=%d < batch=%d", global_batch, dims->batch);
+    rc = launch_sample(*dims, *hp, *replay, *nets, draws, learn_mask, 1, (char*)workspace, w, (cudaStream_t)stream);
+    if (rc) return rc;
+    return launch_learn(*dims, *hp, *replay, *nets, metrics_out, (char*)workspace, w,
+                        DMDQN_STAGE_TARGET | DMDQN_STAGE_ONLINE | DMDQN_STAGE_WGRAD, grads_out, global_batch, nullptr,
+                        (cudaStream_t)stream);
+}
+
+int dmdqn_adam_apply(const dmdqn_dims* dims, const dmdqn_hparams* hp, const dmdqn_nets* nets, const float* grads,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+    Workspace w;
+    int rc = check_workspace(dims, workspace, workspace_bytes, &w);
+    if (rc) return rc;
+    DMDQN_CHECK_ARG(hp && nets && nets->theta && nets->theta_tgt && nets->adam_m && nets->adam_v && grads,
+                    "adam_apply: NULL argument");
+    dmdqn_replay none = {};
+    return launch_learn(*dims, *hp, none, *nets, nullptr, (char*)workspace, w, 0, nullptr, 0, grads, (cudaStream_t)stream);
 }
 
 int dmdqn_debug(const dmdqn_dims* dims, void* workspace, size_t workspace_bytes, dmdqn_debug_views* out) {

@@ -120,7 +120,8 @@ int launch_gather(const dmdqn_dims& d, const dmdqn_replay& rp, const char* ws, c
                   float* states, int32_t* actions, float* rewards, float* next_states, float* dones,
                   int32_t* active_out, cudaStream_t s);
 int launch_learn(const dmdqn_dims& d, const dmdqn_hparams& hp, const dmdqn_replay& rp, const dmdqn_nets& nets,
-                 float* metrics, char* ws, const Workspace& w, int stages, cudaStream_t s);
+                 float* metrics, char* ws, const Workspace& w, int stages, float* grads, int loss_batch,
+                 const float* apply_grads, cudaStream_t s);
 int launch_sync_target(const dmdqn_dims& d, const dmdqn_nets& nets, const uint8_t* mask, double tau,
                        cudaStream_t s);
 

@@ -37,49 +37,43 @@ struct Coord {
 };
 
 // ------------------------------------------------------------------------------------------
-// Streaming a KC x H chunk of the weight operand: global -> registers -> shared.
-//   direct     : chunk[kk][n] = W[(k0+kk)*ldw + n]           (forward:  x . W)
-//   transposed : chunk[kk][n] = W[n*ldw + k0 + kk]           (backward: d . W^T)
+// Streaming a KC x H chunk of the weight operand global -> shared with cp.async (LDGSTS): no
+// register staging, so the copy of chunk c+1 is in flight for the whole FFMA block of chunk c.
+//   direct     : chunk[kk][n] = W[(k0+kk)*ldw + n]   16-byte copies   (forward:  x . W)
+//   transposed : chunk[kk][n] = W[n*ldw + k0 + kk]    4-byte copies, transposing on the fly
+//                                                                      (backward: d . W^T)
 // ------------------------------------------------------------------------------------------
-template <int H>
-struct Stage {
-    static constexpr int N4 = Tile<H>::KC * H / 4 / Tile<H>::NT;  // float4 per thread per chunk
-    float4 v[N4];
-};
-
-template <int H, bool TRANS>
-__device__ __forceinline__ void chunk_load(Stage<H>& st, const float* __restrict__ W, int ldw, int k0) {
-    using T = Tile<H>;
-#pragma unroll
-    for (int r = 0; r < Stage<H>::N4; ++r) {
-        const int f = threadIdx.x + r * T::NT;
-        if (!TRANS) {
-            const int kk = f / (H / 4), n4 = f % (H / 4);
-            st.v[r] = __ldg(reinterpret_cast<const float4*>(W + (size_t)(k0 + kk) * ldw + n4 * 4));
-        } else {
-            const int n = f / (T::KC / 4), k4 = f % (T::KC / 4);
-            st.v[r] = __ldg(reinterpret_cast<const float4*>(W + (size_t)n * ldw + k0 + k4 * 4));
-        }
-    }
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, bool valid = true) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int src_bytes = valid ? 16 : 0;            // 0 -> the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gsrc), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 template <int H, bool TRANS>
-__device__ __forceinline__ void chunk_store(const Stage<H>& st, float* Ws) {
+__device__ __forceinline__ void chunk_issue(float* Ws, const float* __restrict__ W, int ldw, int k0) {
     using T = Tile<H>;
+    if (!TRANS) {
 #pragma unroll
-    for (int r = 0; r < Stage<H>::N4; ++r) {
-        const int f = threadIdx.x + r * T::NT;
-        if (!TRANS) {
+        for (int r = 0; r < T::KC * H / 4 / T::NT; ++r) {
+            const int f = threadIdx.x + r * T::NT;
             const int kk = f / (H / 4), n4 = f % (H / 4);
-            *reinterpret_cast<float4*>(Ws + kk * T::LDW + n4 * 4) = st.v[r];
-        } else {
-            const int n = f / (T::KC / 4), k4 = f % (T::KC / 4);
-            Ws[(k4 * 4 + 0) * T::LDW + n] = st.v[r].x;
-            Ws[(k4 * 4 + 1) * T::LDW + n] = st.v[r].y;
-            Ws[(k4 * 4 + 2) * T::LDW + n] = st.v[r].z;
-            Ws[(k4 * 4 + 3) * T::LDW + n] = st.v[r].w;
+            cp_async16(Ws + kk * T::LDW + n4 * 4, W + (size_t)(k0 + kk) * ldw + n4 * 4);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < T::KC * H / T::NT; ++r) {
+            const int f = threadIdx.x + r * T::NT;
+            const int n = f / T::KC, kk = f % T::KC;
+            cp_async4(Ws + kk * T::LDW + n, W + (size_t)n * ldw + k0 + kk);
         }
     }
+    cp_async_commit();
 }
 
 __device__ __forceinline__ void fma8(float (&acc)[8], float a, const float4& b0, const float4& b1) {
@@ -99,14 +93,13 @@ __device__ __forceinline__ void gemm_rowA(float (&acc)[8][8], const Coord<H>& c,
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-    Stage<H> st;
-    chunk_load<H, TRANS>(st, W, ldw, 0);
-    chunk_store<H, TRANS>(st, Ws);
+    chunk_issue<H, TRANS>(Ws, W, ldw, 0);
+    cp_async_wait_all();
     __syncthreads();
     int buf = 0;
     for (int k0 = 0; k0 < K; k0 += T::KC) {
         const bool more = k0 + T::KC < K;
-        if (more) chunk_load<H, TRANS>(st, W, ldw, k0 + T::KC);
+        if (more) chunk_issue<H, TRANS>(Ws + (buf ^ 1) * (T::KC * T::LDW), W, ldw, k0 + T::KC);
         const float* Wb = Ws + buf * (T::KC * T::LDW);
 #pragma unroll
         for (int kk = 0; kk < T::KC; kk += 4) {
@@ -125,7 +118,7 @@ __device__ __forceinline__ void gemm_rowA(float (&acc)[8][8], const Coord<H>& c,
                 }
             }
         }
-        if (more) chunk_store<H, TRANS>(st, Ws + (buf ^ 1) * (T::KC * T::LDW));
+        if (more) cp_async_wait_all();
         __syncthreads();
         buf ^= 1;
     }
@@ -170,18 +163,35 @@ __device__ __forceinline__ void gather_tile(float* Xs, int ldx, const float* __r
     }
 }
 
-// qs[i][a] = b3[a] + sum_j Hs2[i][j] * W3[j][a], j ascending.  Caller syncs before and after.
+// qs[i][a] = b3[a] + sum_j Hs2[i][j] * W3[j][a].  W3 (H x 4) is staged in shared memory (w3s,
+// reusing the idle weight-chunk buffer); a row is split over 4 adjacent lanes (j = q, q+4, ...)
+// whose partial sums are combined by a fixed xor butterfly.  Caller syncs before; ends synced.
 template <int H>
 __device__ __forceinline__ void layer3(const float* Hs2, const float* __restrict__ W3,
-                                       const float* __restrict__ b3, float* qs) {
+                                       const float* __restrict__ b3, float* qs, float* w3s) {
     using T = Tile<H>;
+    for (int f = threadIdx.x; f < H; f += T::NT)
+        reinterpret_cast<float4*>(w3s)[f] = __ldg(reinterpret_cast<const float4*>(W3) + f);
+    __syncthreads();
     for (int o = threadIdx.x; o < T::BM * 4; o += T::NT) {
-        const int i = o >> 2, a = o & 3;
-        float s = 0.f;
+        const int i = o >> 2, q = o & 3;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 8
-        for (int j = 0; j < H; ++j) s = fmaf(Hs2[i * T::LDH + j], __ldg(W3 + j * 4 + a), s);
-        qs[o] = s + __ldg(b3 + a);
+        for (int j = q; j < H; j += 4) {
+            const float h = Hs2[i * T::LDH + j];
+            const float4 w = reinterpret_cast<const float4*>(w3s)[j];
+            s.x = fmaf(h, w.x, s.x); s.y = fmaf(h, w.y, s.y);
+            s.z = fmaf(h, w.z, s.z); s.w = fmaf(h, w.w, s.w);
+        }
+#pragma unroll
+        for (int off = 1; off < 4; off <<= 1) {
+            s.x += __shfl_xor_sync(0xffffffffu, s.x, off); s.y += __shfl_xor_sync(0xffffffffu, s.y, off);
+            s.z += __shfl_xor_sync(0xffffffffu, s.z, off); s.w += __shfl_xor_sync(0xffffffffu, s.w, off);
+        }
+        const float v = q == 0 ? s.x : q == 1 ? s.y : q == 2 ? s.z : s.w;
+        qs[o] = v + __ldg(b3 + q);
     }
+    __syncthreads();
 }
 
 template <int H>
@@ -221,6 +231,8 @@ struct LearnArgs {
     float *y, *q_all, *q_next, *tq_all, *h1, *dh1, *dh2;
     float *part_loss, *part_b3, *part_w3, *part_b2, *part_b1;
     float* metrics;
+    float* grads;       // non-NULL: K4b stores dL/dtheta here instead of applying Adam (shared parameters, N>1 ranks)
+    int loss_batch;     // batch the loss mean runs over (== batch, or the global batch when ranks split it)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -247,8 +259,7 @@ __global__ void __launch_bounds__(Tile<H>::NT, 1) target_kernel(const LearnArgs 
         gemm_rowA<H, false>(acc, c, S.Hs1, T::LDH, P + A.L.w2, H, H, S.Ws);
         store_relu<H>(acc, c, P + A.L.b2, S.Hs2, nullptr, r0, B);
         __syncthreads();
-        layer3<H>(S.Hs2, P + A.L.w3, P + A.L.b3, pass == 0 ? S.qs0 : S.qs1);
-        __syncthreads();
+        layer3<H>(S.Hs2, P + A.L.w3, P + A.L.b3, pass == 0 ? S.qs0 : S.qs1, S.Ws);
     }
     for (int i = threadIdx.x; i < T::BM; i += T::NT) {
         const int gr = r0 + i;
@@ -295,8 +306,7 @@ __global__ void __launch_bounds__(Tile<H>::NT, 1) online_kernel(const LearnArgs 
     gemm_rowA<H, false>(acc, c, S.Hs1, T::LDH, P + A.L.w2, H, H, S.Ws);
     store_relu<H>(acc, c, P + A.L.b2, S.Hs2, nullptr, r0, B);
     __syncthreads();
-    layer3<H>(S.Hs2, P + A.L.w3, P + A.L.b3, S.qs0);
-    __syncthreads();
+    layer3<H>(S.Hs2, P + A.L.w3, P + A.L.b3, S.qs0, S.Ws);
 
     // loss terms and dL/dpred per row (:349-352)
     float* terms = S.qs1;                            // [BM] loss terms
@@ -309,11 +319,11 @@ __global__ void __launch_bounds__(Tile<H>::NT, 1) online_kernel(const LearnArgs 
             const float e = S.qs0[i * 4 + ai] - A.y[sb + gr];
             if (A.loss == DMDQN_LOSS_MSE) {
                 term = e * e;
-                gi = (2.0f * e) / (float)B;
+                gi = (2.0f * e) / (float)A.loss_batch;
             } else {
                 const float ae = fabsf(e);
                 term = ae <= 1.0f ? 0.5f * e * e : ae - 0.5f;
-                gi = fminf(fmaxf(e, -1.0f), 1.0f) / (float)B;
+                gi = fminf(fmaxf(e, -1.0f), 1.0f) / (float)A.loss_batch;
             }
             for (int k = 0; k < 4; ++k) A.q_all[(sb + gr) * 4 + k] = S.qs0[i * 4 + k];
         }
@@ -482,6 +492,10 @@ __global__ void __launch_bounds__(Tile<H>::NT) wgrad_adam_kernel(const LearnArgs
                 for (int r = 0; r < A.tiles; ++r) gsum += A.part_b3[(p0 + r) * 4 + (e - 6 * H)];
                 off = A.L.b3 + (e - 6 * H);
             }
+            if (A.grads) {
+                A.grads[(size_t)g * A.L.stride + off] = gsum;
+                continue;
+            }
             float tgv = k.sync == 2 ? tg[off] : 0.f;
             adam_elem(k, gsum, th[off], am[off], av[off], tgv);
             if (k.sync) tg[off] = tgv;
@@ -496,7 +510,7 @@ __global__ void __launch_bounds__(Tile<H>::NT) wgrad_adam_kernel(const LearnArgs
             const double cnt = (double)B * A.d.n_actions;
             const double mean = qs / cnt, var = fmax(qq / cnt - mean * mean, 0.0);
             float* m = A.metrics + g * DMDQN_METRICS_STRIDE;
-            m[0] = (float)(ls / B);                        // batch-mean loss (:352)
+            m[0] = (float)(ls / A.loss_batch);             // batch-mean loss (:352)
             m[1] = (float)mean;
             m[2] = (float)sqrt(var);
             for (int a = 0; a < 4; ++a) m[3 + a] = (float)hist[a];
@@ -516,42 +530,28 @@ __global__ void __launch_bounds__(Tile<H>::NT) wgrad_adam_kernel(const LearnArgs
     const int lda_src = is_w2 ? H : Dp;
     const Coord<H> c;
 
-    constexpr int A4 = T::KC * T::BM / 4;            // float4 in an A chunk
+    constexpr int A4 = T::KC * T::BM / 4;            // 16-byte pieces in an A chunk
     constexpr int NA = (A4 + T::NT - 1) / T::NT;
-    float4 sa[NA];
-    Stage<H> sbv;
-    auto load = [&](int k0) {
+    auto issue = [&](int k0, int buf) {
 #pragma unroll
         for (int r = 0; r < NA; ++r) {
             const int f = threadIdx.x + r * T::NT;
-            sa[r] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (f < A4) {
                 const int kk = f / (T::BM / 4), m4 = f % (T::BM / 4);
                 const int kr = k0 + kk, m = m0 + m4 * 4;
-                if (kr < B && m < m_valid) {
-                    const size_t src_row = is_w2 ? (size_t)kr : (size_t)rows[kr];
-                    sa[r] = __ldg(reinterpret_cast<const float4*>(Asrc + src_row * lda_src + m));
-                }
+                const bool ok = kr < B && m < m_valid;
+                const size_t src_row = ok ? (is_w2 ? (size_t)kr : (size_t)rows[kr]) : 0;
+                cp_async16(&As[buf][kk * LDA + m4 * 4], Asrc + src_row * lda_src + (ok ? m : 0), ok);
             }
         }
 #pragma unroll
-        for (int r = 0; r < Stage<H>::N4; ++r) {
+        for (int r = 0; r < T::KC * H / 4 / T::NT; ++r) {
             const int f = threadIdx.x + r * T::NT;
             const int kk = f / (H / 4), n4 = f % (H / 4);
-            sbv.v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (k0 + kk < B) sbv.v[r] = __ldg(reinterpret_cast<const float4*>(Dsrc + (size_t)(k0 + kk) * H) + n4);
+            const bool ok = k0 + kk < B;
+            cp_async16(&Bs[buf][kk * T::LDW + n4 * 4], Dsrc + (size_t)(ok ? k0 + kk : 0) * H + n4 * 4, ok);
         }
-    };
-    auto store = [&](int buf) {
-#pragma unroll
-        for (int r = 0; r < NA; ++r) {
-            const int f = threadIdx.x + r * T::NT;
-            if (f < A4) {
-                const int kk = f / (T::BM / 4), m4 = f % (T::BM / 4);
-                *reinterpret_cast<float4*>(&As[buf][kk * LDA + m4 * 4]) = sa[r];
-            }
-        }
-        chunk_store<H, false>(sbv, Bs[buf]);
+        cp_async_commit();
     };
 
     float acc[8][8];
@@ -559,13 +559,13 @@ __global__ void __launch_bounds__(Tile<H>::NT) wgrad_adam_kernel(const LearnArgs
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-    load(0);
-    store(0);
+    issue(0, 0);
+    cp_async_wait_all();
     __syncthreads();
     int buf = 0;
     for (int k0 = 0; k0 < B; k0 += T::KC) {
         const bool more = k0 + T::KC < B;
-        if (more) load(k0 + T::KC);
+        if (more) issue(k0 + T::KC, buf ^ 1);
 #pragma unroll
         for (int kk = 0; kk < T::KC; ++kk) {
             const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk * LDA + c.wm * 32 + c.lm * 4]);
@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(Tile<H>::NT) wgrad_adam_kernel(const LearnArgs
             fma8(acc[4], a1.x, b0, b1); fma8(acc[5], a1.y, b0, b1);
             fma8(acc[6], a1.z, b0, b1); fma8(acc[7], a1.w, b0, b1);
         }
-        if (more) store(buf ^ 1);
+        if (more) cp_async_wait_all();
         __syncthreads();
         buf ^= 1;
     }
@@ -591,7 +591,11 @@ __global__ void __launch_bounds__(Tile<H>::NT) wgrad_adam_kernel(const LearnArgs
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             const int64_t off = wbase + (int64_t)m * H + c.col0(half);
-            adam_vec4(k, &acc[i][half * 4], th + off, am + off, av + off, tg + off);
+            if (A.grads)
+                *reinterpret_cast<float4*>(A.grads + (size_t)g * A.L.stride + off) =
+                    make_float4(acc[i][half * 4], acc[i][half * 4 + 1], acc[i][half * 4 + 2], acc[i][half * 4 + 3]);
+            else
+                adam_vec4(k, &acc[i][half * 4], th + off, am + off, av + off, tg + off);
         }
     }
 }
@@ -612,6 +616,22 @@ __global__ void sync_target_kernel(int64_t stride, const float* __restrict__ the
             s.z = tau * s.z + (1.f - tau) * o.z; s.w = tau * s.w + (1.f - tau) * o.w;
         }
         dst[i] = s;
+    }
+}
+
+// Adam + target sync from an explicit (all-reduced) gradient block: the tail of K4b when the
+// gradient had to leave the kernel for the NCCL all-reduce.
+__global__ void adam_apply_kernel(const LearnArgs A, const float* __restrict__ grads) {
+    const int g = blockIdx.y;
+    if (!A.active[g]) return;
+    const AdamCoef k = adam_coef(A, A.step_t[g]);
+    const size_t base = (size_t)g * A.L.stride;
+    const int64_t n4 = (A.L.b3 + 4) / 4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 g4 = *reinterpret_cast<const float4*>(grads + base + i * 4);
+        const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+        adam_vec4(k, gv, A.nets.theta + base + i * 4, A.nets.adam_m + base + i * 4, A.nets.adam_v + base + i * 4,
+                  A.nets.theta_tgt + base + i * 4);
     }
 }
 
@@ -647,7 +667,8 @@ int launch_learn_h(const LearnArgs& A, int stages, cudaStream_t s) {
 }  // namespace
 
 int launch_learn(const dmdqn_dims& d, const dmdqn_hparams& hp, const dmdqn_replay& rp, const dmdqn_nets& nets,
-                 float* metrics, char* ws, const Workspace& w, int stages, cudaStream_t s) {
+                 float* metrics, char* ws, const Workspace& w, int stages, float* grads, int loss_batch,
+                 const float* apply_grads, cudaStream_t s) {
     LearnArgs A;
     A.d = d;
     A.L = make_layout(d.obs_stride, d.hidden);
@@ -679,6 +700,14 @@ int launch_learn(const dmdqn_dims& d, const dmdqn_hparams& hp, const dmdqn_repla
     A.part_b2 = reinterpret_cast<float*>(ws + w.part_b2);
     A.part_b1 = reinterpret_cast<float*>(ws + w.part_b1);
     A.metrics = metrics;
+    A.grads = grads;
+    A.loss_batch = loss_batch > 0 ? loss_batch : d.batch;
+    if (apply_grads) {
+        dim3 grid(64, d.n_nets);
+        adam_apply_kernel<<<grid, 256, 0, s>>>(A, apply_grads);
+        DMDQN_CUDA(cudaGetLastError());
+        return DMDQN_OK;
+    }
     switch (d.hidden) {
         case 64: return launch_learn_h<64>(A, stages, s);
         case 128: return launch_learn_h<128>(A, stages, s);

@@ -1,0 +1,84 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), torch.distributed for rendezvous.
+
+Independent networks (the reference's semantics, train.py:123-126) shard by contiguous
+agent ranges with NO data-path collective: GPU r owns agents [r*N/G, (r+1)*N/G) with their
+replay rings, theta, theta_tgt, Adam state.  Per-agent results are
+bit-identical to the 1-GPU run because every kernel works on one agent's data only.
+
+Shared parameters (BASELINE.json cfg5, not in the reference): every rank holds
+a replica of theta/theta_tgt/m/v, draws batch/G transitions from its own rings, computes
+dL/dtheta with the loss mean over the GLOBAL batch, the gradient blocks are summed with one
+all-reduce (NCCL over NVLink/NVSwitch; gloo in the CPU tests), and every rank applies the
+same Adam step.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_total: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous agent range of ``rank``; the first ``n_total % world`` ranks get one extra."""
+    if not (0 <= rank < world) or n_total < 0:
+        raise ValueError(f"bad shard request n_total={n_total} world={world} rank={rank}")
+    base, extra = divmod(n_total, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def shard_seed(seed: int, agent_global_index: int) -> int:
+    """Per-agent init seed that does not depend on how agents are sharded."""
+    return int(seed) + int(agent_global_index)
+
+
+def allreduce_sum_(t: torch.Tensor, group=None) -> torch.Tensor:
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+class SharedParameterStep:
+    """One data-parallel learn step of a shared network: local gradients -> all-reduce ->
+    identical Adam on every replica.  ``local_grads(global_batch)`` returns the rank's
+    gradient block (already divided by the global batch) and a [.., 8] metrics tensor whose
+    column 0 is the rank's share of the loss; ``apply(grads)`` performs the update.  The two
+    callables are the native calls on a GPU (``for_group``) and oracle stand-ins in the CPU
+    (gloo) tests, so the same host logic is exercised in both."""
+
+    def __init__(self, local_grads, apply, local_batch: int, group=None):
+        self.local_grads, self.apply, self.local_batch, self.group = local_grads, apply, int(local_batch), group
+
+    @property
+    def world(self) -> int:
+        return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
+    def step(self):
+        grads, metrics = self.local_grads(self.local_batch * self.world)
+        allreduce_sum_(grads, self.group)           # 4*P bytes, latency bound (1.24 MB at H=512)
+        loss = allreduce_sum_(metrics[..., 0].clone(), self.group)
+        self.apply(grads)
+        return loss
+
+    @classmethod
+    def for_group(cls, grp, group=None) -> "SharedParameterStep":
+        """Bind to an AgentGroup built with ``share_parameters=True``."""
+        from . import _native as N
+        from .group import _ptr
+        if not grp.shared:
+            raise ValueError("SharedParameterStep needs share_parameters=True")
+        grads = torch.zeros_like(grp.theta)
+
+        def local_grads(global_batch: int):
+            d = grp.draw_words((1, grp.batch_size))
+            N.check(grp.lib.dmdqn_learn_grads(C.byref(grp.dims), C.byref(grp.hp), C.byref(grp.replay), C.byref(grp.nets),
+                                              _ptr(d), None, int(global_batch), _ptr(grads), _ptr(grp.metrics),
+                                              _ptr(grp.workspace), grp.workspace.numel(), grp._stream))
+            grp.learn_step_host += grp.active_host().astype("int64")
+            return grads, grp.metrics
+
+        def apply(g: torch.Tensor):
+            N.check(grp.lib.dmdqn_adam_apply(C.byref(grp.dims), C.byref(grp.hp), C.byref(grp.nets), _ptr(g),
+                                             _ptr(grp.workspace), grp.workspace.numel(), grp._stream))
+        return cls(local_grads, apply, grp.batch_size, group)

@@ -218,6 +218,18 @@ int dmdqn_learn_stages(const dmdqn_dims* dims, const dmdqn_hparams* hp, const dm
                        float* metrics_out, void* workspace, size_t workspace_bytes, int32_t stages,
                        void* stream);
 
+/* Shared-parameter mode across ranks (n_nets == 1; not in the reference, BASELINE.json cfg5):
+ * the same step but K4b stores dL/dtheta into grads_out[n_nets][layout.stride] instead of
+ * applying Adam, with the loss mean taken over global_batch (= batch * ranks), so that the
+ * caller can sum the blocks over ranks (ncclAllReduce) and finish with dmdqn_adam_apply,
+ * which reads the step counters dmdqn_learn_grads left in the workspace. */
+int dmdqn_learn_grads(const dmdqn_dims* dims, const dmdqn_hparams* hp, const dmdqn_replay* replay,
+                      const dmdqn_nets* nets, const void* draws, const uint8_t* learn_mask,
+                      int32_t global_batch, float* grads_out, float* metrics_out, void* workspace,
+                      size_t workspace_bytes, void* stream);
+int dmdqn_adam_apply(const dmdqn_dims* dims, const dmdqn_hparams* hp, const dmdqn_nets* nets,
+                     const float* grads, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Debug / parity views into the workspace after dmdqn_learn (device pointers into it):
  * y[n_nets][B], q_all[n_nets][B][4] (online Q of s), q_next[n_nets][B][4] (online Q of s'),
  * tq_all[n_nets][B][4] (target Q of s'), rows int32[n_nets][B] (agent*C + slot). */

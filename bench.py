@@ -36,9 +36,10 @@ WORKLOADS = {
 D, A = 89, 4
 
 
-def agent_cfg(w):
+def agent_cfg(w, precision="fp32"):
     return {"learning_rate": 5e-4, "gamma": 0.99, "replay_buffer_size": w["capacity"], "batch_size": w["batch"],
-            "target_update_frequency": 1000, "nn_layers": [w["hidden"], w["hidden"]]}   # config/agent_config.yaml
+            "target_update_frequency": 1000, "nn_layers": [w["hidden"], w["hidden"]],    # config/agent_config.yaml
+            "precision": precision}
 
 
 def flops_bytes(w):
@@ -130,7 +131,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     w = WORKLOADS[args.workload]
     fb = flops_bytes(w)
-    grp = AgentGroup(w["agents"], agent_cfg(w), D, A, seed=1000 * rank)
+    grp = AgentGroup(w["agents"], agent_cfg(w, args.precision), D, A, seed=1000 * rank)
     synth_fill(grp, seed=rank)
     n, b = grp.n_agents, grp.batch_size
     K, W = args.steps, args.warmup
@@ -172,6 +173,36 @@ def run_ours(args):
     torch.cuda.synchronize()
     grp.learn_step_host += K
     stage_ms = {nm: statistics.mean(evs[i][s].elapsed_time(evs[i][s + 1]) for i in range(K)) for s, nm in enumerate(stage_names)}
+
+    # ---- the other kernels of the path, device-resident (actions/s is BASELINE's second metric) ----
+    obs_dev = grp.obs[:, 0, :].contiguous()
+    eps0 = torch.zeros(n, dtype=torch.float64, device=grp.device)
+    w_zero = torch.zeros(n, dtype=torch.int32, device=grp.device)
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(reps):
+            fn()
+        b_.record(stream)
+        torch.cuda.synchronize()
+        return a.elapsed_time(b_) / reps
+    act_ms = timed(lambda: grp.act(obs_dev, eps0, w_zero, w_zero), 4 * K)       # eps = 0: every agent runs its network
+    halting = torch.randint(0, 20, (n, 12), dtype=torch.int32, device=grp.device)
+    zi = torch.zeros(n, dtype=torch.int32, device=grp.device); zd = torch.zeros(n, dtype=torch.float64, device=grp.device)
+    zv = torch.zeros(n, dtype=torch.uint8, device=grp.device)
+    side = int(round(n ** 0.5))
+    from oracle.featurize import grid_neighbors                               # index table only (not on the timed path)
+    nbr = torch.as_tensor(grid_neighbors(side, max(1, n // side))[:n]).to(grp.device)
+    feat_ms = timed(lambda: grp.featurize(halting, zi, zd, zd, 0.0, zv, nbr), 4 * K)
+    act_bytes = n * 4 * fb["params"]
+    extra = {"act": {"value": n * world / (act_ms / 1e3), "unit": "actions/s", "ms": act_ms, "eps": 0.0,
+                     "hbm_gbs": act_bytes / (act_ms / 1e3) / 1e9, "hbm_frac": act_bytes / (act_ms / 1e3) / 1e9 / peaks()["hbm_gbs"],
+                     "bytes_per_action": 4 * fb["params"]},
+             "featurize": {"ms": feat_ms, "agents_per_s": n * world / (feat_ms / 1e3), "bytes_per_agent": 64 + 96 * 4 + 17 * 8 + 8}}
 
     # ---- end to end: host transitions + draws in, losses out, every step ------------------
     pin = lambda t: t.pin_memory()
@@ -221,7 +252,7 @@ def run_ours(args):
         "data": "synthetic replay (observation-shaped integers, full rings), random-init weights",
         "config": {"workload": f"{args.workload}: {w['agents']} agents/GPU ({w['grid']}), batch {w['batch']}, hidden "
                                f"[{w['hidden']},{w['hidden']}], obs 89, actions 4, replay capacity {w['capacity']}, "
-                               f"independent networks, fp32 FFMA path",
+                               f"independent networks, precision {args.precision}",
                    "agents_total": total_agents, "sharding": "agent ranges, no collectives" if world > 1 else "single GPU",
                    "l2_policy": "working set (replay ring 5.9 GB, theta/m/v 368 MB, scratch 200 MB at cfg3) exceeds the 126 MB L2",
                    "sample_mode": "fisher_yates (device draws)"},
@@ -232,10 +263,13 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": dom, "achieved": ach_tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": ach_tf / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"],
-                     "note": "fp32 FFMA kernel (1e-5 parity path): fraction of the fp32 FFMA peak at the sampled clock = "
-                             f"{ach_tf / ffma_peak:.3f} of {ffma_peak:.1f} TFLOP/s"},
+                     "note": (f"fp32 FFMA kernel: fraction of the fp32 FFMA peak at the sampled clock = {ach_tf / ffma_peak:.3f} of "
+                              f"{ffma_peak:.1f} TFLOP/s") if args.precision == "fp32" else
+                             ("tcgen05 kind::tf32; achieved counts ALGORITHMIC flops (each product is issued as "
+                              f"{3 if args.precision == 'tf32x3' else 1} MMA(s)); peak is the measured bf16 figure (tf32 dense peak is half of it)")},
         "kernels": {k_: {"ms": stage_ms[k_], "tflops": n * fb["kernels"][k_]["flops"] / (stage_ms[k_] / 1e3) / 1e12,
                          "gbs": n * fb["kernels"][k_]["bytes"] / (stage_ms[k_] / 1e3) / 1e9} for k_ in stage_names},
+        **extra,
         "step": {"flops_per_agent_update": fb["flops"], "bytes_per_agent_update": fb["bytes"],
                  "tflops": n * fb["flops"] / (ms / K / 1e3) / 1e12, "hbm_gbs_algorithmic": n * fb["bytes"] / (ms / K / 1e3) / 1e9,
                  "hbm_frac": n * fb["bytes"] / (ms / K / 1e3) / 1e9 / pk["hbm_gbs"]},
@@ -329,6 +363,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()

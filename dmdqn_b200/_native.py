@@ -12,7 +12,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_WORKSPACE = 0, -1, -2, -3
 LOSS = {"mse": 0, "huber": 1}
 SAMPLE = {"indices": 0, "fisher_yates": 1, "replacement": 2}
 ADAM = {"keras": 0, "torch": 1}
-PRECISION = {"fp32": 0, "tf32": 1}
+PRECISION = {"fp32": 0, "tf32": 1, "tf32x3": 2}
 METRICS_STRIDE = 8
 
 
@@ -40,7 +40,7 @@ class HParams(C.Structure):
 
 
 class DebugViews(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("y", "q_all", "q_next", "tq_all", "rows", "r_hat", "active")]
+    _fields_ = [(n, C.c_void_p) for n in ("y", "q_all", "q_next", "tq_all", "rows", "r_hat", "active", "tc_error", "dh1", "dh2")]
 
 
 # name -> (restype, argtypes); mirrors include/dmdqn_b200.h one to one

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdmdqn_b200.so")
-SOURCES = ["api.cu", "featurize.cu", "act.cu", "replay.cu", "learn.cu"]
+SOURCES = ["api.cu", "featurize.cu", "act.cu", "replay.cu", "learn.cu", "learn_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-extended-lambda", "-Xcompiler", "-fPIC", "-shared"]
 

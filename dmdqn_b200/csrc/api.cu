@@ -123,7 +123,8 @@ static int check_learn_args(const dmdqn_hparams* hp, const dmdqn_replay* replay,
                     "NULL network pointer");
     DMDQN_CHECK_ARG(hp->sample_mode >= 0 && hp->sample_mode <= 2, "sample_mode=%d", hp->sample_mode);
     DMDQN_CHECK_ARG(hp->loss == DMDQN_LOSS_MSE || hp->loss == DMDQN_LOSS_HUBER, "loss=%d", hp->loss);
-    DMDQN_CHECK_ARG(hp->precision == DMDQN_PRECISION_FP32, "precision=%d: only fp32 is built", hp->precision);
+    DMDQN_CHECK_ARG(hp->precision >= DMDQN_PRECISION_FP32 && hp->precision <= DMDQN_PRECISION_TF32X3, "precision=%d",
+                    hp->precision);
     return DMDQN_OK;
 }
 
@@ -215,6 +216,9 @@ int dmdqn_debug(const dmdqn_dims* dims, void* workspace, size_t workspace_bytes,
     out->rows = (const int32_t*)(ws + w.rows);
     out->r_hat = (const float*)(ws + w.r_hat);
     out->active = (const int32_t*)(ws + w.active);
+    out->tc_error = (const int32_t*)(ws + w.tc_error);
+    out->dh1 = (const float*)(ws + w.dh1);
+    out->dh2 = (const float*)(ws + w.dh2);
     return DMDQN_OK;
 }
 

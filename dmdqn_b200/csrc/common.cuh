@@ -60,7 +60,8 @@ inline int row_tiles(int batch, int bm) { return (batch + bm - 1) / bm; }
 // Workspace carve-up (device scratch of sample/learn), offsets in bytes, 256-aligned.
 struct Workspace {
     size_t rows, r_hat, act_b, done_b, active, step_t, y, gcoef, q_all, q_next, tq_all;
-    size_t h1, dh1, dh2;              // [n_nets][B][H] floats each
+    size_t h1, h2, dh1, dh2;          // [n_nets][B][H] floats each (h2 only used by the tcgen05 path)
+    size_t tc_error;                  // int: set by a tcgen05 kernel whose mbarrier wait timed out
     size_t part_loss;                 // [n_nets][T][8]
     size_t part_b3;                   // [n_nets][T][4]
     size_t part_w3;                   // [n_nets][T][H][4]
@@ -88,6 +89,8 @@ inline Workspace make_workspace(const dmdqn_dims& d) {
     w.q_next = take(nb * 16);
     w.tq_all = take(nb * 16);
     w.h1 = take(nb * d.hidden * 4);
+    w.h2 = take(nb * d.hidden * 4);
+    w.tc_error = take(4);
     w.dh1 = take(nb * d.hidden * 4);
     w.dh2 = take(nb * d.hidden * 4);
     w.part_loss = take(nt * 8 * 4);
@@ -122,6 +125,10 @@ int launch_gather(const dmdqn_dims& d, const dmdqn_replay& rp, const char* ws, c
 int launch_learn(const dmdqn_dims& d, const dmdqn_hparams& hp, const dmdqn_replay& rp, const dmdqn_nets& nets,
                  float* metrics, char* ws, const Workspace& w, int stages, float* grads, int loss_batch,
                  const float* apply_grads, cudaStream_t s);
+bool tc_supported(const dmdqn_dims& d);
+int launch_learn_tc(const dmdqn_dims& d, const dmdqn_hparams& hp, const dmdqn_replay& rp, const dmdqn_nets& nets,
+                    float* metrics, char* ws, const Workspace& w, int stages, float* grads, int loss_batch,
+                    cudaStream_t s);
 int launch_sync_target(const dmdqn_dims& d, const dmdqn_nets& nets, const uint8_t* mask, double tau,
                        cudaStream_t s);
 

@@ -669,6 +669,14 @@ int launch_learn_h(const LearnArgs& A, int stages, cudaStream_t s) {
 int launch_learn(const dmdqn_dims& d, const dmdqn_hparams& hp, const dmdqn_replay& rp, const dmdqn_nets& nets,
                  float* metrics, char* ws, const Workspace& w, int stages, float* grads, int loss_batch,
                  const float* apply_grads, cudaStream_t s) {
+    if (hp.precision != DMDQN_PRECISION_FP32 && !apply_grads) {
+        if (!tc_supported(d)) {
+            set_error("precision=%d (tcgen05) needs hidden=256 and obs_stride in {32,64,96}; got hidden=%d obs_stride=%d",
+                      hp.precision, d.hidden, d.obs_stride);
+            return DMDQN_ERR_ARG;
+        }
+        return launch_learn_tc(d, hp, rp, nets, metrics, ws, w, stages, grads, loss_batch, s);
+    }
     LearnArgs A;
     A.d = d;
     A.L = make_layout(d.obs_stride, d.hidden);

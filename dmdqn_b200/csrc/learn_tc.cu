@@ -1,0 +1,891 @@
+// K3 / K4 on the 5th-generation tensor cores (tcgen05, kind::tf32, accumulators in TMEM).
+//
+// Same arithmetic contract as learn.cu (reference src/agents/dqn_agent.py:328-380), H = 256:
+//   tc_target_kernel   K3   s' -> online(s'), target(s') -> TD target
+//   tc_online_kernel   K4a  s  -> online(s), loss gradient, dh2, dh1 = (dh2 W2^T) * relu'(h1)
+//   tc_wgrad_kernel    K4b  dW2 = h1^T dh2, dW1 = s^T dh1 with Adam + target sync in the epilogue
+//
+// tcgen05 has no fp32 MMA kind, so every fp32 operand x is split as x = hi + lo with
+// hi = x rounded to tf32 and lo = x - hi (exact), and a product A*B is issued as three MMAs
+// A_lo*B_hi + A_hi*B_lo + A_hi*B_hi accumulated in fp32 in TMEM ("3xTF32"; measured 3e-7 relative
+// on B200, tools/umma_probe.cu).  PASSES = 1 issues only A*B (plain TF32, ~1e-3, toleranced apart).
+//
+// A CTA owns 128 batch rows of one network (UMMA M = 128, N = 256 = all output columns):
+//   * activations: hi part in shared memory as the next layer's A operand (K-major, 128-byte
+//     swizzle), lo part in TMEM columns 256..511 (A-from-TMEM MMA) -- 128 KB each, so the full
+//     512 TMEM columns are used: 256 accumulator + 256 operand;
+//   * weights: 16 x 256 chunks streamed from L2 with cp.async straight into the UMMA canonical
+//     layout (MN-major "128B_BASE32B" for x.W, K-major 64-byte swizzle for d.W^T), split hi/lo
+//     in place by the thread that copied them, two stages, freed by tcgen05.commit -> mbarrier;
+//   * epilogues read the accumulator with tcgen05.ld (thread = batch row), so bias/ReLU, the
+//     4-wide head (layer 3), TD target, loss gradient and dh2 are computed per row in registers.
+#include "common.cuh"
+
+namespace dmdqn {
+
+namespace {
+
+constexpr int H = 256;          // hidden width served by this path
+constexpr int BM = 128;         // batch rows per CTA (UMMA M)
+constexpr int NT = 256;         // threads per CTA: 8 warps, two per TMEM sub-partition
+constexpr int KC = 16;          // k-rows of the streamed operand per stage
+constexpr uint32_t ATOM = BM * 128;           // bytes of one K-major SW128 atom column (128 rows x 32 floats)
+constexpr uint32_t STAGE = 2 * KC * H * 4;    // hi + lo of a 16 x 256 chunk
+constexpr uint32_t SPIN_LIMIT = 1u << 26;
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers (syntax as in the CUTLASS sm100 headers shipped with the image).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 1 = SWIZZLE_128B_BASE32B (the only MN-major layout for tf32)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16 |
+           (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32 | (uint64_t)1 << 46 | (uint64_t)layout << 61;
+}
+// kind::tf32, fp32 accumulate, M = 128, N = 256
+__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+           ((uint32_t)(H >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accum) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d), "l"(a), "l"(b), "r"(idesc),
+                 "r"(accum) : "memory");
+}
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t accum) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d), "r"(a_tmem), "l"(b),
+                 "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+// Bounded wait: a wrong descriptor must end in an error flag, not in a hung GPU.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < SPIN_LIMIT && !done; ++spin)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
+        "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
+        "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};\n" ::"r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+        "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+        "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+        "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+        "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void cp16(uint32_t dst, const float* src, bool valid = true) {
+    const int n = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// x = hi + lo, hi = x rounded to tf32 (nearest, ties away), lo exact in fp32
+__device__ __forceinline__ float tf32_hi(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+template <int PASSES>
+__device__ __forceinline__ void split4(const float4& x, float4& hi, float4& lo) {
+    if (PASSES == 1) { hi = x; lo = make_float4(0.f, 0.f, 0.f, 0.f); return; }   // the tensor core truncates itself
+    hi = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+    lo = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+}
+
+// Byte offsets inside UMMA canonical tiles (validated by tools/umma_probe.cu).
+//   K-major, 128-byte swizzle: [k/32][row][128 B], 16-byte piece index ^= row % 8
+__device__ __forceinline__ uint32_t off_k128(int rows, int r, int k) {
+    return (uint32_t)((k >> 5) * rows * 128 + r * 128 + ((((k & 31) >> 2) ^ (r & 7)) << 4) + ((k & 3) << 2));
+}
+//   K-major, 64-byte swizzle: [k/16][row][64 B], piece index ^= (row / 2) % 4
+__device__ __forceinline__ uint32_t off_k64(int rows, int r, int k) {
+    return (uint32_t)((k >> 4) * rows * 64 + r * 64 + ((((k & 15) >> 2) ^ ((r >> 1) & 3)) << 4) + ((k & 3) << 2));
+}
+//   MN-major tf32 (128B_BASE32B): atoms of 4 k x 32 mn = 512 B, [k/4][mn/32][k%4][128 B], 32-byte piece ^= k % 4
+__device__ __forceinline__ uint32_t off_mn(int mn_total, int k, int mn) {
+    return (uint32_t)((k >> 2) * (mn_total >> 5) * 512 + (mn >> 5) * 512 + (k & 3) * 128 +
+                      ((((mn & 31) >> 3) ^ (k & 3)) << 5) + ((mn & 7) << 2));
+}
+
+struct TcArgs {
+    dmdqn_dims d;
+    Layout L;
+    dmdqn_replay rp;
+    dmdqn_nets nets;
+    float gamma;
+    int loss, double_dqn, adam_form, freq, loss_batch, tiles;
+    double lr, beta1, beta2, adam_eps, tau;
+    const int32_t *rows, *act_b, *active, *step_t;
+    const float *r_hat, *done_b;
+    float *y, *gcoef, *q_all, *q_next, *tq_all, *h1, *h2, *dh1, *dh2, *part_loss, *metrics, *grads;
+    int* error;
+};
+
+// Shared-memory carve-up of the K3 / K4a kernels (offsets from a 1024-byte aligned base).
+struct Fwd {
+    static constexpr uint32_t R = 0;                          // 128 KB: X hi|lo during layer 1, then activation hi
+    static constexpr uint32_t XLO = 3 * ATOM;                 // X lo (K <= 96) inside R
+    static constexpr uint32_t WB = 8 * ATOM;                  // 2 weight stages
+    static constexpr uint32_t BIAS1 = WB + 2 * STAGE;         // b1[256]
+    static constexpr uint32_t BIAS2 = BIAS1 + 1024;           // b2[256]
+    static constexpr uint32_t W3S = BIAS2 + 1024;             // W3[256][4]
+    static constexpr uint32_t QP = W3S + 4096;                // q partials [2][128][4]
+    static constexpr uint32_t ROWF = QP + 4096;               // per-row words [6][128]: loss term, q[4], action
+    static constexpr uint32_t BARS = ROWF + 4096;             // 2 mbarriers + tmem base
+    static constexpr uint32_t TOTAL = BARS + 64;
+};
+
+// ------------------------------------------------------------------------------------------
+// Streamed GEMM: D[128 x 256] (TMEM columns 0..255) = A[128 x K] * op(W), fp32 via PASSES MMAs.
+//   A hi: shared memory, K-major SW128 at a_hi; A lo: shared memory (a_lo_smem != 0) or TMEM columns.
+//   BT = false: W is [K][256] row-major (x.W),   staged MN-major;
+//   BT = true : W is [256][K] row-major (d.W^T), staged K-major SW64.
+// `uses` counts commits per stage barrier (mbarrier phase bookkeeping, uniform over the CTA).
+// ------------------------------------------------------------------------------------------
+template <int PASSES, bool BT>
+__device__ __forceinline__ bool gemm_stream(uint32_t sbase, uint32_t tmem, uint32_t a_hi, uint32_t a_lo_smem,
+                                            uint32_t a_lo_tmem, const float* __restrict__ W, int ldw, int K,
+                                            uint32_t (&uses)[2]) {
+    const int tid = threadIdx.x;
+    const uint32_t bar0 = sbase + Fwd::BARS;
+    const int nchunks = K / KC;
+    bool ok = true;
+    auto issue = [&](int c) {
+        const uint32_t st = sbase + Fwd::WB + (c & 1) * STAGE;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int p = tid + r * NT;
+            if (!BT) {
+                const int kk = p >> 6, n = (p & 63) << 2;
+                cp16(st + off_mn(H, kk, n), W + (size_t)(c * KC + kk) * ldw + n);
+            } else {
+                const int n = p >> 2, k = (p & 3) << 2;
+                cp16(st + off_k64(H, n, k), W + (size_t)n * ldw + c * KC + k);
+            }
+        }
+    };
+    issue(0);
+    cp_commit();
+    for (int c = 0; c < nchunks; ++c) {
+        if (c + 1 < nchunks) {
+            const int b = (c + 1) & 1;
+            if (uses[b]) ok &= mbar_wait(bar0 + 8 * b, (uses[b] - 1) & 1);   // MMAs that read this stage are done
+            issue(c + 1);
+        }
+        cp_commit();
+        cp_wait<1>();                                        // this thread's pieces of chunk c have landed
+        if (PASSES == 3) {                                   // split them: hi in place, lo beside
+            const uint32_t st = sbase + Fwd::WB + (c & 1) * STAGE;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int p = tid + r * NT;
+                uint32_t o;
+                if (!BT) o = off_mn(H, p >> 6, (p & 63) << 2);
+                else o = off_k64(H, p >> 2, (p & 3) << 2);
+                float4 x, hi, lo;
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(st + o));
+                split4<3>(x, hi, lo);
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(st + o), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(st + STAGE / 2 + o), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+            }
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t st = sbase + Fwd::WB + (c & 1) * STAGE;
+            constexpr uint32_t idesc = make_idesc(false, !BT);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                const int kg = c * KC + ks * 8;
+                const uint32_t a_off = (uint32_t)(kg >> 5) * ATOM + (uint32_t)((kg & 31) >> 3) * 32;
+                const uint64_t a_hi_d = make_desc(a_hi + a_off, 16, 1024, 2);
+                uint64_t b_hi, b_lo;
+                if (!BT) {
+                    b_hi = make_desc(st + ks * 2 * 4096, 512, 4096, 1);
+                    b_lo = make_desc(st + STAGE / 2 + ks * 2 * 4096, 512, 4096, 1);
+                } else {
+                    b_hi = make_desc(st + ks * 32, 16, 512, 4);
+                    b_lo = make_desc(st + STAGE / 2 + ks * 32, 16, 512, 4);
+                }
+                uint32_t acc = (c | ks) ? 1u : 0u;
+                if (PASSES == 3) {                           // small terms first
+                    if (a_lo_smem) mma_ss(tmem, make_desc(a_lo_smem + a_off, 16, 1024, 2), b_hi, idesc, acc);
+                    else mma_ts(tmem, a_lo_tmem + (uint32_t)kg, b_hi, idesc, acc);
+                    mma_ss(tmem, a_hi_d, b_lo, idesc, 1u);
+                    acc = 1u;
+                }
+                mma_ss(tmem, a_hi_d, b_hi, idesc, acc);
+            }
+            umma_commit(bar0 + 8 * (c & 1));
+        }
+        uses[c & 1] += 1;
+    }
+    // all MMAs of this GEMM complete (commit tracks every earlier MMA of the issuing thread)
+    const int last = (nchunks - 1) & 1;
+    ok &= mbar_wait(bar0 + 8 * last, (uses[last] - 1) & 1);
+    tc_fence_after();
+    return ok;
+}
+
+// Gather 128 observation rows -> hi (R) and lo (R + XLO), K-major SW128; rows past the batch are zero.
+template <int PASSES>
+__device__ __forceinline__ void gather_x(uint32_t sbase, const float* __restrict__ ring, const int32_t* __restrict__ rows,
+                                         int r0, int B, int Dp) {
+    const int q = Dp >> 2;
+    for (int f = threadIdx.x; f < BM * q; f += NT) {
+        const int i = f / q, k = (f % q) << 2;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f), hi, lo;
+        if (r0 + i < B) x = __ldg(reinterpret_cast<const float4*>(ring + (size_t)rows[r0 + i] * Dp + k));
+        split4<PASSES>(x, hi, lo);
+        const uint32_t o = off_k128(BM, i, k);
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sbase + Fwd::R + o), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+        if (PASSES == 3)
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sbase + Fwd::XLO + o), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+    }
+}
+
+// Per-thread epilogue coordinates: thread = batch row of the tile, two warps share a TMEM
+// sub-partition and split the 256 columns in halves.
+struct Epi {
+    int row, half;
+    uint32_t lane_addr;
+    __device__ __forceinline__ Epi() {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        row = (warp & 3) * 32 + lane;
+        half = warp >> 2;
+        lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    }
+};
+
+// Epilogue of a hidden layer feeding another GEMM: a = relu(D + bias) (or D * mask for dh2 built by
+// the caller); hi -> shared memory R (next A operand), lo -> TMEM columns 256.., raw -> global (optional),
+// returns the relu mask bits of this thread's 128 columns.
+template <int PASSES>
+__device__ __forceinline__ void epi_hidden(uint32_t sbase, uint32_t tmem, const Epi& e, uint32_t bias_off,
+                                           float* __restrict__ gout_row, uint32_t (&mask)[4]) {
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+        const int c0 = e.half * 128 + cc * 32;
+        float v[32], lo[32];
+        tmem_ld32(tmem + e.lane_addr + (uint32_t)c0, v);
+        uint32_t m = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            float4 b;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                         : "r"(sbase + bias_off + (uint32_t)(c0 + j) * 4));
+            float4 x = make_float4(fmaxf(v[j] + b.x, 0.f), fmaxf(v[j + 1] + b.y, 0.f), fmaxf(v[j + 2] + b.z, 0.f),
+                                   fmaxf(v[j + 3] + b.w, 0.f));
+            m |= (x.x > 0.f ? 1u : 0u) << j | (x.y > 0.f ? 1u : 0u) << (j + 1) | (x.z > 0.f ? 1u : 0u) << (j + 2) |
+                 (x.w > 0.f ? 1u : 0u) << (j + 3);
+            if (gout_row) *reinterpret_cast<float4*>(gout_row + c0 + j) = x;
+            float4 hi, l4;
+            split4<PASSES>(x, hi, l4);
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sbase + Fwd::R + off_k128(BM, e.row, c0 + j)), "f"(hi.x),
+                         "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+            lo[j] = l4.x; lo[j + 1] = l4.y; lo[j + 2] = l4.z; lo[j + 3] = l4.w;
+        }
+        mask[cc] = m;
+        if (PASSES == 3) tmem_st32(tmem + e.lane_addr + 256u + (uint32_t)c0, lo);
+    }
+    if (PASSES == 3) tmem_st_wait();
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+}
+
+// Epilogue of layer 2 feeding the 4-wide head: q[a] = b3[a] + sum_j relu(D[j] + b2[j]) * W3[j][a]; the two
+// column halves of a row are combined in fixed order through shared memory.  Optionally stores the raw
+// h2 row (for dW3) and returns the relu mask.
+__device__ __forceinline__ void epi_head(uint32_t sbase, uint32_t tmem, const Epi& e, float* __restrict__ h2_row,
+                                         uint32_t (&mask)[4], float (&q)[4], const float* __restrict__ b3) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+        const int c0 = e.half * 128 + cc * 32;
+        float v[32];
+        tmem_ld32(tmem + e.lane_addr + (uint32_t)c0, v);
+        uint32_t m = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float b;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(b) : "r"(sbase + Fwd::BIAS2 + (uint32_t)(c0 + j) * 4));
+            const float x = fmaxf(v[j] + b, 0.f);
+            v[j] = x;
+            m |= (x > 0.f ? 1u : 0u) << j;
+            float4 w;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w)
+                         : "r"(sbase + Fwd::W3S + (uint32_t)(c0 + j) * 16));
+            acc.x = fmaf(x, w.x, acc.x); acc.y = fmaf(x, w.y, acc.y);
+            acc.z = fmaf(x, w.z, acc.z); acc.w = fmaf(x, w.w, acc.w);
+        }
+        mask[cc] = m;
+        if (h2_row) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(h2_row + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+    }
+    float4* qp = reinterpret_cast<float4*>(__cvta_shared_to_generic((size_t)(sbase + Fwd::QP)));
+    qp[e.half * BM + e.row] = acc;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const float4 p0 = qp[e.row], p1 = qp[BM + e.row];
+    q[0] = (p0.x + p1.x) + __ldg(b3 + 0); q[1] = (p0.y + p1.y) + __ldg(b3 + 1);
+    q[2] = (p0.z + p1.z) + __ldg(b3 + 2); q[3] = (p0.w + p1.w) + __ldg(b3 + 3);
+}
+
+__device__ __forceinline__ void load_small_params(uint32_t sbase, const float* __restrict__ P, const Layout& L) {
+    float* s = reinterpret_cast<float*>(__cvta_shared_to_generic((size_t)sbase));
+    for (int j = threadIdx.x; j < H; j += NT) {
+        s[Fwd::BIAS1 / 4 + j] = __ldg(P + L.b1 + j);
+        s[Fwd::BIAS2 / 4 + j] = __ldg(P + L.b2 + j);
+        reinterpret_cast<float4*>(s + Fwd::W3S / 4)[j] = __ldg(reinterpret_cast<const float4*>(P + L.w3) + j);
+    }
+}
+
+__device__ __forceinline__ uint32_t tc_prologue(uint32_t sbase) {
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        mbar_init(sbase + Fwd::BARS, 1);
+        mbar_init(sbase + Fwd::BARS + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + Fwd::BARS + 16), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(sbase + Fwd::BARS + 16));
+    return tmem;
+}
+__device__ __forceinline__ void tc_epilogue(uint32_t tmem) {
+    tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+// ------------------------------------------------------------------------------------------
+// K3
+// ------------------------------------------------------------------------------------------
+template <int PASSES>
+__global__ void __launch_bounds__(NT, 1) tc_target_kernel(const TcArgs A) {
+    extern __shared__ uint8_t smem_raw[];
+    const int g = blockIdx.x / A.tiles, rt = blockIdx.x % A.tiles;
+    if (!A.active[g]) return;
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int B = A.d.batch, Dp = A.d.obs_stride, r0 = rt * BM;
+    const int32_t* rows = A.rows + (size_t)g * B;
+    const uint32_t tmem = tc_prologue(sbase);
+    const Epi e;
+    uint32_t uses[2] = {0, 0};
+    bool ok = true;
+    float q_on[4], q_tg[4];
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        const float* P = (pass == 0 ? A.nets.theta : A.nets.theta_tgt) + (size_t)g * A.L.stride;
+        gather_x<PASSES>(sbase, A.rp.next_obs, rows, r0, B, Dp);
+        load_small_params(sbase, P, A.L);
+        ok &= gemm_stream<PASSES, false>(sbase, tmem, sbase + Fwd::R, sbase + Fwd::XLO, 0, P + A.L.w1, H, Dp, uses);
+        uint32_t mask[4];
+        epi_hidden<PASSES>(sbase, tmem, e, Fwd::BIAS1, nullptr, mask);
+        ok &= gemm_stream<PASSES, false>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, P + A.L.w2, H, H, uses);
+        epi_head(sbase, tmem, e, nullptr, mask, pass == 0 ? q_on : q_tg, P + A.L.b3);
+        __syncthreads();   // q partials consumed; R / TMEM free for the next pass
+    }
+    const int gr = r0 + e.row;
+    if (e.half == 0 && gr < B) {
+        int best = 0;
+        float tmax = q_tg[0];
+        for (int k = 1; k < A.d.n_actions; ++k) {
+            if (q_on[k] > q_on[best]) best = k;
+            tmax = fmaxf(tmax, q_tg[k]);
+        }
+        const float tq = A.double_dqn ? q_tg[best] : tmax;
+        const size_t o = (size_t)g * B + gr;
+        A.y[o] = A.r_hat[o] + (A.gamma * (1.0f - A.done_b[o])) * tq;
+        for (int k = 0; k < 4; ++k) {
+            A.q_next[o * 4 + k] = q_on[k];
+            A.tq_all[o * 4 + k] = q_tg[k];
+        }
+    }
+    if (!ok && threadIdx.x == 0) atomicExch(A.error, 3);
+    tc_epilogue(tmem);
+}
+
+// ------------------------------------------------------------------------------------------
+// K4a
+// ------------------------------------------------------------------------------------------
+template <int PASSES>
+__global__ void __launch_bounds__(NT, 1) tc_online_kernel(const TcArgs A) {
+    extern __shared__ uint8_t smem_raw[];
+    const int g = blockIdx.x / A.tiles, rt = blockIdx.x % A.tiles;
+    if (!A.active[g]) return;
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    float* sf = reinterpret_cast<float*>(__cvta_shared_to_generic((size_t)sbase));
+    const int B = A.d.batch, Dp = A.d.obs_stride, r0 = rt * BM;
+    const size_t sb = (size_t)g * B;
+    const int32_t* rows = A.rows + sb;
+    const float* P = A.nets.theta + (size_t)g * A.L.stride;
+    const uint32_t tmem = tc_prologue(sbase);
+    const Epi e;
+    const int gr = r0 + e.row;
+    const bool valid = gr < B;
+    uint32_t uses[2] = {0, 0};
+    bool ok = true;
+
+    gather_x<PASSES>(sbase, A.rp.obs, rows, r0, B, Dp);
+    load_small_params(sbase, P, A.L);
+    ok &= gemm_stream<PASSES, false>(sbase, tmem, sbase + Fwd::R, sbase + Fwd::XLO, 0, P + A.L.w1, H, Dp, uses);
+    uint32_t mask1[4], mask2[4];
+    epi_hidden<PASSES>(sbase, tmem, e, Fwd::BIAS1, valid ? A.h1 + (sb + gr) * H : nullptr, mask1);
+    ok &= gemm_stream<PASSES, false>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, P + A.L.w2, H, H, uses);
+    float q[4];
+    epi_head(sbase, tmem, e, valid ? A.h2 + (sb + gr) * H : nullptr, mask2, q, P + A.L.b3);
+
+    // loss term and dL/dpred of this row (reference :349-352)
+    float gi = 0.f, term = 0.f;
+    int ai = 0;
+    if (valid) {
+        ai = A.act_b[sb + gr];
+        const float err = q[ai] - A.y[sb + gr];
+        if (A.loss == DMDQN_LOSS_MSE) {
+            term = err * err;
+            gi = (2.0f * err) / (float)A.loss_batch;
+        } else {
+            const float ae = fabsf(err);
+            term = ae <= 1.0f ? 0.5f * err * err : ae - 0.5f;
+            gi = fminf(fmaxf(err, -1.0f), 1.0f) / (float)A.loss_batch;
+        }
+        if (e.half == 0) {
+            A.gcoef[sb + gr] = gi;
+            for (int k = 0; k < 4; ++k) A.q_all[(sb + gr) * 4 + k] = q[k];
+        }
+    }
+    float* rowf = sf + Fwd::ROWF / 4;                     // [0]: loss term, [1..4]: q per row
+    if (e.half == 0) {
+        rowf[e.row] = term;
+        for (int k = 0; k < 4; ++k) rowf[(1 + k) * BM + e.row] = valid ? q[k] : 0.f;
+        reinterpret_cast<int*>(rowf)[5 * BM + e.row] = valid ? ai : -1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                               // per-tile loss / metric partials, rows in order
+        float ls = 0.f, qsum = 0.f, qsq = 0.f, hist[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int i = 0; i < BM && r0 + i < B; ++i) {
+            ls += rowf[i];
+            for (int k = 0; k < A.d.n_actions; ++k) {
+                const float qq = rowf[(1 + k) * BM + i];
+                qsum += qq;
+                qsq = fmaf(qq, qq, qsq);
+            }
+            const int a = reinterpret_cast<int*>(rowf)[5 * BM + i];
+            hist[0] += a == 0; hist[1] += a == 1; hist[2] += a == 2; hist[3] += a == 3;
+        }
+        float* pl = A.part_loss + ((size_t)g * A.tiles + rt) * 8;
+        pl[0] = ls; pl[1] = qsum; pl[2] = qsq; pl[3] = hist[0]; pl[4] = hist[1]; pl[5] = hist[2]; pl[6] = hist[3]; pl[7] = 0.f;
+    }
+
+    // dh2[j] = relu'(h2[j]) * g * W3[j][a]  (dq has one non-zero per row): hi -> R, lo -> TMEM, raw -> scratch
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+        const int c0 = e.half * 128 + cc * 32;
+        float lo[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            float x[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                float w;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w) : "r"(sbase + Fwd::W3S + (uint32_t)(c0 + j + t) * 16 + (uint32_t)ai * 4));
+                x[t] = ((mask2[cc] >> (j + t)) & 1u) ? gi * w : 0.f;
+            }
+            const float4 x4 = make_float4(x[0], x[1], x[2], x[3]);
+            if (valid) *reinterpret_cast<float4*>(A.dh2 + (sb + gr) * H + c0 + j) = x4;
+            float4 hi, l4;
+            split4<PASSES>(x4, hi, l4);
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sbase + Fwd::R + off_k128(BM, e.row, c0 + j)), "f"(hi.x),
+                         "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+            lo[j] = l4.x; lo[j + 1] = l4.y; lo[j + 2] = l4.z; lo[j + 3] = l4.w;
+        }
+        if (PASSES == 3) tmem_st32(tmem + e.lane_addr + 256u + (uint32_t)c0, lo);
+    }
+    if (PASSES == 3) tmem_st_wait();
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    // dh1 = (dh2 W2^T) * relu'(h1)
+    ok &= gemm_stream<PASSES, true>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, P + A.L.w2, H, H, uses);
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+        const int c0 = e.half * 128 + cc * 32;
+        float v[32];
+        tmem_ld32(tmem + e.lane_addr + (uint32_t)c0, v);
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(A.dh1 + (sb + gr) * H + c0 + j) =
+                    make_float4(((mask1[cc] >> j) & 1u) ? v[j] : 0.f, ((mask1[cc] >> (j + 1)) & 1u) ? v[j + 1] : 0.f,
+                                ((mask1[cc] >> (j + 2)) & 1u) ? v[j + 2] : 0.f, ((mask1[cc] >> (j + 3)) & 1u) ? v[j + 3] : 0.f);
+        }
+    }
+    if (!ok && threadIdx.x == 0) atomicExch(A.error, 4);
+    tc_epilogue(tmem);
+}
+
+// ------------------------------------------------------------------------------------------
+// K4b
+// ------------------------------------------------------------------------------------------
+struct AdamK {
+    float alpha, eps, omb1, omb2, tau;
+    int sync;
+};
+__device__ __forceinline__ AdamK adam_k(const TcArgs& A, int t) {
+    AdamK k;
+    const double bc1 = 1.0 - pow(A.beta1, (double)t), bc2 = 1.0 - pow(A.beta2, (double)t);
+    k.alpha = (float)(A.lr * sqrt(bc2) / bc1);
+    k.eps = (float)(A.adam_form == DMDQN_ADAM_KERAS ? A.adam_eps : A.adam_eps * sqrt(bc2));
+    k.omb1 = (float)(1.0 - A.beta1);
+    k.omb2 = (float)(1.0 - A.beta2);
+    k.tau = (float)A.tau;
+    k.sync = A.tau >= 0.0 ? 2 : (t % A.freq == 0 ? 1 : 0);
+    return k;
+}
+__device__ __forceinline__ void adam1(const AdamK& k, float g, float& th, float& m, float& v, float& tg) {
+    m = m + (g - m) * k.omb1;
+    v = v + (g * g - v) * k.omb2;
+    th = th - (m * k.alpha) / (sqrtf(v) + k.eps);
+    if (k.sync == 1) tg = th;
+    else if (k.sync == 2) tg = k.tau * th + (1.0f - k.tau) * tg;
+}
+
+struct Wg {     // shared-memory carve-up of the wgrad kernel: 3 stages of (A hi|lo 16 KB, B hi|lo 32 KB)
+    static constexpr int STAGES = 3;
+    static constexpr uint32_t A_BYTES = KC * BM * 4;          // 8 KB
+    static constexpr uint32_t B_BYTES = KC * H * 4;           // 16 KB
+    static constexpr uint32_t STG = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr uint32_t BARS = STAGES * STG;
+    static constexpr uint32_t TOTAL = BARS + 64;
+};
+
+template <int PASSES>
+__global__ void __launch_bounds__(NT, 1) tc_wgrad_kernel(const TcArgs A) {
+    extern __shared__ uint8_t smem_raw[];
+    const int B = A.d.batch, Dp = A.d.obs_stride;
+    constexpr int per_net = 4;                                // dW2 rows 0..127, 128..255; dW1; misc
+    const int g = blockIdx.x / per_net, t = blockIdx.x % per_net;
+    const size_t sb = (size_t)g * B;
+    const size_t pb = (size_t)g * A.L.stride;
+    float* th = A.nets.theta + pb;
+    float* tg = A.nets.theta_tgt + pb;
+    float* am = A.nets.adam_m + pb;
+    float* av = A.nets.adam_v + pb;
+    const int tid = threadIdx.x;
+
+    if (t == per_net - 1) {
+        // misc tile: biases and the head from the activation-gradient scratch, batch rows in order
+        if (!A.active[g]) {
+            if (tid < DMDQN_METRICS_STRIDE && A.metrics) A.metrics[g * DMDQN_METRICS_STRIDE + tid] = 0.f;
+            return;
+        }
+        const AdamK k = adam_k(A, A.step_t[g]);
+        float* sg = reinterpret_cast<float*>(smem_raw);       // g_i [B], then a_i [B]
+        int* sa = reinterpret_cast<int*>(sg + B);
+        for (int i = tid; i < B; i += NT) { sg[i] = A.gcoef[sb + i]; sa[i] = A.act_b[sb + i]; }
+        __syncthreads();
+        const int j = tid;                                    // column (NT == H)
+        float s1 = 0.f, s2 = 0.f, w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+#pragma unroll 4
+        for (int i = 0; i < B; ++i) {
+            s1 += A.dh1[(sb + i) * H + j];
+            s2 += A.dh2[(sb + i) * H + j];
+            const float tv = A.h2[(sb + i) * H + j] * sg[i];
+            const int a = sa[i];
+            w0 += a == 0 ? tv : 0.f; w1 += a == 1 ? tv : 0.f; w2 += a == 2 ? tv : 0.f; w3 += a == 3 ? tv : 0.f;
+        }
+        const float gw[4] = {w0, w1, w2, w3};
+        auto upd = [&](int64_t off, float grad) {
+            if (A.grads) { A.grads[pb + off] = grad; return; }
+            float tgv = k.sync == 2 ? tg[off] : 0.f;
+            adam1(k, grad, th[off], am[off], av[off], tgv);
+            if (k.sync) tg[off] = tgv;
+        };
+        upd(A.L.b1 + j, s1);
+        upd(A.L.b2 + j, s2);
+        for (int a = 0; a < 4; ++a) upd(A.L.w3 + (int64_t)j * 4 + a, gw[a]);
+        if (tid < 4) {
+            float s = 0.f;
+            for (int i = 0; i < B; ++i) s += sa[i] == tid ? sg[i] : 0.f;
+            upd(A.L.b3 + tid, s);
+        }
+        if (tid == 0 && A.metrics) {
+            double ls = 0, qs = 0, qq = 0, hist[4] = {0, 0, 0, 0};
+            for (int r = 0; r < A.tiles; ++r) {
+                const float* pl = A.part_loss + ((size_t)g * A.tiles + r) * 8;
+                ls += pl[0]; qs += pl[1]; qq += pl[2];
+                for (int a = 0; a < 4; ++a) hist[a] += pl[3 + a];
+            }
+            const double cnt = (double)B * A.d.n_actions, mean = qs / cnt, var = fmax(qq / cnt - mean * mean, 0.0);
+            float* m = A.metrics + g * DMDQN_METRICS_STRIDE;
+            m[0] = (float)(ls / A.loss_batch); m[1] = (float)mean; m[2] = (float)sqrt(var);
+            for (int a = 0; a < 4; ++a) m[3 + a] = (float)hist[a];
+            m[7] = 1.f;
+        }
+        return;
+    }
+    if (!A.active[g]) return;
+
+    // GEMM tile: D[128 x 256] = Asrc[:, m0:m0+128]^T * Dsrc, K = batch.  Both operands MN-major.
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const bool is_w2 = t < 2;
+    const int m0 = is_w2 ? t * BM : 0;
+    const int m_valid = is_w2 ? H : Dp;
+    const float* Asrc = is_w2 ? A.h1 + sb * H : A.rp.obs;
+    const float* Dsrc = (is_w2 ? A.dh2 : A.dh1) + sb * H;
+    const int lda = is_w2 ? H : Dp;
+    const int32_t* rows = A.rows + sb;
+
+    const int warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < Wg::STAGES; ++s) mbar_init(sbase + Wg::BARS + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + Wg::BARS + 32), "r"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(sbase + Wg::BARS + 32));
+
+    const int nchunks = (B + KC - 1) / KC;
+    uint32_t uses[Wg::STAGES] = {0, 0, 0};
+    bool ok = true;
+    auto issue = [&](int c) {
+        const uint32_t st = sbase + (c % Wg::STAGES) * Wg::STG;
+        // A chunk: 16 k x 128 m floats = 512 pieces, threads 0..255 take 2; B chunk: 1024 pieces, 4 each
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int p = tid + r * NT;
+            const int kk = p >> 5, m = (p & 31) << 2;
+            const int kr = c * KC + kk;
+            const bool v = kr < B && m0 + m < m_valid;
+            const size_t srow = v ? (is_w2 ? (size_t)kr : (size_t)rows[kr]) : 0;
+            cp16(st + off_mn(BM, kk, m), Asrc + srow * lda + (v ? m0 + m : 0), v);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int p = tid + r * NT;
+            const int kk = p >> 6, n = (p & 63) << 2;
+            const bool v = c * KC + kk < B;
+            cp16(st + 2 * Wg::A_BYTES + off_mn(H, kk, n), Dsrc + (size_t)(v ? c * KC + kk : 0) * H + n, v);
+        }
+    };
+    issue(0);
+    cp_commit();
+    if (nchunks > 1) issue(1);
+    cp_commit();
+    for (int c = 0; c < nchunks; ++c) {
+        if (c + 2 < nchunks) {
+            const int b = (c + 2) % Wg::STAGES;
+            if (uses[b]) ok &= mbar_wait(sbase + Wg::BARS + 8 * b, (uses[b] - 1) & 1);
+            issue(c + 2);
+        }
+        cp_commit();
+        cp_wait<2>();
+        const uint32_t st = sbase + (c % Wg::STAGES) * Wg::STG;
+        if (PASSES == 3) {
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                uint32_t o;
+                if (r < 2) { const int p = tid + r * NT; o = off_mn(BM, p >> 5, (p & 31) << 2); }
+                else { const int p = tid + (r - 2) * NT; o = 2 * Wg::A_BYTES + off_mn(H, p >> 6, (p & 63) << 2); }
+                const uint32_t lo_off = r < 2 ? Wg::A_BYTES : Wg::B_BYTES;
+                float4 x, hi, lo;
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(st + o));
+                split4<3>(x, hi, lo);
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(st + o), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(st + lo_off + o), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+            }
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            constexpr uint32_t idesc = make_idesc(true, true);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                // A: 4 m-groups per k-group -> k-group stride 2048 B; B: 8 n-groups -> 4096 B
+                const uint64_t a_hi = make_desc(st + ks * 2 * 2048, 512, 2048, 1);
+                const uint64_t a_lo = make_desc(st + Wg::A_BYTES + ks * 2 * 2048, 512, 2048, 1);
+                const uint64_t b_hi = make_desc(st + 2 * Wg::A_BYTES + ks * 2 * 4096, 512, 4096, 1);
+                const uint64_t b_lo = make_desc(st + 2 * Wg::A_BYTES + Wg::B_BYTES + ks * 2 * 4096, 512, 4096, 1);
+                uint32_t acc = (c | ks) ? 1u : 0u;
+                if (PASSES == 3) {
+                    mma_ss(tmem, a_lo, b_hi, idesc, acc);
+                    mma_ss(tmem, a_hi, b_lo, idesc, 1u);
+                    acc = 1u;
+                }
+                mma_ss(tmem, a_hi, b_hi, idesc, acc);
+            }
+            umma_commit(sbase + Wg::BARS + 8 * (c % Wg::STAGES));
+        }
+        uses[c % Wg::STAGES] += 1;
+    }
+    {
+        const int last = (nchunks - 1) % Wg::STAGES;
+        ok &= mbar_wait(sbase + Wg::BARS + 8 * last, (uses[last] - 1) & 1);
+        tc_fence_after();
+    }
+
+    // epilogue: thread = weight row m (Adam on 128 of its 256 columns)
+    const AdamK k = adam_k(A, A.step_t[g]);
+    const Epi e;
+    const int m = m0 + e.row;
+    const int64_t wbase = is_w2 ? A.L.w2 : A.L.w1;
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+        const int c0 = e.half * 128 + cc * 32;
+        float v[32];
+        tmem_ld32(tmem + e.lane_addr + (uint32_t)c0, v);
+        if (m < m_valid) {
+            const int64_t off = wbase + (int64_t)m * H + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                if (A.grads) {
+                    *reinterpret_cast<float4*>(A.grads + pb + off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    continue;
+                }
+                float4 t4 = *reinterpret_cast<float4*>(th + off + j), m4 = *reinterpret_cast<float4*>(am + off + j);
+                float4 v4 = *reinterpret_cast<float4*>(av + off + j);
+                float4 g4 = k.sync == 2 ? *reinterpret_cast<float4*>(tg + off + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                adam1(k, v[j], t4.x, m4.x, v4.x, g4.x); adam1(k, v[j + 1], t4.y, m4.y, v4.y, g4.y);
+                adam1(k, v[j + 2], t4.z, m4.z, v4.z, g4.z); adam1(k, v[j + 3], t4.w, m4.w, v4.w, g4.w);
+                *reinterpret_cast<float4*>(th + off + j) = t4;
+                *reinterpret_cast<float4*>(am + off + j) = m4;
+                *reinterpret_cast<float4*>(av + off + j) = v4;
+                if (k.sync) *reinterpret_cast<float4*>(tg + off + j) = g4;
+            }
+        }
+    }
+    if (!ok && tid == 0) atomicExch(A.error, 5);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
+}
+
+template <int PASSES>
+int launch_tc(const TcArgs& A, int stages, cudaStream_t s) {
+    const size_t smem_f = Fwd::TOTAL + 1024, smem_w = Wg::TOTAL + 1024;
+    static bool configured = false;
+    if (!configured) {
+        DMDQN_CUDA(cudaFuncSetAttribute(tc_target_kernel<PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+        DMDQN_CUDA(cudaFuncSetAttribute(tc_online_kernel<PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+        DMDQN_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+        configured = true;
+    }
+    const int grid = A.d.n_nets * A.tiles;
+    if (stages & DMDQN_STAGE_TARGET) {
+        tc_target_kernel<PASSES><<<grid, NT, smem_f, s>>>(A);
+        DMDQN_CUDA(cudaGetLastError());
+    }
+    if (stages & DMDQN_STAGE_ONLINE) {
+        tc_online_kernel<PASSES><<<grid, NT, smem_f, s>>>(A);
+        DMDQN_CUDA(cudaGetLastError());
+    }
+    if (stages & DMDQN_STAGE_WGRAD) {
+        tc_wgrad_kernel<PASSES><<<A.d.n_nets * 4, NT, smem_w, s>>>(A);
+        DMDQN_CUDA(cudaGetLastError());
+    }
+    return DMDQN_OK;
+}
+
+}  // namespace
+
+bool tc_supported(const dmdqn_dims& d) {
+    return d.hidden == H && d.obs_stride % 32 == 0 && d.obs_stride <= 96 && d.batch >= 1 && d.batch * 8 <= 200 * 1024;
+}
+
+int launch_learn_tc(const dmdqn_dims& d, const dmdqn_hparams& hp, const dmdqn_replay& rp, const dmdqn_nets& nets,
+                    float* metrics, char* ws, const Workspace& w, int stages, float* grads, int loss_batch,
+                    cudaStream_t s) {
+    TcArgs A;
+    A.d = d;
+    A.L = make_layout(d.obs_stride, d.hidden);
+    A.rp = rp;
+    A.nets = nets;
+    A.gamma = (float)hp.gamma;
+    A.loss = hp.loss;
+    A.double_dqn = hp.double_dqn;
+    A.adam_form = hp.adam_form;
+    A.freq = hp.target_update_frequency > 0 ? hp.target_update_frequency : 1;
+    A.loss_batch = loss_batch > 0 ? loss_batch : d.batch;
+    A.tiles = (d.batch + BM - 1) / BM;
+    A.lr = hp.learning_rate; A.beta1 = hp.beta1; A.beta2 = hp.beta2; A.adam_eps = hp.adam_eps; A.tau = hp.tau;
+    A.rows = reinterpret_cast<const int32_t*>(ws + w.rows);
+    A.act_b = reinterpret_cast<const int32_t*>(ws + w.act_b);
+    A.active = reinterpret_cast<const int32_t*>(ws + w.active);
+    A.step_t = reinterpret_cast<const int32_t*>(ws + w.step_t);
+    A.r_hat = reinterpret_cast<const float*>(ws + w.r_hat);
+    A.done_b = reinterpret_cast<const float*>(ws + w.done_b);
+    A.y = reinterpret_cast<float*>(ws + w.y);
+    A.gcoef = reinterpret_cast<float*>(ws + w.gcoef);
+    A.q_all = reinterpret_cast<float*>(ws + w.q_all);
+    A.q_next = reinterpret_cast<float*>(ws + w.q_next);
+    A.tq_all = reinterpret_cast<float*>(ws + w.tq_all);
+    A.h1 = reinterpret_cast<float*>(ws + w.h1);
+    A.h2 = reinterpret_cast<float*>(ws + w.h2);
+    A.dh1 = reinterpret_cast<float*>(ws + w.dh1);
+    A.dh2 = reinterpret_cast<float*>(ws + w.dh2);
+    A.part_loss = reinterpret_cast<float*>(ws + w.part_loss);
+    A.metrics = metrics;
+    A.grads = grads;
+    A.error = reinterpret_cast<int*>(ws + w.tc_error);
+    return hp.precision == DMDQN_PRECISION_TF32 ? launch_tc<1>(A, stages, s) : launch_tc<3>(A, stages, s);
+}
+
+}  // namespace dmdqn

@@ -347,7 +347,8 @@ class AgentGroup:
         return {"y": view(v.y, torch.float32, (g, b)), "q_all": view(v.q_all, torch.float32, (g, b, 4)),
                 "q_next": view(v.q_next, torch.float32, (g, b, 4)), "tq_all": view(v.tq_all, torch.float32, (g, b, 4)),
                 "rows": view(v.rows, torch.int32, (g, b)), "r_hat": view(v.r_hat, torch.float32, (g, b)),
-                "active": view(v.active, torch.int32, (g,))}
+                "active": view(v.active, torch.int32, (g,)), "tc_error": view(v.tc_error, torch.int32, (1,)),
+                "dh1": view(v.dh1, torch.float32, (g, b, self.hidden)), "dh2": view(v.dh2, torch.float32, (g, b, self.hidden))}
 
     def sync_target(self, mask=None, tau: float | None = None) -> None:
         """update_target_network (tau None, dqn_agent.py:382-384) / soft update (:389-399)."""

@@ -60,8 +60,10 @@ extern "C" {
 #define DMDQN_ADAM_KERAS 0      /* eps = adam_eps                       (keras 3.9.2)      */
 #define DMDQN_ADAM_TORCH 1      /* eps = adam_eps * sqrt(1 - beta2^t)   (torch.optim.Adam) */
 
-#define DMDQN_PRECISION_FP32 0  /* FFMA, fp32 accumulate: the 1e-5 parity path            */
-#define DMDQN_PRECISION_TF32 1  /* tcgen05 kind::tf32 on the HxH contractions (toleranced) */
+#define DMDQN_PRECISION_FP32   0 /* FFMA, fp32 accumulate                                                   */
+#define DMDQN_PRECISION_TF32   1 /* tcgen05 kind::tf32, one MMA per product (~1e-3; toleranced separately)   */
+#define DMDQN_PRECISION_TF32X3 2 /* tcgen05 kind::tf32, error-compensated hi/lo split, 3 MMAs per product:   */
+                                 /* fp32-class accuracy on the tensor cores (H = 256 only)                   */
 
 #define DMDQN_MAX_ACTIONS 4
 #define DMDQN_OWN_DIM 17        /* order_lanes.py:430-499 */
@@ -236,6 +238,8 @@ int dmdqn_adam_apply(const dmdqn_dims* dims, const dmdqn_hparams* hp, const dmdq
 typedef struct dmdqn_debug_views {
     const float* y; const float* q_all; const float* q_next; const float* tq_all;
     const int32_t* rows; const float* r_hat; const int32_t* active;
+    const int32_t* tc_error;   /* != 0: a tcgen05 kernel's bounded mbarrier wait expired (results invalid) */
+    const float* dh1; const float* dh2;   /* [n_nets][B][H] activation gradients of the last step */
 } dmdqn_debug_views;
 int dmdqn_debug(const dmdqn_dims* dims, void* workspace, size_t workspace_bytes, dmdqn_debug_views* out);
 

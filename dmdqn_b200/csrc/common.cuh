@@ -60,7 +60,7 @@ inline int row_tiles(int batch, int bm) { return (batch + bm - 1) / bm; }
 // Workspace carve-up (device scratch of sample/learn), offsets in bytes, 256-aligned.
 struct Workspace {
     size_t rows, r_hat, act_b, done_b, active, step_t, y, gcoef, q_all, q_next, tq_all;
-    size_t h1, h2, dh1, dh2;          // [n_nets][B][H] floats each (h2 only used by the tcgen05 path)
+    size_t h1, dh1, dh2;              // [n_nets][B][H] floats each ([H][B] per network on the tcgen05 path)
     size_t tc_error;                  // int: set by a tcgen05 kernel whose mbarrier wait timed out
     size_t part_loss;                 // [n_nets][T][8]
     size_t part_b3;                   // [n_nets][T][4]
@@ -89,7 +89,6 @@ inline Workspace make_workspace(const dmdqn_dims& d) {
     w.q_next = take(nb * 16);
     w.tq_all = take(nb * 16);
     w.h1 = take(nb * d.hidden * 4);
-    w.h2 = take(nb * d.hidden * 4);
     w.tc_error = take(4);
     w.dh1 = take(nb * d.hidden * 4);
     w.dh2 = take(nb * d.hidden * 4);

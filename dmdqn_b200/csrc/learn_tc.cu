@@ -152,7 +152,7 @@ struct TcArgs {
     double lr, beta1, beta2, adam_eps, tau;
     const int32_t *rows, *act_b, *active, *step_t;
     const float *r_hat, *done_b;
-    float *y, *gcoef, *q_all, *q_next, *tq_all, *h1, *h2, *dh1, *dh2, *part_loss, *metrics, *grads;
+    float *y, *gcoef, *q_all, *q_next, *tq_all, *h1, *dh1, *dh2, *part_loss, *part_b3, *part_w3, *part_b2, *metrics, *grads;
     int* error;
 };
 
@@ -166,7 +166,7 @@ struct Fwd {
     static constexpr uint32_t W3S = BIAS2 + 1024;             // W3[256][4]
     static constexpr uint32_t QP = W3S + 4096;                // q partials [2][128][4]
     static constexpr uint32_t ROWF = QP + 4096;               // per-row words [6][128]: loss term, q[4], action
-    static constexpr uint32_t BARS = ROWF + 4096;             // 2 mbarriers + tmem base
+    static constexpr uint32_t BARS = ROWF + 4096;             // 4 mbarriers + tmem base
     static constexpr uint32_t TOTAL = BARS + 64;
 };
 
@@ -180,71 +180,74 @@ struct Fwd {
 template <int PASSES, bool BT>
 __device__ __forceinline__ bool gemm_stream(uint32_t sbase, uint32_t tmem, uint32_t a_hi, uint32_t a_lo_smem,
                                             uint32_t a_lo_tmem, const float* __restrict__ W, int ldw, int K,
-                                            uint32_t (&uses)[2]) {
+                                            uint32_t (&uses)[4]) {
+    // x.W : 8-row chunks, 4 stages (copies run 3 chunks ahead of the MMAs); d.W^T : 16-column chunks, 2 stages.
+    constexpr int KCX = BT ? 16 : 8;
+    constexpr int NST = BT ? 2 : 4;
+    constexpr uint32_t HALF = KCX * H * 4;                    // bytes of the hi (or lo) part of a stage
+    constexpr int PIECES = KCX * H / 4 / NT;                  // 16-byte pieces per thread per chunk
     const int tid = threadIdx.x;
     const uint32_t bar0 = sbase + Fwd::BARS;
-    const int nchunks = K / KC;
+    const int nchunks = K / KCX;
     bool ok = true;
+    auto piece_off = [&](int p) -> uint32_t {
+        if (!BT) return off_mn(H, p >> 6, (p & 63) << 2);     // k-row p/64, column piece p%64
+        return off_k64(H, p >> 2, (p & 3) << 2);              // row n = p/4, k piece p%4
+    };
     auto issue = [&](int c) {
-        const uint32_t st = sbase + Fwd::WB + (c & 1) * STAGE;
+        const uint32_t st = sbase + Fwd::WB + (c % NST) * (2 * HALF);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
+        for (int r = 0; r < PIECES; ++r) {
             const int p = tid + r * NT;
-            if (!BT) {
-                const int kk = p >> 6, n = (p & 63) << 2;
-                cp16(st + off_mn(H, kk, n), W + (size_t)(c * KC + kk) * ldw + n);
-            } else {
-                const int n = p >> 2, k = (p & 3) << 2;
-                cp16(st + off_k64(H, n, k), W + (size_t)n * ldw + c * KC + k);
-            }
+            if (!BT) cp16(st + piece_off(p), W + (size_t)(c * KCX + (p >> 6)) * ldw + ((p & 63) << 2));
+            else cp16(st + piece_off(p), W + (size_t)(p >> 2) * ldw + c * KCX + ((p & 3) << 2));
         }
     };
-    issue(0);
-    cp_commit();
+#pragma unroll
+    for (int c = 0; c < NST - 1; ++c) {
+        if (c < nchunks) issue(c);
+        cp_commit();
+    }
     for (int c = 0; c < nchunks; ++c) {
-        if (c + 1 < nchunks) {
-            const int b = (c + 1) & 1;
-            if (uses[b]) ok &= mbar_wait(bar0 + 8 * b, (uses[b] - 1) & 1);   // MMAs that read this stage are done
-            issue(c + 1);
+        if (c + NST - 1 < nchunks) {
+            const int b = (c + NST - 1) % NST;                // stage last read by the MMAs of chunk c-1
+            if (uses[b]) ok &= mbar_wait(bar0 + 8 * b, (uses[b] - 1) & 1);
+            issue(c + NST - 1);
         }
         cp_commit();
-        cp_wait<1>();                                        // this thread's pieces of chunk c have landed
-        if (PASSES == 3) {                                   // split them: hi in place, lo beside
-            const uint32_t st = sbase + Fwd::WB + (c & 1) * STAGE;
+        cp_wait<NST - 1>();                                   // this thread's pieces of chunk c have landed
+        const uint32_t st = sbase + Fwd::WB + (c % NST) * (2 * HALF);
+        if (PASSES == 3) {                                    // split them: hi in place, lo beside
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int p = tid + r * NT;
-                uint32_t o;
-                if (!BT) o = off_mn(H, p >> 6, (p & 63) << 2);
-                else o = off_k64(H, p >> 2, (p & 3) << 2);
+            for (int r = 0; r < PIECES; ++r) {
+                const uint32_t o = piece_off(tid + r * NT);
                 float4 x, hi, lo;
                 asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(st + o));
                 split4<3>(x, hi, lo);
                 asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(st + o), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
-                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(st + STAGE / 2 + o), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(st + HALF + o), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
             }
         }
         fence_async_smem();
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
-            const uint32_t st = sbase + Fwd::WB + (c & 1) * STAGE;
             constexpr uint32_t idesc = make_idesc(false, !BT);
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-                const int kg = c * KC + ks * 8;
+            for (int ks = 0; ks < KCX / 8; ++ks) {
+                const int kg = c * KCX + ks * 8;
                 const uint32_t a_off = (uint32_t)(kg >> 5) * ATOM + (uint32_t)((kg & 31) >> 3) * 32;
                 const uint64_t a_hi_d = make_desc(a_hi + a_off, 16, 1024, 2);
                 uint64_t b_hi, b_lo;
-                if (!BT) {
+                if (!BT) {      // MN-major: 8 n-groups per k-group of 4 rows -> 4096 B per k-group
                     b_hi = make_desc(st + ks * 2 * 4096, 512, 4096, 1);
-                    b_lo = make_desc(st + STAGE / 2 + ks * 2 * 4096, 512, 4096, 1);
+                    b_lo = make_desc(st + HALF + ks * 2 * 4096, 512, 4096, 1);
                 } else {
                     b_hi = make_desc(st + ks * 32, 16, 512, 4);
-                    b_lo = make_desc(st + STAGE / 2 + ks * 32, 16, 512, 4);
+                    b_lo = make_desc(st + HALF + ks * 32, 16, 512, 4);
                 }
                 uint32_t acc = (c | ks) ? 1u : 0u;
-                if (PASSES == 3) {                           // small terms first
+                if (PASSES == 3) {                            // small terms first
                     if (a_lo_smem) mma_ss(tmem, make_desc(a_lo_smem + a_off, 16, 1024, 2), b_hi, idesc, acc);
                     else mma_ts(tmem, a_lo_tmem + (uint32_t)kg, b_hi, idesc, acc);
                     mma_ss(tmem, a_hi_d, b_lo, idesc, 1u);
@@ -252,12 +255,12 @@ __device__ __forceinline__ bool gemm_stream(uint32_t sbase, uint32_t tmem, uint3
                 }
                 mma_ss(tmem, a_hi_d, b_hi, idesc, acc);
             }
-            umma_commit(bar0 + 8 * (c & 1));
+            umma_commit(bar0 + 8 * (c % NST));
         }
-        uses[c & 1] += 1;
+        uses[c % NST] += 1;
     }
-    // all MMAs of this GEMM complete (commit tracks every earlier MMA of the issuing thread)
-    const int last = (nchunks - 1) & 1;
+    // all MMAs of this GEMM complete (a commit tracks every earlier MMA of the issuing thread)
+    const int last = (nchunks - 1) % NST;
     ok &= mbar_wait(bar0 + 8 * last, (uses[last] - 1) & 1);
     tc_fence_after();
     return ok;
@@ -296,9 +299,11 @@ struct Epi {
 // Epilogue of a hidden layer feeding another GEMM: a = relu(D + bias) (or D * mask for dh2 built by
 // the caller); hi -> shared memory R (next A operand), lo -> TMEM columns 256.., raw -> global (optional),
 // returns the relu mask bits of this thread's 128 columns.
+// Scratch activations are stored TRANSPOSED, [feature][batch]: a warp's 32 lanes are 32 consecutive
+// batch rows, so every store below is one full 128-byte line, and K4b can stream them K-major.
 template <int PASSES>
 __device__ __forceinline__ void epi_hidden(uint32_t sbase, uint32_t tmem, const Epi& e, uint32_t bias_off,
-                                           float* __restrict__ gout_row, uint32_t (&mask)[4]) {
+                                           float* __restrict__ gout_t, int ldt, uint32_t (&mask)[4]) {
 #pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {
         const int c0 = e.half * 128 + cc * 32;
@@ -314,7 +319,10 @@ __device__ __forceinline__ void epi_hidden(uint32_t sbase, uint32_t tmem, const 
                                    fmaxf(v[j + 3] + b.w, 0.f));
             m |= (x.x > 0.f ? 1u : 0u) << j | (x.y > 0.f ? 1u : 0u) << (j + 1) | (x.z > 0.f ? 1u : 0u) << (j + 2) |
                  (x.w > 0.f ? 1u : 0u) << (j + 3);
-            if (gout_row) *reinterpret_cast<float4*>(gout_row + c0 + j) = x;
+            if (gout_t) {
+                gout_t[(size_t)(c0 + j) * ldt] = x.x; gout_t[(size_t)(c0 + j + 1) * ldt] = x.y;
+                gout_t[(size_t)(c0 + j + 2) * ldt] = x.z; gout_t[(size_t)(c0 + j + 3) * ldt] = x.w;
+            }
             float4 hi, l4;
             split4<PASSES>(x, hi, l4);
             asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sbase + Fwd::R + off_k128(BM, e.row, c0 + j)), "f"(hi.x),
@@ -334,7 +342,7 @@ __device__ __forceinline__ void epi_hidden(uint32_t sbase, uint32_t tmem, const 
 // Epilogue of layer 2 feeding the 4-wide head: q[a] = b3[a] + sum_j relu(D[j] + b2[j]) * W3[j][a]; the two
 // column halves of a row are combined in fixed order through shared memory.  Optionally stores the raw
 // h2 row (for dW3) and returns the relu mask.
-__device__ __forceinline__ void epi_head(uint32_t sbase, uint32_t tmem, const Epi& e, float* __restrict__ h2_row,
+__device__ __forceinline__ void epi_head(uint32_t sbase, uint32_t tmem, const Epi& e, bool keep_h2,
                                          uint32_t (&mask)[4], float (&q)[4], const float* __restrict__ b3) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
@@ -357,10 +365,11 @@ __device__ __forceinline__ void epi_head(uint32_t sbase, uint32_t tmem, const Ep
             acc.z = fmaf(x, w.z, acc.z); acc.w = fmaf(x, w.w, acc.w);
         }
         mask[cc] = m;
-        if (h2_row) {
+        if (keep_h2) {      // raw h2 tile -> R (free once layer 2 has run), read back column-wise for dW3 / db2
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(h2_row + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sbase + Fwd::R + off_k128(BM, e.row, c0 + j)), "f"(v[j]),
+                             "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
         }
     }
     float4* qp = reinterpret_cast<float4*>(__cvta_shared_to_generic((size_t)(sbase + Fwd::QP)));
@@ -385,19 +394,18 @@ __device__ __forceinline__ void load_small_params(uint32_t sbase, const float* _
 __device__ __forceinline__ uint32_t tc_prologue(uint32_t sbase) {
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
-        mbar_init(sbase + Fwd::BARS, 1);
-        mbar_init(sbase + Fwd::BARS + 8, 1);
+        for (int b = 0; b < 4; ++b) mbar_init(sbase + Fwd::BARS + 8 * b, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + Fwd::BARS + 16), "r"(512));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + Fwd::BARS + 32), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     uint32_t tmem;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(sbase + Fwd::BARS + 16));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(sbase + Fwd::BARS + 32));
     return tmem;
 }
 __device__ __forceinline__ void tc_epilogue(uint32_t tmem) {
@@ -419,7 +427,7 @@ __global__ void __launch_bounds__(NT, 1) tc_target_kernel(const TcArgs A) {
     const int32_t* rows = A.rows + (size_t)g * B;
     const uint32_t tmem = tc_prologue(sbase);
     const Epi e;
-    uint32_t uses[2] = {0, 0};
+    uint32_t uses[4] = {0, 0, 0, 0};
     bool ok = true;
     float q_on[4], q_tg[4];
 #pragma unroll 1
@@ -429,9 +437,9 @@ __global__ void __launch_bounds__(NT, 1) tc_target_kernel(const TcArgs A) {
         load_small_params(sbase, P, A.L);
         ok &= gemm_stream<PASSES, false>(sbase, tmem, sbase + Fwd::R, sbase + Fwd::XLO, 0, P + A.L.w1, H, Dp, uses);
         uint32_t mask[4];
-        epi_hidden<PASSES>(sbase, tmem, e, Fwd::BIAS1, nullptr, mask);
+        epi_hidden<PASSES>(sbase, tmem, e, Fwd::BIAS1, nullptr, 0, mask);
         ok &= gemm_stream<PASSES, false>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, P + A.L.w2, H, H, uses);
-        epi_head(sbase, tmem, e, nullptr, mask, pass == 0 ? q_on : q_tg, P + A.L.b3);
+        epi_head(sbase, tmem, e, false, mask, pass == 0 ? q_on : q_tg, P + A.L.b3);
         __syncthreads();   // q partials consumed; R / TMEM free for the next pass
     }
     const int gr = r0 + e.row;
@@ -472,17 +480,17 @@ __global__ void __launch_bounds__(NT, 1) tc_online_kernel(const TcArgs A) {
     const Epi e;
     const int gr = r0 + e.row;
     const bool valid = gr < B;
-    uint32_t uses[2] = {0, 0};
+    uint32_t uses[4] = {0, 0, 0, 0};
     bool ok = true;
 
     gather_x<PASSES>(sbase, A.rp.obs, rows, r0, B, Dp);
     load_small_params(sbase, P, A.L);
     ok &= gemm_stream<PASSES, false>(sbase, tmem, sbase + Fwd::R, sbase + Fwd::XLO, 0, P + A.L.w1, H, Dp, uses);
     uint32_t mask1[4], mask2[4];
-    epi_hidden<PASSES>(sbase, tmem, e, Fwd::BIAS1, valid ? A.h1 + (sb + gr) * H : nullptr, mask1);
+    epi_hidden<PASSES>(sbase, tmem, e, Fwd::BIAS1, valid ? A.h1 + sb * H + gr : nullptr, B, mask1);
     ok &= gemm_stream<PASSES, false>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, P + A.L.w2, H, H, uses);
     float q[4];
-    epi_head(sbase, tmem, e, valid ? A.h2 + (sb + gr) * H : nullptr, mask2, q, P + A.L.b3);
+    epi_head(sbase, tmem, e, true, mask2, q, P + A.L.b3);
 
     // loss term and dL/dpred of this row (reference :349-352)
     float gi = 0.f, term = 0.f;
@@ -508,6 +516,7 @@ __global__ void __launch_bounds__(NT, 1) tc_online_kernel(const TcArgs A) {
         rowf[e.row] = term;
         for (int k = 0; k < 4; ++k) rowf[(1 + k) * BM + e.row] = valid ? q[k] : 0.f;
         reinterpret_cast<int*>(rowf)[5 * BM + e.row] = valid ? ai : -1;
+        rowf[6 * BM + e.row] = gi;
     }
     __syncthreads();
     if (threadIdx.x == 0) {                               // per-tile loss / metric partials, rows in order
@@ -524,7 +533,37 @@ __global__ void __launch_bounds__(NT, 1) tc_online_kernel(const TcArgs A) {
         }
         float* pl = A.part_loss + ((size_t)g * A.tiles + rt) * 8;
         pl[0] = ls; pl[1] = qsum; pl[2] = qsq; pl[3] = hist[0]; pl[4] = hist[1]; pl[5] = hist[2]; pl[6] = hist[3]; pl[7] = 0.f;
+        float db3[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int i = 0; i < BM && r0 + i < B; ++i) {
+            const int a = reinterpret_cast<int*>(rowf)[5 * BM + i];
+            const float gv = rowf[6 * BM + i];
+            db3[0] += a == 0 ? gv : 0.f; db3[1] += a == 1 ? gv : 0.f; db3[2] += a == 2 ? gv : 0.f; db3[3] += a == 3 ? gv : 0.f;
+        }
+        for (int a = 0; a < 4; ++a) A.part_b3[((size_t)g * A.tiles + rt) * 4 + a] = db3[a];
     }
+    {   // dW3[j][a] = sum_i h2[i][j] g_i [a_i = a] and db2[j] = sum_i dh2[i][j] over this tile's rows (in order):
+        // thread = column j, rows read back from the h2 tile left in R by epi_head
+        const int j = threadIdx.x;
+        float4 w3;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w3.x), "=f"(w3.y), "=f"(w3.z), "=f"(w3.w)
+                     : "r"(sbase + Fwd::W3S + (uint32_t)j * 16));
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, s2 = 0.f;
+#pragma unroll 4
+        for (int i = 0; i < BM; ++i) {
+            float h;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(h) : "r"(sbase + Fwd::R + off_k128(BM, i, j)));
+            const float gv = rowf[6 * BM + i];
+            const int a = reinterpret_cast<int*>(rowf)[5 * BM + i];
+            const float tv = h * gv;
+            d0 += a == 0 ? tv : 0.f; d1 += a == 1 ? tv : 0.f; d2 += a == 2 ? tv : 0.f; d3 += a == 3 ? tv : 0.f;
+            const float w = a == 0 ? w3.x : a == 1 ? w3.y : a == 2 ? w3.z : w3.w;
+            s2 += h > 0.f ? gv * w : 0.f;
+        }
+        const size_t pt = (size_t)g * A.tiles + rt;
+        reinterpret_cast<float4*>(A.part_w3 + pt * H * 4)[j] = make_float4(d0, d1, d2, d3);
+        A.part_b2[pt * H + j] = s2;
+    }
+    __syncthreads();      // R is rewritten with dh2 below
 
     // dh2[j] = relu'(h2[j]) * g * W3[j][a]  (dq has one non-zero per row): hi -> R, lo -> TMEM, raw -> scratch
 #pragma unroll 1
@@ -541,7 +580,10 @@ __global__ void __launch_bounds__(NT, 1) tc_online_kernel(const TcArgs A) {
                 x[t] = ((mask2[cc] >> (j + t)) & 1u) ? gi * w : 0.f;
             }
             const float4 x4 = make_float4(x[0], x[1], x[2], x[3]);
-            if (valid) *reinterpret_cast<float4*>(A.dh2 + (sb + gr) * H + c0 + j) = x4;
+            if (valid) {
+                float* o = A.dh2 + sb * H + (size_t)(c0 + j) * B + gr;
+                o[0] = x[0]; o[B] = x[1]; o[2 * (size_t)B] = x[2]; o[3 * (size_t)B] = x[3];
+            }
             float4 hi, l4;
             split4<PASSES>(x4, hi, l4);
             asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sbase + Fwd::R + off_k128(BM, e.row, c0 + j)), "f"(hi.x),
@@ -565,10 +607,8 @@ __global__ void __launch_bounds__(NT, 1) tc_online_kernel(const TcArgs A) {
         tmem_ld32(tmem + e.lane_addr + (uint32_t)c0, v);
         if (valid) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(A.dh1 + (sb + gr) * H + c0 + j) =
-                    make_float4(((mask1[cc] >> j) & 1u) ? v[j] : 0.f, ((mask1[cc] >> (j + 1)) & 1u) ? v[j + 1] : 0.f,
-                                ((mask1[cc] >> (j + 2)) & 1u) ? v[j + 2] : 0.f, ((mask1[cc] >> (j + 3)) & 1u) ? v[j + 3] : 0.f);
+            for (int j = 0; j < 32; ++j)
+                A.dh1[sb * H + (size_t)(c0 + j) * B + gr] = ((mask1[cc] >> j) & 1u) ? v[j] : 0.f;
         }
     }
     if (!ok && threadIdx.x == 0) atomicExch(A.error, 4);
@@ -601,69 +641,64 @@ __device__ __forceinline__ void adam1(const AdamK& k, float g, float& th, float&
     else if (k.sync == 2) tg = k.tau * th + (1.0f - k.tau) * tg;
 }
 
-struct Wg {     // shared-memory carve-up of the wgrad kernel: 3 stages of (A hi|lo 16 KB, B hi|lo 32 KB)
-    static constexpr int STAGES = 3;
+struct Wg {     // shared-memory carve-up of the wgrad kernel: 2 stages of (A hi|lo 16 KB, B hi|lo 32 KB); 2 CTAs / SM
+    static constexpr int STAGES = 2;
     static constexpr uint32_t A_BYTES = KC * BM * 4;          // 8 KB
     static constexpr uint32_t B_BYTES = KC * H * 4;           // 16 KB
     static constexpr uint32_t STG = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr uint32_t BARS = STAGES * STG;
     static constexpr uint32_t TOTAL = BARS + 64;
+    static constexpr int TLD = 36;                            // floats per row of an epilogue transpose tile
 };
 
+// dW tile: D[128 x 256] = A^T-operand * D-operand over K = batch, Adam in the epilogue.
+//   t = 0,1: dW2 rows t*128.. : A = h1^T scratch [m][k] (K-major SW64), B = dh2^T scratch [n][k] (K-major SW64)
+//   t = 2  : dW1 rows 0..95   : A = s gathered from the ring [k][m] (MN-major),  B = dh1^T scratch (K-major SW64);
+//            A column m = obs_stride is set to 1, so row obs_stride of the tile is db1 = sum_k dh1[k][:] for free;
+//            this CTA also folds the per-row-tile partials of db2 / dW3 / db3 (from K4a) and emits the metrics.
 template <int PASSES>
-__global__ void __launch_bounds__(NT, 1) tc_wgrad_kernel(const TcArgs A) {
+__global__ void __launch_bounds__(NT, 2) tc_wgrad_kernel(const TcArgs A) {
     extern __shared__ uint8_t smem_raw[];
     const int B = A.d.batch, Dp = A.d.obs_stride;
-    constexpr int per_net = 4;                                // dW2 rows 0..127, 128..255; dW1; misc
+    constexpr int per_net = 3;
     const int g = blockIdx.x / per_net, t = blockIdx.x % per_net;
-    const size_t sb = (size_t)g * B;
-    const size_t pb = (size_t)g * A.L.stride;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (!A.active[g]) {
+        if (t == 2 && tid < DMDQN_METRICS_STRIDE && A.metrics) A.metrics[g * DMDQN_METRICS_STRIDE + tid] = 0.f;
+        return;
+    }
+    const size_t sb = (size_t)g * B, pb = (size_t)g * A.L.stride;
     float* th = A.nets.theta + pb;
     float* tg = A.nets.theta_tgt + pb;
     float* am = A.nets.adam_m + pb;
     float* av = A.nets.adam_v + pb;
-    const int tid = threadIdx.x;
-
-    if (t == per_net - 1) {
-        // misc tile: biases and the head from the activation-gradient scratch, batch rows in order
-        if (!A.active[g]) {
-            if (tid < DMDQN_METRICS_STRIDE && A.metrics) A.metrics[g * DMDQN_METRICS_STRIDE + tid] = 0.f;
-            return;
-        }
-        const AdamK k = adam_k(A, A.step_t[g]);
-        float* sg = reinterpret_cast<float*>(smem_raw);       // g_i [B], then a_i [B]
-        int* sa = reinterpret_cast<int*>(sg + B);
-        for (int i = tid; i < B; i += NT) { sg[i] = A.gcoef[sb + i]; sa[i] = A.act_b[sb + i]; }
-        __syncthreads();
-        const int j = tid;                                    // column (NT == H)
-        float s1 = 0.f, s2 = 0.f, w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
-#pragma unroll 4
-        for (int i = 0; i < B; ++i) {
-            s1 += A.dh1[(sb + i) * H + j];
-            s2 += A.dh2[(sb + i) * H + j];
-            const float tv = A.h2[(sb + i) * H + j] * sg[i];
-            const int a = sa[i];
-            w0 += a == 0 ? tv : 0.f; w1 += a == 1 ? tv : 0.f; w2 += a == 2 ? tv : 0.f; w3 += a == 3 ? tv : 0.f;
-        }
-        const float gw[4] = {w0, w1, w2, w3};
+    const AdamK k = adam_k(A, A.step_t[g]);
+    if (t == 2) {
+        // head / bias gradients: per-row-tile partials from K4a summed in tile order, then Adam
         auto upd = [&](int64_t off, float grad) {
             if (A.grads) { A.grads[pb + off] = grad; return; }
             float tgv = k.sync == 2 ? tg[off] : 0.f;
             adam1(k, grad, th[off], am[off], av[off], tgv);
             if (k.sync) tg[off] = tgv;
         };
-        upd(A.L.b1 + j, s1);
-        upd(A.L.b2 + j, s2);
-        for (int a = 0; a < 4; ++a) upd(A.L.w3 + (int64_t)j * 4 + a, gw[a]);
+        const size_t p0 = (size_t)g * A.tiles;
+        float s2 = 0.f, w[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int r = 0; r < A.tiles; ++r) {
+            s2 += A.part_b2[(p0 + r) * H + tid];
+            const float4 pw = reinterpret_cast<const float4*>(A.part_w3 + (p0 + r) * H * 4)[tid];
+            w[0] += pw.x; w[1] += pw.y; w[2] += pw.z; w[3] += pw.w;
+        }
+        upd(A.L.b2 + tid, s2);
+        for (int a = 0; a < 4; ++a) upd(A.L.w3 + (int64_t)tid * 4 + a, w[a]);
         if (tid < 4) {
-            float s = 0.f;
-            for (int i = 0; i < B; ++i) s += sa[i] == tid ? sg[i] : 0.f;
-            upd(A.L.b3 + tid, s);
+            float s3 = 0.f;
+            for (int r = 0; r < A.tiles; ++r) s3 += A.part_b3[(p0 + r) * 4 + tid];
+            upd(A.L.b3 + tid, s3);
         }
         if (tid == 0 && A.metrics) {
             double ls = 0, qs = 0, qq = 0, hist[4] = {0, 0, 0, 0};
             for (int r = 0; r < A.tiles; ++r) {
-                const float* pl = A.part_loss + ((size_t)g * A.tiles + r) * 8;
+                const float* pl = A.part_loss + (p0 + r) * 8;
                 ls += pl[0]; qs += pl[1]; qq += pl[2];
                 for (int a = 0; a < 4; ++a) hist[a] += pl[3 + a];
             }
@@ -673,21 +708,15 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_kernel(const TcArgs A) {
             for (int a = 0; a < 4; ++a) m[3 + a] = (float)hist[a];
             m[7] = 1.f;
         }
-        return;
     }
-    if (!A.active[g]) return;
-
-    // GEMM tile: D[128 x 256] = Asrc[:, m0:m0+128]^T * Dsrc, K = batch.  Both operands MN-major.
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const bool is_w2 = t < 2;
     const int m0 = is_w2 ? t * BM : 0;
     const int m_valid = is_w2 ? H : Dp;
-    const float* Asrc = is_w2 ? A.h1 + sb * H : A.rp.obs;
-    const float* Dsrc = (is_w2 ? A.dh2 : A.dh1) + sb * H;
-    const int lda = is_w2 ? H : Dp;
+    const float* AsrcT = A.h1 + sb * H;                       // [H][B]
+    const float* DsrcT = (is_w2 ? A.dh2 : A.dh1) + sb * H;    // [H][B]
     const int32_t* rows = A.rows + sb;
 
-    const int warp = tid >> 5;
     if (tid == 0) {
         for (int s = 0; s < Wg::STAGES; ++s) mbar_init(sbase + Wg::BARS + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -703,47 +732,55 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_kernel(const TcArgs A) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(sbase + Wg::BARS + 32));
 
     const int nchunks = (B + KC - 1) / KC;
-    uint32_t uses[Wg::STAGES] = {0, 0, 0};
+    uint32_t uses[Wg::STAGES] = {0, 0};
     bool ok = true;
+    // piece -> smem offset (same mapping for the copy and for the hi/lo split)
+    auto a_off = [&](int p) -> uint32_t {                     // 512 pieces
+        if (is_w2) return off_k64(BM, p >> 2, (p & 3) << 2);  // row m = p/4, 4 k-pieces per row
+        return off_mn(BM, p >> 5, (p & 31) << 2);             // k = p/32, 32 m-pieces per k-row
+    };
+    auto b_off = [&](int p) -> uint32_t { return 2 * Wg::A_BYTES + off_k64(H, p >> 2, (p & 3) << 2); };   // 1024 pieces
     auto issue = [&](int c) {
         const uint32_t st = sbase + (c % Wg::STAGES) * Wg::STG;
-        // A chunk: 16 k x 128 m floats = 512 pieces, threads 0..255 take 2; B chunk: 1024 pieces, 4 each
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const int p = tid + r * NT;
-            const int kk = p >> 5, m = (p & 31) << 2;
-            const int kr = c * KC + kk;
-            const bool v = kr < B && m0 + m < m_valid;
-            const size_t srow = v ? (is_w2 ? (size_t)kr : (size_t)rows[kr]) : 0;
-            cp16(st + off_mn(BM, kk, m), Asrc + srow * lda + (v ? m0 + m : 0), v);
+            if (is_w2) {
+                const int m = p >> 2, k = c * KC + ((p & 3) << 2);
+                const bool v = k < B;
+                cp16(st + a_off(p), AsrcT + (size_t)(m0 + m) * B + (v ? k : 0), v);
+            } else {
+                const int kr = c * KC + (p >> 5), m = (p & 31) << 2;
+                const bool v = kr < B && m < m_valid;
+                if (m == Dp)      // the "ones" column: tile row Dp accumulates sum_k dh1[k][:] = db1
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%2,%2};" ::"r"(st + a_off(p)), "f"(kr < B ? 1.f : 0.f), "f"(0.f) : "memory");
+                else
+                    cp16(st + a_off(p), A.rp.obs + (v ? (size_t)rows[kr] * Dp + m : 0), v);
+            }
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int p = tid + r * NT;
-            const int kk = p >> 6, n = (p & 63) << 2;
-            const bool v = c * KC + kk < B;
-            cp16(st + 2 * Wg::A_BYTES + off_mn(H, kk, n), Dsrc + (size_t)(v ? c * KC + kk : 0) * H + n, v);
+            const int n = p >> 2, k = c * KC + ((p & 3) << 2);
+            const bool v = k < B;
+            cp16(st + b_off(p), DsrcT + (size_t)n * B + (v ? k : 0), v);
         }
     };
     issue(0);
     cp_commit();
-    if (nchunks > 1) issue(1);
-    cp_commit();
     for (int c = 0; c < nchunks; ++c) {
-        if (c + 2 < nchunks) {
-            const int b = (c + 2) % Wg::STAGES;
+        if (c + 1 < nchunks) {
+            const int b = (c + 1) % Wg::STAGES;
             if (uses[b]) ok &= mbar_wait(sbase + Wg::BARS + 8 * b, (uses[b] - 1) & 1);
-            issue(c + 2);
+            issue(c + 1);
         }
         cp_commit();
-        cp_wait<2>();
+        cp_wait<1>();
         const uint32_t st = sbase + (c % Wg::STAGES) * Wg::STG;
         if (PASSES == 3) {
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
-                uint32_t o;
-                if (r < 2) { const int p = tid + r * NT; o = off_mn(BM, p >> 5, (p & 31) << 2); }
-                else { const int p = tid + (r - 2) * NT; o = 2 * Wg::A_BYTES + off_mn(H, p >> 6, (p & 63) << 2); }
+                const uint32_t o = r < 2 ? a_off(tid + r * NT) : b_off(tid + (r - 2) * NT);
                 const uint32_t lo_off = r < 2 ? Wg::A_BYTES : Wg::B_BYTES;
                 float4 x, hi, lo;
                 asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(st + o));
@@ -756,14 +793,19 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_kernel(const TcArgs A) {
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
-            constexpr uint32_t idesc = make_idesc(true, true);
+            const uint32_t idesc = make_idesc(!is_w2, false);
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
-                // A: 4 m-groups per k-group -> k-group stride 2048 B; B: 8 n-groups -> 4096 B
-                const uint64_t a_hi = make_desc(st + ks * 2 * 2048, 512, 2048, 1);
-                const uint64_t a_lo = make_desc(st + Wg::A_BYTES + ks * 2 * 2048, 512, 2048, 1);
-                const uint64_t b_hi = make_desc(st + 2 * Wg::A_BYTES + ks * 2 * 4096, 512, 4096, 1);
-                const uint64_t b_lo = make_desc(st + 2 * Wg::A_BYTES + Wg::B_BYTES + ks * 2 * 4096, 512, 4096, 1);
+                uint64_t a_hi, a_lo;
+                if (is_w2) {
+                    a_hi = make_desc(st + ks * 32, 16, 512, 4);
+                    a_lo = make_desc(st + Wg::A_BYTES + ks * 32, 16, 512, 4);
+                } else {      // MN-major: 4 m-groups per k-group -> k-group stride 2048 B
+                    a_hi = make_desc(st + ks * 2 * 2048, 512, 2048, 1);
+                    a_lo = make_desc(st + Wg::A_BYTES + ks * 2 * 2048, 512, 2048, 1);
+                }
+                const uint64_t b_hi = make_desc(st + 2 * Wg::A_BYTES + ks * 32, 16, 512, 4);
+                const uint64_t b_lo = make_desc(st + 2 * Wg::A_BYTES + Wg::B_BYTES + ks * 32, 16, 512, 4);
                 uint32_t acc = (c | ks) ? 1u : 0u;
                 if (PASSES == 3) {
                     mma_ss(tmem, a_lo, b_hi, idesc, acc);
@@ -781,35 +823,45 @@ __global__ void __launch_bounds__(NT, 1) tc_wgrad_kernel(const TcArgs A) {
         ok &= mbar_wait(sbase + Wg::BARS + 8 * last, (uses[last] - 1) & 1);
         tc_fence_after();
     }
+    __syncthreads();      // every thread has seen the GEMM finish: the stage memory becomes the transpose tiles
 
-    // epilogue: thread = weight row m (Adam on 128 of its 256 columns)
-    const AdamK k = adam_k(A, A.step_t[g]);
+    // epilogue: TMEM (lane = weight row) -> per-warp smem tile -> 8 lanes per 128-byte row segment, so the
+    // Adam read-modify-write of theta / m / v / theta_tgt is fully coalesced.
     const Epi e;
-    const int m = m0 + e.row;
+    float* tile = reinterpret_cast<float*>(__cvta_shared_to_generic((size_t)sbase)) + warp * (32 * Wg::TLD);
     const int64_t wbase = is_w2 ? A.L.w2 : A.L.w1;
+    const int rsub = lane >> 3, c4 = (lane & 7) << 2;
 #pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {
         const int c0 = e.half * 128 + cc * 32;
         float v[32];
         tmem_ld32(tmem + e.lane_addr + (uint32_t)c0, v);
-        if (m < m_valid) {
-            const int64_t off = wbase + (int64_t)m * H + c0;
+        __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                if (A.grads) {
-                    *reinterpret_cast<float4*>(A.grads + pb + off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    continue;
-                }
-                float4 t4 = *reinterpret_cast<float4*>(th + off + j), m4 = *reinterpret_cast<float4*>(am + off + j);
-                float4 v4 = *reinterpret_cast<float4*>(av + off + j);
-                float4 g4 = k.sync == 2 ? *reinterpret_cast<float4*>(tg + off + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                adam1(k, v[j], t4.x, m4.x, v4.x, g4.x); adam1(k, v[j + 1], t4.y, m4.y, v4.y, g4.y);
-                adam1(k, v[j + 2], t4.z, m4.z, v4.z, g4.z); adam1(k, v[j + 3], t4.w, m4.w, v4.w, g4.w);
-                *reinterpret_cast<float4*>(th + off + j) = t4;
-                *reinterpret_cast<float4*>(am + off + j) = m4;
-                *reinterpret_cast<float4*>(av + off + j) = v4;
-                if (k.sync) *reinterpret_cast<float4*>(tg + off + j) = g4;
+        for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(tile + lane * Wg::TLD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        __syncwarp();
+#pragma unroll 2
+        for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + rsub;
+            const int m = m0 + (warp & 3) * 32 + r;
+            const bool bias_row = !is_w2 && m == Dp;               // db1 from the ones column
+            if (m >= m_valid && !bias_row) continue;
+            const float4 gr4 = *reinterpret_cast<const float4*>(tile + r * Wg::TLD + c4);
+            const int64_t off = bias_row ? A.L.b1 + c0 + c4 : wbase + (int64_t)m * H + c0 + c4;
+            if (A.grads) {
+                *reinterpret_cast<float4*>(A.grads + pb + off) = gr4;
+                continue;
             }
+            float4 t4 = *reinterpret_cast<float4*>(th + off), m4 = *reinterpret_cast<float4*>(am + off);
+            float4 v4 = *reinterpret_cast<float4*>(av + off);
+            float4 g4 = k.sync == 2 ? *reinterpret_cast<float4*>(tg + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+            adam1(k, gr4.x, t4.x, m4.x, v4.x, g4.x); adam1(k, gr4.y, t4.y, m4.y, v4.y, g4.y);
+            adam1(k, gr4.z, t4.z, m4.z, v4.z, g4.z); adam1(k, gr4.w, t4.w, m4.w, v4.w, g4.w);
+            *reinterpret_cast<float4*>(th + off) = t4;
+            *reinterpret_cast<float4*>(am + off) = m4;
+            *reinterpret_cast<float4*>(av + off) = v4;
+            if (k.sync) *reinterpret_cast<float4*>(tg + off) = g4;
         }
     }
     if (!ok && tid == 0) atomicExch(A.error, 5);
@@ -838,7 +890,7 @@ int launch_tc(const TcArgs& A, int stages, cudaStream_t s) {
         DMDQN_CUDA(cudaGetLastError());
     }
     if (stages & DMDQN_STAGE_WGRAD) {
-        tc_wgrad_kernel<PASSES><<<A.d.n_nets * 4, NT, smem_w, s>>>(A);
+        tc_wgrad_kernel<PASSES><<<A.d.n_nets * 3, NT, smem_w, s>>>(A);
         DMDQN_CUDA(cudaGetLastError());
     }
     return DMDQN_OK;
@@ -847,7 +899,8 @@ int launch_tc(const TcArgs& A, int stages, cudaStream_t s) {
 }  // namespace
 
 bool tc_supported(const dmdqn_dims& d) {
-    return d.hidden == H && d.obs_stride % 32 == 0 && d.obs_stride <= 96 && d.batch >= 1 && d.batch * 8 <= 200 * 1024;
+    // batch % 4: the transposed scratch is streamed in 16-byte pieces along the batch axis
+    return d.hidden == H && d.obs_stride % 32 == 0 && d.obs_stride <= 96 && d.batch % 4 == 0 && d.batch <= 4096;
 }
 
 int launch_learn_tc(const dmdqn_dims& d, const dmdqn_hparams& hp, const dmdqn_replay& rp, const dmdqn_nets& nets,
@@ -878,10 +931,12 @@ int launch_learn_tc(const dmdqn_dims& d, const dmdqn_hparams& hp, const dmdqn_re
     A.q_next = reinterpret_cast<float*>(ws + w.q_next);
     A.tq_all = reinterpret_cast<float*>(ws + w.tq_all);
     A.h1 = reinterpret_cast<float*>(ws + w.h1);
-    A.h2 = reinterpret_cast<float*>(ws + w.h2);
     A.dh1 = reinterpret_cast<float*>(ws + w.dh1);
     A.dh2 = reinterpret_cast<float*>(ws + w.dh2);
     A.part_loss = reinterpret_cast<float*>(ws + w.part_loss);
+    A.part_b3 = reinterpret_cast<float*>(ws + w.part_b3);
+    A.part_w3 = reinterpret_cast<float*>(ws + w.part_w3);
+    A.part_b2 = reinterpret_cast<float*>(ws + w.part_b2);
     A.metrics = metrics;
     A.grads = grads;
     A.error = reinterpret_cast<int*>(ws + w.tc_error);

@@ -348,7 +348,9 @@ class AgentGroup:
                 "q_next": view(v.q_next, torch.float32, (g, b, 4)), "tq_all": view(v.tq_all, torch.float32, (g, b, 4)),
                 "rows": view(v.rows, torch.int32, (g, b)), "r_hat": view(v.r_hat, torch.float32, (g, b)),
                 "active": view(v.active, torch.int32, (g,)), "tc_error": view(v.tc_error, torch.int32, (1,)),
-                "dh1": view(v.dh1, torch.float32, (g, b, self.hidden)), "dh2": view(v.dh2, torch.float32, (g, b, self.hidden))}
+                # the tcgen05 path keeps its activation scratch transposed ([feature][batch])
+                **{k_: (view(p_, torch.float32, (g, self.hidden, b)).transpose(1, 2) if self.hp.precision != 0
+                        else view(p_, torch.float32, (g, b, self.hidden))) for k_, p_ in (("dh1", v.dh1), ("dh2", v.dh2))}}
 
     def sync_target(self, mask=None, tau: float | None = None) -> None:
         """update_target_network (tau None, dqn_agent.py:382-384) / soft update (:389-399)."""

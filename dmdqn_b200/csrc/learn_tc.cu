@@ -14,9 +14,10 @@
 //   * activations: hi part in shared memory as the next layer's A operand (K-major, 128-byte
 //     swizzle), lo part in TMEM columns 256..511 (A-from-TMEM MMA) -- 128 KB each, so the full
 //     512 TMEM columns are used: 256 accumulator + 256 operand;
-//   * weights: 16 x 256 chunks streamed from L2 with cp.async straight into the UMMA canonical
-//     layout (MN-major "128B_BASE32B" for x.W, K-major 64-byte swizzle for d.W^T), split hi/lo
-//     in place by the thread that copied them, two stages, freed by tcgen05.commit -> mbarrier;
+//   * weights: 8 x 256 (x.W) or 256 x 16 (d.W^T) chunks streamed from L2 with cp.async straight into
+//     the UMMA canonical layout (MN-major "128B_BASE32B" / K-major 64-byte swizzle), split hi/lo in
+//     place by the thread that copied them; a full/empty mbarrier ring (4 / 2 stages) couples the 8
+//     producer warps to the single MMA-issuing lane (warp 8), tcgen05.commit frees a stage;
 //   * epilogues read the accumulator with tcgen05.ld (thread = batch row), so bias/ReLU, the
 //     4-wide head (layer 3), TD target, loss gradient and dh2 are computed per row in registers.
 #include "common.cuh"
@@ -27,7 +28,8 @@ namespace {
 
 constexpr int H = 256;          // hidden width served by this path
 constexpr int BM = 128;         // batch rows per CTA (UMMA M)
-constexpr int NT = 256;         // threads per CTA: 8 warps, two per TMEM sub-partition
+constexpr int NT = 256;         // producer / epilogue threads: 8 warps, two per TMEM sub-partition
+constexpr int NT_F = NT + 32;   // K3 / K4a add one warp whose lane 0 only issues tcgen05.mma
 constexpr int KC = 16;          // k-rows of the streamed operand per stage
 constexpr uint32_t ATOM = BM * 128;           // bytes of one K-major SW128 atom column (128 rows x 32 floats)
 constexpr uint32_t STAGE = 2 * KC * H * 4;    // hi + lo of a 16 x 256 chunk
@@ -72,6 +74,10 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     return done != 0;
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void prod_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 producer warps only
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -166,103 +172,122 @@ struct Fwd {
     static constexpr uint32_t W3S = BIAS2 + 1024;             // W3[256][4]
     static constexpr uint32_t QP = W3S + 4096;                // q partials [2][128][4]
     static constexpr uint32_t ROWF = QP + 4096;               // per-row words [6][128]: loss term, q[4], action
-    static constexpr uint32_t BARS = ROWF + 4096;             // 4 mbarriers + tmem base
-    static constexpr uint32_t TOTAL = BARS + 64;
+    static constexpr uint32_t BARS = ROWF + 4096;             // full[4] | empty[4] mbarriers | tmem base
+    static constexpr uint32_t TOTAL = BARS + 128;
 };
 
 // ------------------------------------------------------------------------------------------
 // Streamed GEMM: D[128 x 256] (TMEM columns 0..255) = A[128 x K] * op(W), fp32 via PASSES MMAs.
 //   A hi: shared memory, K-major SW128 at a_hi; A lo: shared memory (a_lo_smem != 0) or TMEM columns.
-//   BT = false: W is [K][256] row-major (x.W),   staged MN-major;
-//   BT = true : W is [256][K] row-major (d.W^T), staged K-major SW64.
-// `uses` counts commits per stage barrier (mbarrier phase bookkeeping, uniform over the CTA).
+//   BT = false: W is [K][256] row-major (x.W),   staged MN-major, 8-row chunks, 4 stages;
+//   BT = true : W is [256][K] row-major (d.W^T), staged K-major SW64, 16-column chunks, 2 stages.
+// Warp-specialised: the 8 producer warps copy + split weight chunks and arrive on full[stage]; lane 0
+// of warp 8 waits on full[stage], issues the MMAs and commits to empty[stage], which producers wait on
+// before refilling.  No CTA-wide barrier inside the loop.  cnt[] = chunks that have gone through each
+// stage so far (mbarrier phase bookkeeping; both roles run the same sequence).
 // ------------------------------------------------------------------------------------------
+template <bool BT>
+struct Pipe {
+    static constexpr int KCX = BT ? 16 : 8;
+    static constexpr int NST = BT ? 2 : 4;
+    static constexpr uint32_t HALF = KCX * H * 4;             // bytes of the hi (or lo) part of a stage
+    static constexpr int PIECES = KCX * H / 4 / NT;           // 16-byte pieces per producer thread per chunk
+};
+
 template <int PASSES, bool BT>
-__device__ __forceinline__ bool gemm_stream(uint32_t sbase, uint32_t tmem, uint32_t a_hi, uint32_t a_lo_smem,
-                                            uint32_t a_lo_tmem, const float* __restrict__ W, int ldw, int K,
-                                            uint32_t (&uses)[4]) {
-    // x.W : 8-row chunks, 4 stages (copies run 3 chunks ahead of the MMAs); d.W^T : 16-column chunks, 2 stages.
-    constexpr int KCX = BT ? 16 : 8;
-    constexpr int NST = BT ? 2 : 4;
-    constexpr uint32_t HALF = KCX * H * 4;                    // bytes of the hi (or lo) part of a stage
-    constexpr int PIECES = KCX * H / 4 / NT;                  // 16-byte pieces per thread per chunk
+__device__ __forceinline__ bool gemm_produce(uint32_t sbase, const float* __restrict__ W, int ldw, int K, uint32_t (&cnt)[4]) {
+    using P = Pipe<BT>;
     const int tid = threadIdx.x;
-    const uint32_t bar0 = sbase + Fwd::BARS;
-    const int nchunks = K / KCX;
+    const uint32_t full0 = sbase + Fwd::BARS, empty0 = full0 + 32;
+    const int nchunks = K / P::KCX;
     bool ok = true;
     auto piece_off = [&](int p) -> uint32_t {
         if (!BT) return off_mn(H, p >> 6, (p & 63) << 2);     // k-row p/64, column piece p%64
         return off_k64(H, p >> 2, (p & 3) << 2);              // row n = p/4, k piece p%4
     };
     auto issue = [&](int c) {
-        const uint32_t st = sbase + Fwd::WB + (c % NST) * (2 * HALF);
+        const int b = c % P::NST;
+        if (cnt[b]) ok &= mbar_wait(empty0 + 8 * b, (cnt[b] - 1) & 1);   // the MMAs that read this stage are done
+        cnt[b] += 1;
+        const uint32_t st = sbase + Fwd::WB + b * (2 * P::HALF);
 #pragma unroll
-        for (int r = 0; r < PIECES; ++r) {
+        for (int r = 0; r < P::PIECES; ++r) {
             const int p = tid + r * NT;
-            if (!BT) cp16(st + piece_off(p), W + (size_t)(c * KCX + (p >> 6)) * ldw + ((p & 63) << 2));
-            else cp16(st + piece_off(p), W + (size_t)(p >> 2) * ldw + c * KCX + ((p & 3) << 2));
+            if (!BT) cp16(st + piece_off(p), W + (size_t)(c * P::KCX + (p >> 6)) * ldw + ((p & 63) << 2));
+            else cp16(st + piece_off(p), W + (size_t)(p >> 2) * ldw + c * P::KCX + ((p & 3) << 2));
         }
     };
 #pragma unroll
-    for (int c = 0; c < NST - 1; ++c) {
+    for (int c = 0; c < P::NST - 1; ++c) {
         if (c < nchunks) issue(c);
         cp_commit();
     }
     for (int c = 0; c < nchunks; ++c) {
-        if (c + NST - 1 < nchunks) {
-            const int b = (c + NST - 1) % NST;                // stage last read by the MMAs of chunk c-1
-            if (uses[b]) ok &= mbar_wait(bar0 + 8 * b, (uses[b] - 1) & 1);
-            issue(c + NST - 1);
-        }
-        cp_commit();
-        cp_wait<NST - 1>();                                   // this thread's pieces of chunk c have landed
-        const uint32_t st = sbase + Fwd::WB + (c % NST) * (2 * HALF);
+        cp_wait<P::NST - 2>();                                // this thread's pieces of chunk c have landed
+        const uint32_t st = sbase + Fwd::WB + (c % P::NST) * (2 * P::HALF);
         if (PASSES == 3) {                                    // split them: hi in place, lo beside
 #pragma unroll
-            for (int r = 0; r < PIECES; ++r) {
+            for (int r = 0; r < P::PIECES; ++r) {
                 const uint32_t o = piece_off(tid + r * NT);
                 float4 x, hi, lo;
                 asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(st + o));
                 split4<3>(x, hi, lo);
                 asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(st + o), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
-                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(st + HALF + o), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(st + P::HALF + o), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
             }
         }
-        fence_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            constexpr uint32_t idesc = make_idesc(false, !BT);
-#pragma unroll
-            for (int ks = 0; ks < KCX / 8; ++ks) {
-                const int kg = c * KCX + ks * 8;
-                const uint32_t a_off = (uint32_t)(kg >> 5) * ATOM + (uint32_t)((kg & 31) >> 3) * 32;
-                const uint64_t a_hi_d = make_desc(a_hi + a_off, 16, 1024, 2);
-                uint64_t b_hi, b_lo;
-                if (!BT) {      // MN-major: 8 n-groups per k-group of 4 rows -> 4096 B per k-group
-                    b_hi = make_desc(st + ks * 2 * 4096, 512, 4096, 1);
-                    b_lo = make_desc(st + HALF + ks * 2 * 4096, 512, 4096, 1);
-                } else {
-                    b_hi = make_desc(st + ks * 32, 16, 512, 4);
-                    b_lo = make_desc(st + HALF + ks * 32, 16, 512, 4);
-                }
-                uint32_t acc = (c | ks) ? 1u : 0u;
-                if (PASSES == 3) {                            // small terms first
-                    if (a_lo_smem) mma_ss(tmem, make_desc(a_lo_smem + a_off, 16, 1024, 2), b_hi, idesc, acc);
-                    else mma_ts(tmem, a_lo_tmem + (uint32_t)kg, b_hi, idesc, acc);
-                    mma_ss(tmem, a_hi_d, b_lo, idesc, 1u);
-                    acc = 1u;
-                }
-                mma_ss(tmem, a_hi_d, b_hi, idesc, acc);
-            }
-            umma_commit(bar0 + 8 * (c % NST));
-        }
-        uses[c % NST] += 1;
+        fence_async_smem();                                   // generic-proxy writes (this chunk, and the A operand before it)
+        tc_fence_before();
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(full0 + 8 * (c % P::NST));   // one arrival per producer warp
+        // only now block on the MMAs of chunk c-1 (their stage is refilled with chunk c+NST-1): the split of
+        // chunk c above overlaps with them instead of queueing behind them
+        if (c + P::NST - 1 < nchunks) issue(c + P::NST - 1);
+        cp_commit();
     }
     // all MMAs of this GEMM complete (a commit tracks every earlier MMA of the issuing thread)
-    const int last = (nchunks - 1) % NST;
-    ok &= mbar_wait(bar0 + 8 * last, (uses[last] - 1) & 1);
+    const int last = (nchunks - 1) % P::NST;
+    ok &= mbar_wait(empty0 + 8 * last, (cnt[last] - 1) & 1);
     tc_fence_after();
+    return ok;
+}
+
+template <int PASSES, bool BT>
+__device__ __forceinline__ bool gemm_mma(uint32_t sbase, uint32_t tmem, uint32_t a_hi, uint32_t a_lo_smem,
+                                         uint32_t a_lo_tmem, int K, uint32_t (&cnt)[4]) {
+    using P = Pipe<BT>;
+    const uint32_t full0 = sbase + Fwd::BARS, empty0 = full0 + 32;
+    const int nchunks = K / P::KCX;
+    bool ok = true;
+    constexpr uint32_t idesc = make_idesc(false, !BT);
+    // Descriptors differ only in their 14-bit start-address field: build each once, then add (bytes >> 4).
+    const uint64_t a_hi0 = make_desc(a_hi, 16, 1024, 2);
+    const uint64_t a_lo0 = make_desc(a_lo_smem, 16, 1024, 2);
+    const uint64_t b0 = BT ? make_desc(sbase + Fwd::WB, 16, 512, 4) : make_desc(sbase + Fwd::WB, 512, 4096, 1);
+    constexpr uint32_t KSTEP_B = BT ? 32 : 2 * 4096;          // bytes between the k-steps of a chunk in the B stage
+    for (int c = 0; c < nchunks; ++c) {
+        const int b = c % P::NST;
+        ok &= mbar_wait(full0 + 8 * b, cnt[b] & 1);           // all 8 producer warps have published chunk c
+        cnt[b] += 1;
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < P::KCX / 8; ++ks) {
+            const int kg = c * P::KCX + ks * 8;
+            const uint32_t a_off = ((uint32_t)(kg >> 5) * ATOM + (uint32_t)((kg & 31) >> 3) * 32) >> 4;
+            const uint32_t b_off = ((uint32_t)b * (2 * P::HALF) + ks * KSTEP_B) >> 4;
+            const uint64_t a_hi_d = a_hi0 + a_off;
+            const uint64_t b_hi = b0 + b_off, b_lo = b0 + b_off + (P::HALF >> 4);
+            uint32_t acc = (c | ks) ? 1u : 0u;
+            if (PASSES == 3) {                                // small terms first
+                if (a_lo_smem) mma_ss(tmem, a_lo0 + a_off, b_hi, idesc, acc);
+                else mma_ts(tmem, a_lo_tmem + (uint32_t)kg, b_hi, idesc, acc);
+                mma_ss(tmem, a_hi_d, b_lo, idesc, 1u);
+                acc = 1u;
+            }
+            mma_ss(tmem, a_hi_d, b_hi, idesc, acc);
+        }
+        umma_commit(empty0 + 8 * b);
+    }
     return ok;
 }
 
@@ -270,16 +295,26 @@ __device__ __forceinline__ bool gemm_stream(uint32_t sbase, uint32_t tmem, uint3
 template <int PASSES>
 __device__ __forceinline__ void gather_x(uint32_t sbase, const float* __restrict__ ring, const int32_t* __restrict__ rows,
                                          int r0, int B, int Dp) {
-    const int q = Dp >> 2;
-    for (int f = threadIdx.x; f < BM * q; f += NT) {
-        const int i = f / q, k = (f % q) << 2;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f), hi, lo;
-        if (r0 + i < B) x = __ldg(reinterpret_cast<const float4*>(ring + (size_t)rows[r0 + i] * Dp + k));
-        split4<PASSES>(x, hi, lo);
-        const uint32_t o = off_k128(BM, i, k);
-        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sbase + Fwd::R + o), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
-        if (PASSES == 3)
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sbase + Fwd::XLO + o), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+    const int q = Dp >> 2;                                    // 16-byte pieces per row
+    const int total = BM * q;
+    // four independent loads in flight per thread per round (the sampled rows were prefetched into L2 by K1b)
+    for (int f0 = threadIdx.x; f0 < total; f0 += 4 * NT) {
+        float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0, x2 = x0, x3 = x0;
+        const int f1 = f0 + NT, f2 = f0 + 2 * NT, f3 = f0 + 3 * NT;
+        if (r0 + f0 / q < B) x0 = __ldg(reinterpret_cast<const float4*>(ring + (size_t)__ldg(rows + r0 + f0 / q) * Dp + ((f0 % q) << 2)));
+        if (f1 < total && r0 + f1 / q < B) x1 = __ldg(reinterpret_cast<const float4*>(ring + (size_t)__ldg(rows + r0 + f1 / q) * Dp + ((f1 % q) << 2)));
+        if (f2 < total && r0 + f2 / q < B) x2 = __ldg(reinterpret_cast<const float4*>(ring + (size_t)__ldg(rows + r0 + f2 / q) * Dp + ((f2 % q) << 2)));
+        if (f3 < total && r0 + f3 / q < B) x3 = __ldg(reinterpret_cast<const float4*>(ring + (size_t)__ldg(rows + r0 + f3 / q) * Dp + ((f3 % q) << 2)));
+        auto put = [&](int f, const float4& x) {
+            if (f >= total) return;
+            float4 hi, lo;
+            split4<PASSES>(x, hi, lo);
+            const uint32_t o = off_k128(BM, f / q, (f % q) << 2);
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sbase + Fwd::R + o), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+            if (PASSES == 3)
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sbase + Fwd::XLO + o), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+        };
+        put(f0, x0); put(f1, x1); put(f2, x2); put(f3, x3);
     }
 }
 
@@ -333,10 +368,7 @@ __device__ __forceinline__ void epi_hidden(uint32_t sbase, uint32_t tmem, const 
         if (PASSES == 3) tmem_st32(tmem + e.lane_addr + 256u + (uint32_t)c0, lo);
     }
     if (PASSES == 3) tmem_st_wait();
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
+    // visibility to the MMA warp comes with this thread's next arrive on a full[] barrier
 }
 
 // Epilogue of layer 2 feeding the 4-wide head: q[a] = b3[a] + sum_j relu(D[j] + b2[j]) * W3[j][a]; the two
@@ -374,9 +406,7 @@ __device__ __forceinline__ void epi_head(uint32_t sbase, uint32_t tmem, const Ep
     }
     float4* qp = reinterpret_cast<float4*>(__cvta_shared_to_generic((size_t)(sbase + Fwd::QP)));
     qp[e.half * BM + e.row] = acc;
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
+    prod_sync();
     const float4 p0 = qp[e.row], p1 = qp[BM + e.row];
     q[0] = (p0.x + p1.x) + __ldg(b3 + 0); q[1] = (p0.y + p1.y) + __ldg(b3 + 1);
     q[2] = (p0.z + p1.z) + __ldg(b3 + 2); q[3] = (p0.w + p1.w) + __ldg(b3 + 3);
@@ -394,18 +424,21 @@ __device__ __forceinline__ void load_small_params(uint32_t sbase, const float* _
 __device__ __forceinline__ uint32_t tc_prologue(uint32_t sbase) {
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
-        for (int b = 0; b < 4; ++b) mbar_init(sbase + Fwd::BARS + 8 * b, 1);
+        for (int b = 0; b < 4; ++b) {
+            mbar_init(sbase + Fwd::BARS + 8 * b, NT / 32);     // full[b]: one arrival per producer warp
+            mbar_init(sbase + Fwd::BARS + 32 + 8 * b, 1);      // empty[b]: one tcgen05.commit
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + Fwd::BARS + 32), "r"(512));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + Fwd::BARS + 64), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     uint32_t tmem;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(sbase + Fwd::BARS + 32));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(sbase + Fwd::BARS + 64));
     return tmem;
 }
 __device__ __forceinline__ void tc_epilogue(uint32_t tmem) {
@@ -418,7 +451,7 @@ __device__ __forceinline__ void tc_epilogue(uint32_t tmem) {
 // K3
 // ------------------------------------------------------------------------------------------
 template <int PASSES>
-__global__ void __launch_bounds__(NT, 1) tc_target_kernel(const TcArgs A) {
+__global__ void __launch_bounds__(NT_F, 1) tc_target_kernel(const TcArgs A) {
     extern __shared__ uint8_t smem_raw[];
     const int g = blockIdx.x / A.tiles, rt = blockIdx.x % A.tiles;
     if (!A.active[g]) return;
@@ -426,36 +459,66 @@ __global__ void __launch_bounds__(NT, 1) tc_target_kernel(const TcArgs A) {
     const int B = A.d.batch, Dp = A.d.obs_stride, r0 = rt * BM;
     const int32_t* rows = A.rows + (size_t)g * B;
     const uint32_t tmem = tc_prologue(sbase);
-    const Epi e;
-    uint32_t uses[4] = {0, 0, 0, 0};
+    uint32_t cnt[4] = {0, 0, 0, 0};
     bool ok = true;
-    float q_on[4], q_tg[4];
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-        const float* P = (pass == 0 ? A.nets.theta : A.nets.theta_tgt) + (size_t)g * A.L.stride;
-        gather_x<PASSES>(sbase, A.rp.next_obs, rows, r0, B, Dp);
-        load_small_params(sbase, P, A.L);
-        ok &= gemm_stream<PASSES, false>(sbase, tmem, sbase + Fwd::R, sbase + Fwd::XLO, 0, P + A.L.w1, H, Dp, uses);
-        uint32_t mask[4];
-        epi_hidden<PASSES>(sbase, tmem, e, Fwd::BIAS1, nullptr, 0, mask);
-        ok &= gemm_stream<PASSES, false>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, P + A.L.w2, H, H, uses);
-        epi_head(sbase, tmem, e, false, mask, pass == 0 ? q_on : q_tg, P + A.L.b3);
-        __syncthreads();   // q partials consumed; R / TMEM free for the next pass
-    }
-    const int gr = r0 + e.row;
-    if (e.half == 0 && gr < B) {
-        int best = 0;
-        float tmax = q_tg[0];
-        for (int k = 1; k < A.d.n_actions; ++k) {
-            if (q_on[k] > q_on[best]) best = k;
-            tmax = fmaxf(tmax, q_tg[k]);
+    if (threadIdx.x >= NT) {
+        // ---- MMA warp: lane 0 issues every tcgen05.mma of this CTA ----
+        if (threadIdx.x == NT) {
+            for (int pass = 0; pass < 2; ++pass) {
+                ok &= gemm_mma<PASSES, false>(sbase, tmem, sbase + Fwd::R, sbase + Fwd::XLO, 0, Dp, cnt);
+                ok &= gemm_mma<PASSES, false>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, H, cnt);
+            }
+            if (!ok) atomicExch(A.error, 13);
         }
-        const float tq = A.double_dqn ? q_tg[best] : tmax;
-        const size_t o = (size_t)g * B + gr;
-        A.y[o] = A.r_hat[o] + (A.gamma * (1.0f - A.done_b[o])) * tq;
-        for (int k = 0; k < 4; ++k) {
-            A.q_next[o * 4 + k] = q_on[k];
-            A.tq_all[o * 4 + k] = q_tg[k];
+        __syncwarp();
+    } else {
+        const Epi e;
+        float q_on[4], q_tg[4];
+#ifdef TC_TIMING
+        long long tt[12]; int ti = 0;
+#define TSTAMP() tt[ti++] = clock64()
+#else
+#define TSTAMP()
+#endif
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {          // 0: online(s')  1: target(s')
+            const float* P = (pass == 0 ? A.nets.theta : A.nets.theta_tgt) + (size_t)g * A.L.stride;
+            TSTAMP();
+            gather_x<PASSES>(sbase, A.rp.next_obs, rows, r0, B, Dp);
+            load_small_params(sbase, P, A.L);
+            prod_sync();   // biases / head weights visible to every epilogue thread
+            TSTAMP();
+            ok &= gemm_produce<PASSES, false>(sbase, P + A.L.w1, H, Dp, cnt);
+            TSTAMP();
+            uint32_t mask[4];
+            epi_hidden<PASSES>(sbase, tmem, e, Fwd::BIAS1, nullptr, 0, mask);
+            TSTAMP();
+            ok &= gemm_produce<PASSES, false>(sbase, P + A.L.w2, H, H, cnt);
+            TSTAMP();
+            epi_head(sbase, tmem, e, false, mask, pass == 0 ? q_on : q_tg, P + A.L.b3);
+            prod_sync();   // q partials consumed; R / TMEM free for the next pass
+            TSTAMP();
+        }
+#ifdef TC_TIMING
+        if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 300))
+            printf("K3 cta %d: gather %lld L1 %lld epi1 %lld L2 %lld epi2 %lld | gather %lld L1 %lld epi1 %lld L2 %lld epi2 %lld\n", blockIdx.x,
+                   tt[1]-tt[0], tt[2]-tt[1], tt[3]-tt[2], tt[4]-tt[3], tt[5]-tt[4], tt[7]-tt[6], tt[8]-tt[7], tt[9]-tt[8], tt[10]-tt[9], tt[11]-tt[10]);
+#endif
+        const int gr = r0 + e.row;
+        if (e.half == 0 && gr < B) {
+            int best = 0;
+            float tmax = q_tg[0];
+            for (int k = 1; k < A.d.n_actions; ++k) {
+                if (q_on[k] > q_on[best]) best = k;
+                tmax = fmaxf(tmax, q_tg[k]);
+            }
+            const float tq = A.double_dqn ? q_tg[best] : tmax;
+            const size_t o = (size_t)g * B + gr;
+            A.y[o] = A.r_hat[o] + (A.gamma * (1.0f - A.done_b[o])) * tq;
+            for (int k = 0; k < 4; ++k) {
+                A.q_next[o * 4 + k] = q_on[k];
+                A.tq_all[o * 4 + k] = q_tg[k];
+            }
         }
     }
     if (!ok && threadIdx.x == 0) atomicExch(A.error, 3);
@@ -466,7 +529,7 @@ __global__ void __launch_bounds__(NT, 1) tc_target_kernel(const TcArgs A) {
 // K4a
 // ------------------------------------------------------------------------------------------
 template <int PASSES>
-__global__ void __launch_bounds__(NT, 1) tc_online_kernel(const TcArgs A) {
+__global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A) {
     extern __shared__ uint8_t smem_raw[];
     const int g = blockIdx.x / A.tiles, rt = blockIdx.x % A.tiles;
     if (!A.active[g]) return;
@@ -477,18 +540,31 @@ __global__ void __launch_bounds__(NT, 1) tc_online_kernel(const TcArgs A) {
     const int32_t* rows = A.rows + sb;
     const float* P = A.nets.theta + (size_t)g * A.L.stride;
     const uint32_t tmem = tc_prologue(sbase);
+    uint32_t cnt[4] = {0, 0, 0, 0};
+    bool ok = true;
+    if (threadIdx.x >= NT) {
+        // ---- MMA warp: lane 0 issues every tcgen05.mma of this CTA ----
+        if (threadIdx.x == NT) {
+            ok &= gemm_mma<PASSES, false>(sbase, tmem, sbase + Fwd::R, sbase + Fwd::XLO, 0, Dp, cnt);
+            ok &= gemm_mma<PASSES, false>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, H, cnt);
+            ok &= gemm_mma<PASSES, true>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, H, cnt);
+            if (!ok) atomicExch(A.error, 14);
+        }
+        __syncwarp();
+        tc_epilogue(tmem);
+        return;
+    }
     const Epi e;
     const int gr = r0 + e.row;
     const bool valid = gr < B;
-    uint32_t uses[4] = {0, 0, 0, 0};
-    bool ok = true;
 
     gather_x<PASSES>(sbase, A.rp.obs, rows, r0, B, Dp);
     load_small_params(sbase, P, A.L);
-    ok &= gemm_stream<PASSES, false>(sbase, tmem, sbase + Fwd::R, sbase + Fwd::XLO, 0, P + A.L.w1, H, Dp, uses);
+    prod_sync();   // biases / head weights visible to every epilogue thread
+    ok &= gemm_produce<PASSES, false>(sbase, P + A.L.w1, H, Dp, cnt);
     uint32_t mask1[4], mask2[4];
     epi_hidden<PASSES>(sbase, tmem, e, Fwd::BIAS1, valid ? A.h1 + sb * H + gr : nullptr, B, mask1);
-    ok &= gemm_stream<PASSES, false>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, P + A.L.w2, H, H, uses);
+    ok &= gemm_produce<PASSES, false>(sbase, P + A.L.w2, H, H, cnt);
     float q[4];
     epi_head(sbase, tmem, e, true, mask2, q, P + A.L.b3);
 
@@ -518,7 +594,7 @@ __global__ void __launch_bounds__(NT, 1) tc_online_kernel(const TcArgs A) {
         reinterpret_cast<int*>(rowf)[5 * BM + e.row] = valid ? ai : -1;
         rowf[6 * BM + e.row] = gi;
     }
-    __syncthreads();
+    prod_sync();
     if (threadIdx.x == 0) {                               // per-tile loss / metric partials, rows in order
         float ls = 0.f, qsum = 0.f, qsq = 0.f, hist[4] = {0.f, 0.f, 0.f, 0.f};
         for (int i = 0; i < BM && r0 + i < B; ++i) {
@@ -563,7 +639,7 @@ __global__ void __launch_bounds__(NT, 1) tc_online_kernel(const TcArgs A) {
         reinterpret_cast<float4*>(A.part_w3 + pt * H * 4)[j] = make_float4(d0, d1, d2, d3);
         A.part_b2[pt * H + j] = s2;
     }
-    __syncthreads();      // R is rewritten with dh2 below
+    prod_sync();          // R is rewritten with dh2 below
 
     // dh2[j] = relu'(h2[j]) * g * W3[j][a]  (dq has one non-zero per row): hi -> R, lo -> TMEM, raw -> scratch
 #pragma unroll 1
@@ -593,13 +669,9 @@ __global__ void __launch_bounds__(NT, 1) tc_online_kernel(const TcArgs A) {
         if (PASSES == 3) tmem_st32(tmem + e.lane_addr + 256u + (uint32_t)c0, lo);
     }
     if (PASSES == 3) tmem_st_wait();
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
 
     // dh1 = (dh2 W2^T) * relu'(h1)
-    ok &= gemm_stream<PASSES, true>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, P + A.L.w2, H, H, uses);
+    ok &= gemm_produce<PASSES, true>(sbase, P + A.L.w2, H, H, cnt);
 #pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {
         const int c0 = e.half * 128 + cc * 32;
@@ -769,13 +841,7 @@ __global__ void __launch_bounds__(NT, 2) tc_wgrad_kernel(const TcArgs A) {
     issue(0);
     cp_commit();
     for (int c = 0; c < nchunks; ++c) {
-        if (c + 1 < nchunks) {
-            const int b = (c + 1) % Wg::STAGES;
-            if (uses[b]) ok &= mbar_wait(sbase + Wg::BARS + 8 * b, (uses[b] - 1) & 1);
-            issue(c + 1);
-        }
-        cp_commit();
-        cp_wait<1>();
+        cp_wait<0>();
         const uint32_t st = sbase + (c % Wg::STAGES) * Wg::STG;
         if (PASSES == 3) {
 #pragma unroll
@@ -817,6 +883,13 @@ __global__ void __launch_bounds__(NT, 2) tc_wgrad_kernel(const TcArgs A) {
             umma_commit(sbase + Wg::BARS + 8 * (c % Wg::STAGES));
         }
         uses[c % Wg::STAGES] += 1;
+        // refill the other stage (read by the MMAs of chunk c-1) while the MMAs of chunk c run
+        if (c + 1 < nchunks) {
+            const int b = (c + 1) % Wg::STAGES;
+            if (uses[b]) ok &= mbar_wait(sbase + Wg::BARS + 8 * b, (uses[b] - 1) & 1);
+            issue(c + 1);
+        }
+        cp_commit();
     }
     {
         const int last = (nchunks - 1) % Wg::STAGES;
@@ -841,7 +914,7 @@ __global__ void __launch_bounds__(NT, 2) tc_wgrad_kernel(const TcArgs A) {
         for (int j = 0; j < 32; j += 4)
             *reinterpret_cast<float4*>(tile + lane * Wg::TLD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         __syncwarp();
-#pragma unroll 2
+#pragma unroll 4
         for (int it = 0; it < 8; ++it) {
             const int r = it * 4 + rsub;
             const int m = m0 + (warp & 3) * 32 + r;
@@ -882,11 +955,11 @@ int launch_tc(const TcArgs& A, int stages, cudaStream_t s) {
     }
     const int grid = A.d.n_nets * A.tiles;
     if (stages & DMDQN_STAGE_TARGET) {
-        tc_target_kernel<PASSES><<<grid, NT, smem_f, s>>>(A);
+        tc_target_kernel<PASSES><<<grid, NT_F, smem_f, s>>>(A);
         DMDQN_CUDA(cudaGetLastError());
     }
     if (stages & DMDQN_STAGE_ONLINE) {
-        tc_online_kernel<PASSES><<<grid, NT, smem_f, s>>>(A);
+        tc_online_kernel<PASSES><<<grid, NT_F, smem_f, s>>>(A);
         DMDQN_CUDA(cudaGetLastError());
     }
     if (stages & DMDQN_STAGE_WGRAD) {

@@ -24,7 +24,7 @@ def main():
         return
     import torch
     lib = C.CDLL(SO)
-    lib.umma_probe.argtypes = [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]
+    lib.umma_probe.argtypes = [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_void_p]
     torch.manual_seed(0)
     names = {0: "K-major SW128", 1: "MN-major B32", 2: "K-major SW64"}
     anames = {0: "A K-major", 1: "A MN-major", 2: "A_lo via TMEM"}
@@ -34,14 +34,20 @@ def main():
         A = torch.randn(128, K, device="cuda")
         B = torch.randn((K, N) if b_mn == 1 else (N, K), device="cuda")
         D = torch.full((128, N), float("nan"), device="cuda")
-        st = torch.zeros(1, dtype=torch.int32, device="cuda")
+        st = torch.zeros(4, dtype=torch.int32, device="cuda")
         A_in = A.t().contiguous() if a_mode == 1 else A          # MN-major A is given as [K][128]
-        rc = lib.umma_probe(A_in.data_ptr(), B.data_ptr(), D.data_ptr(), K, N, b_mn, three, a_mode, st.data_ptr(), None)
+        rc = lib.umma_probe(A_in.data_ptr(), B.data_ptr(), D.data_ptr(), K, N, b_mn, three, a_mode, st.data_ptr(), 1, None)
         torch.cuda.synchronize()
         ref = A.double() @ (B.double() if b_mn == 1 else B.double().T)
         err = (D.double() - ref).abs().max().item()
         rel = err / ref.abs().max().item()
-        print(f"K={K:3d} N={N:3d} B={names[b_mn]:14s} {anames[a_mode]:14s} {'3xTF32' if three else 'TF32  '} rc={rc} status={int(st)} "
+        t1 = torch.zeros(4, dtype=torch.int32, device="cuda"); t2 = torch.zeros(4, dtype=torch.int32, device="cuda")
+        lib.umma_probe(A_in.data_ptr(), B.data_ptr(), D.data_ptr(), K, N, b_mn, three, a_mode, t1.data_ptr(), 8, None)
+        lib.umma_probe(A_in.data_ptr(), B.data_ptr(), D.data_ptr(), K, N, b_mn, three, a_mode, t2.data_ptr(), 40, None)
+        torch.cuda.synchronize()
+        cyc = (int(t2[1]) - int(t1[1])) / max(1, int(t2[2]) - int(t1[2]))
+        cyc2 = (int(t2[3]) - int(t1[3])) / ((40 - 8) * 4 * 8)
+        print(f"K={K:3d} N={N:3d} B={names[b_mn]:14s} {anames[a_mode]:14s} {'3xTF32' if three else 'TF32  '} rc={rc} status={int(st[0])} cyc/MMA={cyc:6.1f} back-to-back={cyc2:6.1f} "
               f"max_abs_err={err:.3e} rel={rel:.3e}", flush=True)
 
 

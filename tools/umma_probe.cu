@@ -60,7 +60,7 @@ __device__ __forceinline__ uint32_t off_mnmajor(int n_total, int k, int n) {
 
 __global__ void __launch_bounds__(128, 1)
 probe_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int K, int N,
-             int b_mode, int three_pass, int a_mode, int* status) {
+             int b_mode, int three_pass, int a_mode, int* status, int reps) {
     const int b_mn = b_mode == 1;
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t mbar;
@@ -121,6 +121,8 @@ probe_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __
                                ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
         uint32_t accum = 0;
         const int passes = three_pass ? 3 : 1;
+        const long long t0 = clock64();
+        for (int rep = 0; rep < reps; ++rep)
         for (int p = 0; p < passes; ++p) {
             // small terms first: A_lo*B, A*B_lo, then A*B (the hardware truncates to tf32 itself)
             const uint8_t* a_src = (three_pass && p == 0) ? sAl : sA;
@@ -139,6 +141,36 @@ probe_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __
             }
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
+        uint32_t d2 = 0;
+        for (int spin = 0; spin < (1 << 24) && !d2; ++spin)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                         : "=r"(d2) : "r"(smem_u32(&mbar)), "r"(0u) : "memory");
+        status[1] = (int)(clock64() - t0);
+        status[2] = reps * passes * (K / 8);
+        // issue-rate test: 8 precomputed descriptor pairs, MMAs back to back
+        uint64_t ad[8], bd[8];
+        for (int q = 0; q < 8; ++q) {
+            const int k = (q * 8) % K;
+            ad[q] = a_mode == 1 ? make_desc(smem_u32(sA) + (k >> 2) * 4 * 512, 512, 4 * 512, 1)
+                                : make_desc(smem_u32(sA) + (k >> 5) * (128 * 128) + ((k & 31) >> 3) * 32, 16, 1024);
+            if (b_mn) bd[q] = make_desc(smem_u32(sB) + (k >> 2) * (N >> 5) * 512, 512, (N >> 5) * 512, 1);
+            else if (b_mode == 2) bd[q] = make_desc(smem_u32(sB) + (k >> 4) * (N * 64) + ((k & 15) >> 3) * 32, 16, 512, 4);
+            else bd[q] = make_desc(smem_u32(sB) + (k >> 5) * (N * 128) + ((k & 31) >> 3) * 32, 16, 1024);
+        }
+        const long long t1 = clock64();
+        for (int rep = 0; rep < reps * 4; ++rep) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (a_mode == 2) mma_tf32_ts(tmem, tmem + 256u + (uint32_t)(q * 8 % K), bd[q], idesc, 1u);
+                else mma_tf32(tmem, ad[q], bd[q], idesc, 1u);
+            }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
+        uint32_t d3 = 0;
+        for (int spin = 0; spin < (1 << 24) && !d3; ++spin)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                         : "=r"(d3) : "r"(smem_u32(&mbar)), "r"(1u) : "memory");
+        status[3] = (int)(clock64() - t1);
     }
     // bounded wait (a broken descriptor must not hang the GPU)
     uint32_t done = 0;
@@ -174,10 +206,10 @@ probe_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __
 }  // namespace
 
 extern "C" int umma_probe(const float* A, const float* B, float* D, int K, int N, int b_mode, int three_pass, int a_mode,
-                          int* status, void* stream) {
+                          int* status, int reps, void* stream) {
     const size_t smem = 2 * (size_t)(128 * K * 4) + 2 * (size_t)N * K * 4 + 1024;
     cudaError_t e = cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return -2;
-    probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, K, N, b_mode, three_pass, a_mode, status);
+    probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, K, N, b_mode, three_pass, a_mode, status, reps);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

@@ -363,7 +363,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "tf32"])
+    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()

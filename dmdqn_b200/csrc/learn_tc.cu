@@ -158,6 +158,7 @@ struct TcArgs {
     double lr, beta1, beta2, adam_eps, tau;
     const int32_t *rows, *act_b, *active, *step_t;
     const float *r_hat, *done_b;
+    const float4* adam_sc;
     float *y, *gcoef, *q_all, *q_next, *tq_all, *h1, *dh1, *dh2, *part_loss, *part_b3, *part_w3, *part_b2, *metrics, *grads;
     int* error;
 };
@@ -192,65 +193,95 @@ struct Pipe {
     static constexpr int NST = BT ? 2 : 4;
     static constexpr uint32_t HALF = KCX * H * 4;             // bytes of the hi (or lo) part of a stage
     static constexpr int PIECES = KCX * H / 4 / NT;           // 16-byte pieces per producer thread per chunk
+    static constexpr int DIST = BT ? 2 : 4;                   // chunks held in registers ahead of the one being staged
 };
 
+__device__ __forceinline__ float4 ldg_stream(const float* p) {   // volatile: issue order = program order
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ldg_plain(const float* p) {    // coherent (the same kernel writes these arrays), issue order kept
+    float4 v;
+    asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void sts4(uint32_t a, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// Producer side of a streamed GEMM.  The weight chunks travel global -> registers -> (hi | lo) -> shared
+// memory: the global loads of chunk c + DIST are issued when chunk c is staged, so DIST chunks (about
+// DIST * 384 cycles of MMA time) of L2 / HBM latency are covered by registers, independently of the number
+// of shared-memory stages; the only shared-memory traffic of a chunk is its two 16-byte stores per piece.
+// begin() can be called ahead of the epilogue that produces the A operand, run() after it.
 template <int PASSES, bool BT>
-__device__ __forceinline__ bool gemm_produce(uint32_t sbase, const float* __restrict__ W, int ldw, int K, uint32_t (&cnt)[4]) {
+struct WStream {
     using P = Pipe<BT>;
-    const int tid = threadIdx.x;
-    const uint32_t full0 = sbase + Fwd::BARS, empty0 = full0 + 32;
-    const int nchunks = K / P::KCX;
-    bool ok = true;
-    auto piece_off = [&](int p) -> uint32_t {
-        if (!BT) return off_mn(H, p >> 6, (p & 63) << 2);     // k-row p/64, column piece p%64
-        return off_k64(H, p >> 2, (p & 3) << 2);              // row n = p/4, k piece p%4
-    };
-    auto issue = [&](int c) {
-        const int b = c % P::NST;
-        if (cnt[b]) ok &= mbar_wait(empty0 + 8 * b, (cnt[b] - 1) & 1);   // the MMAs that read this stage are done
-        cnt[b] += 1;
-        const uint32_t st = sbase + Fwd::WB + b * (2 * P::HALF);
+    float4 buf[P::DIST][P::PIECES];
+    const float* src[P::PIECES];
+    uint32_t dst[P::PIECES];
+    int nchunks;
+
+    __device__ __forceinline__ void load(int slot, int c) {
+#pragma unroll
+        for (int r = 0; r < P::PIECES; ++r) buf[slot][r] = ldg_stream(src[r] + (BT ? (size_t)c * P::KCX : (size_t)c * P::KCX * H));
+    }
+    // W: [K][H] row-major (BT = false) or [H][K] row-major (BT = true); both have leading dimension H here
+    __device__ __forceinline__ void begin(const float* __restrict__ W, int K) {
+        const int tid = threadIdx.x;
+        nchunks = K / P::KCX;
 #pragma unroll
         for (int r = 0; r < P::PIECES; ++r) {
             const int p = tid + r * NT;
-            if (!BT) cp16(st + piece_off(p), W + (size_t)(c * P::KCX + (p >> 6)) * ldw + ((p & 63) << 2));
-            else cp16(st + piece_off(p), W + (size_t)(p >> 2) * ldw + c * P::KCX + ((p & 3) << 2));
-        }
-    };
-#pragma unroll
-    for (int c = 0; c < P::NST - 1; ++c) {
-        if (c < nchunks) issue(c);
-        cp_commit();
-    }
-    for (int c = 0; c < nchunks; ++c) {
-        cp_wait<P::NST - 2>();                                // this thread's pieces of chunk c have landed
-        const uint32_t st = sbase + Fwd::WB + (c % P::NST) * (2 * P::HALF);
-        if (PASSES == 3) {                                    // split them: hi in place, lo beside
-#pragma unroll
-            for (int r = 0; r < P::PIECES; ++r) {
-                const uint32_t o = piece_off(tid + r * NT);
-                float4 x, hi, lo;
-                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(st + o));
-                split4<3>(x, hi, lo);
-                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(st + o), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
-                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(st + P::HALF + o), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+            if (!BT) {                                            // k-row p/64, column piece p%64
+                src[r] = W + (size_t)(p >> 6) * H + ((p & 63) << 2);
+                dst[r] = off_mn(H, p >> 6, (p & 63) << 2);
+            } else {                                              // row n = p/4, k piece p%4
+                src[r] = W + (size_t)(p >> 2) * H + ((p & 3) << 2);
+                dst[r] = off_k64(H, p >> 2, (p & 3) << 2);
             }
         }
-        fence_async_smem();                                   // generic-proxy writes (this chunk, and the A operand before it)
-        tc_fence_before();
-        __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(full0 + 8 * (c % P::NST));   // one arrival per producer warp
-        // only now block on the MMAs of chunk c-1 (their stage is refilled with chunk c+NST-1): the split of
-        // chunk c above overlaps with them instead of queueing behind them
-        if (c + P::NST - 1 < nchunks) issue(c + P::NST - 1);
-        cp_commit();
+#pragma unroll
+        for (int j = 0; j < P::DIST; ++j)
+            if (j < nchunks) load(j, j);
     }
-    // all MMAs of this GEMM complete (a commit tracks every earlier MMA of the issuing thread)
-    const int last = (nchunks - 1) % P::NST;
-    ok &= mbar_wait(empty0 + 8 * last, (cnt[last] - 1) & 1);
-    tc_fence_after();
-    return ok;
-}
+    __device__ __forceinline__ bool run(uint32_t sbase, uint32_t (&cnt)[4]) {
+        const uint32_t full0 = sbase + Fwd::BARS, empty0 = full0 + 32;
+        bool ok = true;
+        for (int c0 = 0; c0 < nchunks; c0 += P::DIST) {
+#pragma unroll
+            for (int j = 0; j < P::DIST; ++j) {
+                static_assert(P::DIST == P::NST, "stage index below is the unrolled j");
+                const int c = c0 + j;                             // nchunks is a multiple of DIST
+                const int b = j;
+                float4 x[P::PIECES];
+#pragma unroll
+                for (int r = 0; r < P::PIECES; ++r) x[r] = buf[j][r];
+                if (c + P::DIST < nchunks) load(j, c + P::DIST);
+                if (cnt[b]) ok &= mbar_wait(empty0 + 8 * b, (cnt[b] - 1) & 1);   // the MMAs that read this stage are done
+                cnt[b] += 1;
+                const uint32_t st = sbase + Fwd::WB + b * (2 * P::HALF);
+#pragma unroll
+                for (int r = 0; r < P::PIECES; ++r) {
+                    float4 hi, lo;
+                    split4<PASSES>(x[r], hi, lo);
+                    sts4(st + dst[r], hi);
+                    if (PASSES == 3) sts4(st + P::HALF + dst[r], lo);
+                }
+                fence_async_smem();                               // generic-proxy writes (this chunk, and the A operand before it)
+                tc_fence_before();
+                __syncwarp();
+                if ((threadIdx.x & 31) == 0) mbar_arrive(full0 + 8 * b);         // one arrival per producer warp
+            }
+        }
+        // all MMAs of this GEMM complete (a commit tracks every earlier MMA of the issuing thread)
+        constexpr int last = P::NST - 1;                          // nchunks is a multiple of NST
+        ok &= mbar_wait(empty0 + 8 * last, (cnt[last] - 1) & 1);
+        tc_fence_after();
+        return ok;
+    }
+};
 
 template <int PASSES, bool BT>
 __device__ __forceinline__ bool gemm_mma(uint32_t sbase, uint32_t tmem, uint32_t a_hi, uint32_t a_lo_smem,
@@ -265,58 +296,80 @@ __device__ __forceinline__ bool gemm_mma(uint32_t sbase, uint32_t tmem, uint32_t
     const uint64_t a_lo0 = make_desc(a_lo_smem, 16, 1024, 2);
     const uint64_t b0 = BT ? make_desc(sbase + Fwd::WB, 16, 512, 4) : make_desc(sbase + Fwd::WB, 512, 4096, 1);
     constexpr uint32_t KSTEP_B = BT ? 32 : 2 * 4096;          // bytes between the k-steps of a chunk in the B stage
-    for (int c = 0; c < nchunks; ++c) {
-        const int b = c % P::NST;
-        ok &= mbar_wait(full0 + 8 * b, cnt[b] & 1);           // all 8 producer warps have published chunk c
-        cnt[b] += 1;
-        tc_fence_after();
+    for (int c0 = 0; c0 < nchunks; c0 += P::NST) {
 #pragma unroll
-        for (int ks = 0; ks < P::KCX / 8; ++ks) {
-            const int kg = c * P::KCX + ks * 8;
-            const uint32_t a_off = ((uint32_t)(kg >> 5) * ATOM + (uint32_t)((kg & 31) >> 3) * 32) >> 4;
-            const uint32_t b_off = ((uint32_t)b * (2 * P::HALF) + ks * KSTEP_B) >> 4;
-            const uint64_t a_hi_d = a_hi0 + a_off;
-            const uint64_t b_hi = b0 + b_off, b_lo = b0 + b_off + (P::HALF >> 4);
-            uint32_t acc = (c | ks) ? 1u : 0u;
-            if (PASSES == 3) {                                // small terms first
-                if (a_lo_smem) mma_ss(tmem, a_lo0 + a_off, b_hi, idesc, acc);
-                else mma_ts(tmem, a_lo_tmem + (uint32_t)kg, b_hi, idesc, acc);
-                mma_ss(tmem, a_hi_d, b_lo, idesc, 1u);
-                acc = 1u;
+        for (int b = 0; b < P::NST; ++b) {                    // nchunks is a multiple of NST
+            const int c = c0 + b;
+            ok &= mbar_wait(full0 + 8 * b, cnt[b] & 1);       // all 8 producer warps have published chunk c
+            cnt[b] += 1;
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < P::KCX / 8; ++ks) {
+                const int kg = c * P::KCX + ks * 8;
+                const uint32_t a_off = ((uint32_t)(kg >> 5) * ATOM + (uint32_t)((kg & 31) >> 3) * 32) >> 4;
+                const uint32_t b_off = ((uint32_t)b * (2 * P::HALF) + ks * KSTEP_B) >> 4;
+                const uint64_t a_hi_d = a_hi0 + a_off;
+                const uint64_t b_hi = b0 + b_off, b_lo = b0 + b_off + (P::HALF >> 4);
+                uint32_t acc = (c | ks) ? 1u : 0u;
+                if (PASSES == 3) {                            // small terms first
+                    if (a_lo_smem) mma_ss(tmem, a_lo0 + a_off, b_hi, idesc, acc);
+                    else mma_ts(tmem, a_lo_tmem + (uint32_t)kg, b_hi, idesc, acc);
+                    mma_ss(tmem, a_hi_d, b_lo, idesc, 1u);
+                    acc = 1u;
+                }
+                mma_ss(tmem, a_hi_d, b_hi, idesc, acc);
             }
-            mma_ss(tmem, a_hi_d, b_hi, idesc, acc);
+            umma_commit(empty0 + 8 * b);
         }
-        umma_commit(empty0 + 8 * b);
     }
     return ok;
 }
 
 // Gather 128 observation rows -> hi (R) and lo (R + XLO), K-major SW128; rows past the batch are zero.
+// begin() issues every load of the thread (row ids first, then up to 12 independent 16-byte pieces, the
+// pieces of a row on consecutive lanes); store() splits and writes them once R is free.
 template <int PASSES>
-__device__ __forceinline__ void gather_x(uint32_t sbase, const float* __restrict__ ring, const int32_t* __restrict__ rows,
-                                         int r0, int B, int Dp) {
-    const int q = Dp >> 2;                                    // 16-byte pieces per row
-    const int total = BM * q;
-    // four independent loads in flight per thread per round (the sampled rows were prefetched into L2 by K1b)
-    for (int f0 = threadIdx.x; f0 < total; f0 += 4 * NT) {
-        float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0, x2 = x0, x3 = x0;
-        const int f1 = f0 + NT, f2 = f0 + 2 * NT, f3 = f0 + 3 * NT;
-        if (r0 + f0 / q < B) x0 = __ldg(reinterpret_cast<const float4*>(ring + (size_t)__ldg(rows + r0 + f0 / q) * Dp + ((f0 % q) << 2)));
-        if (f1 < total && r0 + f1 / q < B) x1 = __ldg(reinterpret_cast<const float4*>(ring + (size_t)__ldg(rows + r0 + f1 / q) * Dp + ((f1 % q) << 2)));
-        if (f2 < total && r0 + f2 / q < B) x2 = __ldg(reinterpret_cast<const float4*>(ring + (size_t)__ldg(rows + r0 + f2 / q) * Dp + ((f2 % q) << 2)));
-        if (f3 < total && r0 + f3 / q < B) x3 = __ldg(reinterpret_cast<const float4*>(ring + (size_t)__ldg(rows + r0 + f3 / q) * Dp + ((f3 % q) << 2)));
-        auto put = [&](int f, const float4& x) {
-            if (f >= total) return;
-            float4 hi, lo;
-            split4<PASSES>(x, hi, lo);
-            const uint32_t o = off_k128(BM, f / q, (f % q) << 2);
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sbase + Fwd::R + o), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
-            if (PASSES == 3)
-                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sbase + Fwd::XLO + o), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
-        };
-        put(f0, x0); put(f1, x1); put(f2, x2); put(f3, x3);
+struct XGather {
+    static constexpr int MAXP = BM * 96 / 4 / NT;             // 12 pieces per thread at obs_stride = 96
+    float4 x[MAXP];
+    uint32_t off[MAXP];
+    int n;
+
+    __device__ __forceinline__ void begin(const float* __restrict__ ring, const int32_t* __restrict__ rows, int r0, int B, int Dp) {
+        const int q = Dp >> 2;                                // 16-byte pieces per row
+        n = BM * q / NT;
+        const int dr = NT / q, dp = NT % q;
+        int r = threadIdx.x / q, pc = threadIdx.x % q;
+        int32_t rid[MAXP], col[MAXP];
+#pragma unroll
+        for (int j = 0; j < MAXP; ++j) {
+            rid[j] = -1;
+            if (j < n) {
+                if (r0 + r < B) rid[j] = __ldg(rows + r0 + r);
+                off[j] = off_k128(BM, r, pc << 2);
+                col[j] = pc << 2;
+                r += dr; pc += dp;
+                if (pc >= q) { pc -= q; r += 1; }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < MAXP; ++j) {
+            x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < n && rid[j] >= 0) x[j] = ldg_stream(ring + (size_t)rid[j] * Dp + col[j]);
+        }
     }
-}
+    __device__ __forceinline__ void store(uint32_t sbase) {
+#pragma unroll
+        for (int j = 0; j < MAXP; ++j) {
+            if (j < n) {
+                float4 hi, lo;
+                split4<PASSES>(x[j], hi, lo);
+                sts4(sbase + Fwd::R + off[j], hi);
+                if (PASSES == 3) sts4(sbase + Fwd::XLO + off[j], lo);
+            }
+        }
+    }
+};
 
 // Per-thread epilogue coordinates: thread = batch row of the tile, two warps share a TMEM
 // sub-partition and split the 256 columns in halves.
@@ -448,77 +501,52 @@ __device__ __forceinline__ void tc_epilogue(uint32_t tmem) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K3
+// K3: one CTA = (network, 128-row tile, which parameter set): Q(s') of the online net (-> q_next) or of the
+// target net (-> tq_all).  The two halves are independent CTAs (twice as many, half as long: less tail on
+// 148 SMs); K4a combines them into the TD target of its rows (reference :342-347).
 // ------------------------------------------------------------------------------------------
 template <int PASSES>
 __global__ void __launch_bounds__(NT_F, 1) tc_target_kernel(const TcArgs A) {
     extern __shared__ uint8_t smem_raw[];
-    const int g = blockIdx.x / A.tiles, rt = blockIdx.x % A.tiles;
+    const int item = blockIdx.x >> 1, pass = blockIdx.x & 1;          // 0: online(s')  1: target(s')
+    const int g = item / A.tiles, rt = item % A.tiles;
     if (!A.active[g]) return;
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int B = A.d.batch, Dp = A.d.obs_stride, r0 = rt * BM;
-    const int32_t* rows = A.rows + (size_t)g * B;
     const uint32_t tmem = tc_prologue(sbase);
     uint32_t cnt[4] = {0, 0, 0, 0};
     bool ok = true;
     if (threadIdx.x >= NT) {
         // ---- MMA warp: lane 0 issues every tcgen05.mma of this CTA ----
         if (threadIdx.x == NT) {
-            for (int pass = 0; pass < 2; ++pass) {
-                ok &= gemm_mma<PASSES, false>(sbase, tmem, sbase + Fwd::R, sbase + Fwd::XLO, 0, Dp, cnt);
-                ok &= gemm_mma<PASSES, false>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, H, cnt);
-            }
+            ok &= gemm_mma<PASSES, false>(sbase, tmem, sbase + Fwd::R, sbase + Fwd::XLO, 0, Dp, cnt);
+            ok &= gemm_mma<PASSES, false>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, H, cnt);
             if (!ok) atomicExch(A.error, 13);
         }
         __syncwarp();
     } else {
         const Epi e;
-        float q_on[4], q_tg[4];
-#ifdef TC_TIMING
-        long long tt[12]; int ti = 0;
-#define TSTAMP() tt[ti++] = clock64()
-#else
-#define TSTAMP()
-#endif
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {          // 0: online(s')  1: target(s')
-            const float* P = (pass == 0 ? A.nets.theta : A.nets.theta_tgt) + (size_t)g * A.L.stride;
-            TSTAMP();
-            gather_x<PASSES>(sbase, A.rp.next_obs, rows, r0, B, Dp);
+        const float* P = (pass == 0 ? A.nets.theta : A.nets.theta_tgt) + (size_t)g * A.L.stride;
+        float q[4];
+        WStream<PASSES, false> ws;
+        ws.begin(P + A.L.w1, Dp);                      // first W1 chunks in flight before anything else
+        {
+            XGather<PASSES> xg;
+            xg.begin(A.rp.next_obs, A.rows + (size_t)g * B, r0, B, Dp);
             load_small_params(sbase, P, A.L);
-            prod_sync();   // biases / head weights visible to every epilogue thread
-            TSTAMP();
-            ok &= gemm_produce<PASSES, false>(sbase, P + A.L.w1, H, Dp, cnt);
-            TSTAMP();
-            uint32_t mask[4];
-            epi_hidden<PASSES>(sbase, tmem, e, Fwd::BIAS1, nullptr, 0, mask);
-            TSTAMP();
-            ok &= gemm_produce<PASSES, false>(sbase, P + A.L.w2, H, H, cnt);
-            TSTAMP();
-            epi_head(sbase, tmem, e, false, mask, pass == 0 ? q_on : q_tg, P + A.L.b3);
-            prod_sync();   // q partials consumed; R / TMEM free for the next pass
-            TSTAMP();
+            xg.store(sbase);
         }
-#ifdef TC_TIMING
-        if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 300))
-            printf("K3 cta %d: gather %lld L1 %lld epi1 %lld L2 %lld epi2 %lld | gather %lld L1 %lld epi1 %lld L2 %lld epi2 %lld\n", blockIdx.x,
-                   tt[1]-tt[0], tt[2]-tt[1], tt[3]-tt[2], tt[4]-tt[3], tt[5]-tt[4], tt[7]-tt[6], tt[8]-tt[7], tt[9]-tt[8], tt[10]-tt[9], tt[11]-tt[10]);
-#endif
+        prod_sync();   // biases / head weights visible to every epilogue thread
+        ok &= ws.run(sbase, cnt);
+        ws.begin(P + A.L.w2, H);                       // W2 chunks travel while the epilogue runs
+        uint32_t mask[4];
+        epi_hidden<PASSES>(sbase, tmem, e, Fwd::BIAS1, nullptr, 0, mask);
+        ok &= ws.run(sbase, cnt);
+        epi_head(sbase, tmem, e, false, mask, q, P + A.L.b3);
         const int gr = r0 + e.row;
         if (e.half == 0 && gr < B) {
-            int best = 0;
-            float tmax = q_tg[0];
-            for (int k = 1; k < A.d.n_actions; ++k) {
-                if (q_on[k] > q_on[best]) best = k;
-                tmax = fmaxf(tmax, q_tg[k]);
-            }
-            const float tq = A.double_dqn ? q_tg[best] : tmax;
-            const size_t o = (size_t)g * B + gr;
-            A.y[o] = A.r_hat[o] + (A.gamma * (1.0f - A.done_b[o])) * tq;
-            for (int k = 0; k < 4; ++k) {
-                A.q_next[o * 4 + k] = q_on[k];
-                A.tq_all[o * 4 + k] = q_tg[k];
-            }
+            float* out = (pass == 0 ? A.q_next : A.tq_all) + ((size_t)g * B + gr) * 4;
+            *reinterpret_cast<float4*>(out) = make_float4(q[0], q[1], q[2], q[3]);
         }
     }
     if (!ok && threadIdx.x == 0) atomicExch(A.error, 3);
@@ -558,13 +586,38 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A) {
     const int gr = r0 + e.row;
     const bool valid = gr < B;
 
-    gather_x<PASSES>(sbase, A.rp.obs, rows, r0, B, Dp);
-    load_small_params(sbase, P, A.L);
+    WStream<PASSES, false> ws;
+    ws.begin(P + A.L.w1, Dp);
+    {
+        XGather<PASSES> xg;
+        xg.begin(A.rp.obs, rows, r0, B, Dp);
+        load_small_params(sbase, P, A.L);
+        xg.store(sbase);
+    }
+    // TD target of this row from the two halves of K3 (reference :342-347), ties -> lowest index
+    float yi = 0.f;
+    if (valid) {
+        const float4 qo = *reinterpret_cast<const float4*>(A.q_next + (sb + gr) * 4);
+        const float4 qt = *reinterpret_cast<const float4*>(A.tq_all + (sb + gr) * 4);
+        const float q_on[4] = {qo.x, qo.y, qo.z, qo.w}, q_tg[4] = {qt.x, qt.y, qt.z, qt.w};
+        float bmax = q_on[0], tq = q_tg[0], tmax = q_tg[0];
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+            if (k < A.d.n_actions) {
+                if (q_on[k] > bmax) { bmax = q_on[k]; tq = q_tg[k]; }
+                tmax = fmaxf(tmax, q_tg[k]);
+            }
+        }
+        tq = A.double_dqn ? tq : tmax;
+        yi = A.r_hat[sb + gr] + (A.gamma * (1.0f - A.done_b[sb + gr])) * tq;
+        if (e.half == 0) A.y[sb + gr] = yi;
+    }
     prod_sync();   // biases / head weights visible to every epilogue thread
-    ok &= gemm_produce<PASSES, false>(sbase, P + A.L.w1, H, Dp, cnt);
+    ok &= ws.run(sbase, cnt);
+    ws.begin(P + A.L.w2, H);
     uint32_t mask1[4], mask2[4];
     epi_hidden<PASSES>(sbase, tmem, e, Fwd::BIAS1, valid ? A.h1 + sb * H + gr : nullptr, B, mask1);
-    ok &= gemm_produce<PASSES, false>(sbase, P + A.L.w2, H, H, cnt);
+    ok &= ws.run(sbase, cnt);
     float q[4];
     epi_head(sbase, tmem, e, true, mask2, q, P + A.L.b3);
 
@@ -573,7 +626,8 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A) {
     int ai = 0;
     if (valid) {
         ai = A.act_b[sb + gr];
-        const float err = q[ai] - A.y[sb + gr];
+        const float qa = ai == 0 ? q[0] : ai == 1 ? q[1] : ai == 2 ? q[2] : q[3];
+        const float err = qa - yi;
         if (A.loss == DMDQN_LOSS_MSE) {
             term = err * err;
             gi = (2.0f * err) / (float)A.loss_batch;
@@ -641,6 +695,8 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A) {
     }
     prod_sync();          // R is rewritten with dh2 below
 
+    WStream<PASSES, true> wsb;
+    wsb.begin(P + A.L.w2, H);
     // dh2[j] = relu'(h2[j]) * g * W3[j][a]  (dq has one non-zero per row): hi -> R, lo -> TMEM, raw -> scratch
 #pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {
@@ -671,7 +727,7 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A) {
     if (PASSES == 3) tmem_st_wait();
 
     // dh1 = (dh2 W2^T) * relu'(h1)
-    ok &= gemm_produce<PASSES, true>(sbase, P + A.L.w2, H, H, cnt);
+    ok &= wsb.run(sbase, cnt);
 #pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {
         const int c0 = e.half * 128 + cc * 32;
@@ -694,15 +750,15 @@ struct AdamK {
     float alpha, eps, omb1, omb2, tau;
     int sync;
 };
-__device__ __forceinline__ AdamK adam_k(const TcArgs& A, int t) {
+__device__ __forceinline__ AdamK adam_k(const TcArgs& A, int g) {   // scalars prepared by the sample kernel
     AdamK k;
-    const double bc1 = 1.0 - pow(A.beta1, (double)t), bc2 = 1.0 - pow(A.beta2, (double)t);
-    k.alpha = (float)(A.lr * sqrt(bc2) / bc1);
-    k.eps = (float)(A.adam_form == DMDQN_ADAM_KERAS ? A.adam_eps : A.adam_eps * sqrt(bc2));
+    const float4 sc = __ldg(A.adam_sc + g);
+    k.alpha = sc.x;
+    k.eps = sc.y;
+    k.sync = __float_as_int(sc.z);
     k.omb1 = (float)(1.0 - A.beta1);
     k.omb2 = (float)(1.0 - A.beta2);
     k.tau = (float)A.tau;
-    k.sync = A.tau >= 0.0 ? 2 : (t % A.freq == 0 ? 1 : 0);
     return k;
 }
 __device__ __forceinline__ void adam1(const AdamK& k, float g, float& th, float& m, float& v, float& tg) {
@@ -744,7 +800,7 @@ __global__ void __launch_bounds__(NT, 2) tc_wgrad_kernel(const TcArgs A) {
     float* tg = A.nets.theta_tgt + pb;
     float* am = A.nets.adam_m + pb;
     float* av = A.nets.adam_v + pb;
-    const AdamK k = adam_k(A, A.step_t[g]);
+    const AdamK k = adam_k(A, g);
     if (t == 2) {
         // head / bias gradients: per-row-tile partials from K4a summed in tile order, then Adam
         auto upd = [&](int64_t off, float grad) {
@@ -914,27 +970,43 @@ __global__ void __launch_bounds__(NT, 2) tc_wgrad_kernel(const TcArgs A) {
         for (int j = 0; j < 32; j += 4)
             *reinterpret_cast<float4*>(tile + lane * Wg::TLD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         __syncwarp();
-#pragma unroll 4
-        for (int it = 0; it < 8; ++it) {
-            const int r = it * 4 + rsub;
-            const int m = m0 + (warp & 3) * 32 + r;
-            const bool bias_row = !is_w2 && m == Dp;               // db1 from the ones column
-            if (m >= m_valid && !bias_row) continue;
-            const float4 gr4 = *reinterpret_cast<const float4*>(tile + r * Wg::TLD + c4);
-            const int64_t off = bias_row ? A.L.b1 + c0 + c4 : wbase + (int64_t)m * H + c0 + c4;
-            if (A.grads) {
-                *reinterpret_cast<float4*>(A.grads + pb + off) = gr4;
-                continue;
+        // two batches of four row groups: every load of a batch is issued before its first use, so twelve
+        // (sixteen with Polyak) 16-byte loads per thread are in flight while the HBM latency elapses
+#pragma unroll 1
+        for (int it0 = 0; it0 < 8; it0 += 4) {
+            int64_t off[4];
+            bool live[4];
+            float4 gr4[4], t4[4], m4[4], v4[4], g4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = (it0 + u) * 4 + rsub;
+                const int m = m0 + (warp & 3) * 32 + r;
+                const bool bias_row = !is_w2 && m == Dp;           // db1 from the ones column
+                live[u] = m < m_valid || bias_row;
+                off[u] = bias_row ? A.L.b1 + c0 + c4 : wbase + (int64_t)m * H + c0 + c4;
+                gr4[u] = *reinterpret_cast<const float4*>(tile + r * Wg::TLD + c4);
+                g4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live[u] && !A.grads) {
+                    t4[u] = ldg_plain(th + off[u]);
+                    m4[u] = ldg_plain(am + off[u]);
+                    v4[u] = ldg_plain(av + off[u]);
+                    if (k.sync == 2) g4[u] = ldg_plain(tg + off[u]);
+                }
             }
-            float4 t4 = *reinterpret_cast<float4*>(th + off), m4 = *reinterpret_cast<float4*>(am + off);
-            float4 v4 = *reinterpret_cast<float4*>(av + off);
-            float4 g4 = k.sync == 2 ? *reinterpret_cast<float4*>(tg + off) : make_float4(0.f, 0.f, 0.f, 0.f);
-            adam1(k, gr4.x, t4.x, m4.x, v4.x, g4.x); adam1(k, gr4.y, t4.y, m4.y, v4.y, g4.y);
-            adam1(k, gr4.z, t4.z, m4.z, v4.z, g4.z); adam1(k, gr4.w, t4.w, m4.w, v4.w, g4.w);
-            *reinterpret_cast<float4*>(th + off) = t4;
-            *reinterpret_cast<float4*>(am + off) = m4;
-            *reinterpret_cast<float4*>(av + off) = v4;
-            if (k.sync) *reinterpret_cast<float4*>(tg + off) = g4;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (!live[u]) continue;
+                if (A.grads) {
+                    *reinterpret_cast<float4*>(A.grads + pb + off[u]) = gr4[u];
+                    continue;
+                }
+                adam1(k, gr4[u].x, t4[u].x, m4[u].x, v4[u].x, g4[u].x); adam1(k, gr4[u].y, t4[u].y, m4[u].y, v4[u].y, g4[u].y);
+                adam1(k, gr4[u].z, t4[u].z, m4[u].z, v4[u].z, g4[u].z); adam1(k, gr4[u].w, t4[u].w, m4[u].w, v4[u].w, g4[u].w);
+                *reinterpret_cast<float4*>(th + off[u]) = t4[u];
+                *reinterpret_cast<float4*>(am + off[u]) = m4[u];
+                *reinterpret_cast<float4*>(av + off[u]) = v4[u];
+                if (k.sync) *reinterpret_cast<float4*>(tg + off[u]) = g4[u];
+            }
         }
     }
     if (!ok && tid == 0) atomicExch(A.error, 5);
@@ -955,7 +1027,7 @@ int launch_tc(const TcArgs& A, int stages, cudaStream_t s) {
     }
     const int grid = A.d.n_nets * A.tiles;
     if (stages & DMDQN_STAGE_TARGET) {
-        tc_target_kernel<PASSES><<<grid, NT_F, smem_f, s>>>(A);
+        tc_target_kernel<PASSES><<<2 * grid, NT_F, smem_f, s>>>(A);
         DMDQN_CUDA(cudaGetLastError());
     }
     if (stages & DMDQN_STAGE_ONLINE) {
@@ -996,6 +1068,7 @@ int launch_learn_tc(const dmdqn_dims& d, const dmdqn_hparams& hp, const dmdqn_re
     A.act_b = reinterpret_cast<const int32_t*>(ws + w.act_b);
     A.active = reinterpret_cast<const int32_t*>(ws + w.active);
     A.step_t = reinterpret_cast<const int32_t*>(ws + w.step_t);
+    A.adam_sc = reinterpret_cast<const float4*>(ws + w.adam_sc);
     A.r_hat = reinterpret_cast<const float*>(ws + w.r_hat);
     A.done_b = reinterpret_cast<const float*>(ws + w.done_b);
     A.y = reinterpret_cast<float*>(ws + w.y);

@@ -60,7 +60,7 @@ sample_kernel(dmdqn_dims d, dmdqn_hparams hp, dmdqn_replay rp, int32_t* __restri
               const uint32_t* __restrict__ draws, const uint8_t* __restrict__ learn_mask, int advance,
               int32_t* __restrict__ rows, float* __restrict__ r_hat, int32_t* __restrict__ act_b,
               float* __restrict__ done_b, int32_t* __restrict__ active, int32_t* __restrict__ step_t,
-              int log2t) {
+              float4* __restrict__ adam_sc, int log2t) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int B = d.batch, T = 1 << log2t;
     int* keys = reinterpret_cast<int*>(smem_raw);
@@ -81,6 +81,16 @@ sample_kernel(dmdqn_dims d, dmdqn_hparams hp, dmdqn_replay rp, int32_t* __restri
         int t = learn_step[g];
         if (on && advance) learn_step[g] = ++t;    // dqn_agent.py:359
         step_t[g] = t;
+        if (on) {
+            // Adam scalars of this step, once per network instead of once per thread of K4b:
+            // alpha_t = lr * sqrt(1 - b2^t) / (1 - b1^t) in float64, then rounded (oracle/dqn.py adam_scalars)
+            const double bc1 = 1.0 - pow(hp.beta1, (double)t), bc2 = 1.0 - pow(hp.beta2, (double)t);
+            const int freq = hp.target_update_frequency > 0 ? hp.target_update_frequency : 1;
+            const int sync = hp.tau >= 0.0 ? 2 : (t % freq == 0 ? 1 : 0);          // counter already incremented (:359,376)
+            adam_sc[g] = make_float4((float)(hp.learning_rate * sqrt(bc2) / bc1),
+                                     (float)(hp.adam_form == DMDQN_ADAM_KERAS ? hp.adam_eps : hp.adam_eps * sqrt(bc2)),
+                                     __int_as_float(sync), 0.f);
+        }
     }
     if (!on) return;
 
@@ -212,7 +222,8 @@ int launch_sample(const dmdqn_dims& d, const dmdqn_hparams& hp, const dmdqn_repl
         d, hp, rp, nets.learn_step, static_cast<const uint32_t*>(draws), learn_mask, advance,
         reinterpret_cast<int32_t*>(ws + w.rows), reinterpret_cast<float*>(ws + w.r_hat),
         reinterpret_cast<int32_t*>(ws + w.act_b), reinterpret_cast<float*>(ws + w.done_b),
-        reinterpret_cast<int32_t*>(ws + w.active), reinterpret_cast<int32_t*>(ws + w.step_t), log2t);
+        reinterpret_cast<int32_t*>(ws + w.active), reinterpret_cast<int32_t*>(ws + w.step_t),
+        reinterpret_cast<float4*>(ws + w.adam_sc), log2t);
     DMDQN_CUDA(cudaGetLastError());
     return DMDQN_OK;
 }

@@ -35,6 +35,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
     cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
+    if os.environ.get("DMDQN_TC_TIMING"):          # phase stamps printed by a few CTAs (profiling aid only)
+        cmd.insert(1, "-DTC_TIMING")
+        cmd.insert(1, "-DTC_EXP=" + os.environ.get("DMDQN_TC_EXP", "0"))
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

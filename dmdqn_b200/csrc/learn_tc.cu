@@ -33,7 +33,7 @@ constexpr int NT_F = NT + 32;   // K3 / K4a add one warp whose lane 0 only issue
 constexpr int KC = 16;          // k-rows of the streamed operand per stage
 constexpr uint32_t ATOM = BM * 128;           // bytes of one K-major SW128 atom column (128 rows x 32 floats)
 constexpr uint32_t STAGE = 2 * KC * H * 4;    // hi + lo of a 16 x 256 chunk
-constexpr uint32_t SPIN_LIMIT = 1u << 26;
+constexpr uint32_t SPIN_LIMIT = 1u << 20;
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers (syntax as in the CUTLASS sm100 headers shipped with the image).
@@ -112,14 +112,6 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ void cp16(uint32_t dst, const float* src, bool valid = true) {
-    const int n = valid ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(n) : "memory");
-}
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
 // x = hi + lo, hi = x rounded to tf32 (nearest, ties away), lo exact in fp32
 __device__ __forceinline__ float tf32_hi(float x) {
     uint32_t r;
@@ -163,6 +155,23 @@ struct TcArgs {
     int* error;
 };
 
+// Phase stamps (build with -DTC_TIMING, tools/phase_timing.py): thread 0 of a few CTAs prints clock64 deltas.
+#ifndef TC_EXP
+#define TC_EXP 0
+#endif
+#ifdef TC_TIMING
+#define TS_DECL long long ts_[16]; int tsi_ = 0
+#define TS() do { if (tsi_ < 16) ts_[tsi_++] = clock64(); } while (0)
+#define TS_D(i) (i < tsi_ ? ts_[i] - ts_[i - 1] : 0LL)
+#define TS_PRINT(name) do { if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 301 || blockIdx.x == gridDim.x - 1)) \
+        printf("%s cta %d: %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld | total %lld\n", name, blockIdx.x, TS_D(1), TS_D(2), TS_D(3), \
+               TS_D(4), TS_D(5), TS_D(6), TS_D(7), TS_D(8), TS_D(9), TS_D(10), ts_[tsi_ - 1] - ts_[0]); } while (0)
+#else
+#define TS_DECL
+#define TS()
+#define TS_PRINT(name)
+#endif
+
 // Shared-memory carve-up of the K3 / K4a kernels (offsets from a 1024-byte aligned base).
 struct Fwd {
     static constexpr uint32_t R = 0;                          // 128 KB: X hi|lo during layer 1, then activation hi
@@ -187,13 +196,29 @@ struct Fwd {
 // before refilling.  No CTA-wide barrier inside the loop.  cnt[] = chunks that have gone through each
 // stage so far (mbarrier phase bookkeeping; both roles run the same sequence).
 // ------------------------------------------------------------------------------------------
+// Barrier block of the K3 / K4a kernels (byte offsets from Fwd::BARS).
+struct Bar {
+    static constexpr uint32_t FULL_F = 0, EMPTY_F = 32;      // x.W pipe: 4 stages
+    static constexpr uint32_t TMEM = 64;                     // TMEM base address (written by tcgen05.alloc)
+    static constexpr uint32_t FULL_B = 72, EMPTY_B = 88;     // d.W^T pipe: 2 stages
+    static constexpr uint32_t AREADY = 104, DONE = 112;      // A operand published (8 warps) / GEMM retired (1 commit)
+};
+
 template <bool BT>
 struct Pipe {
-    static constexpr int KCX = BT ? 16 : 8;
-    static constexpr int NST = BT ? 2 : 4;
+    static constexpr int KCX = BT ? 16 : 8;                   // k extent of a chunk
+    static constexpr int NST = BT ? 2 : 4;                    // shared-memory stages
+    static constexpr int WPC = BT ? 2 : 1;                    // producer warps that stage one chunk together
+    static constexpr int GROUPS = (NT / 32) / WPC;            // chunk c belongs to producer group c % GROUPS
     static constexpr uint32_t HALF = KCX * H * 4;             // bytes of the hi (or lo) part of a stage
-    static constexpr int PIECES = KCX * H / 4 / NT;           // 16-byte pieces per producer thread per chunk
-    static constexpr int DIST = BT ? 2 : 4;                   // chunks held in registers ahead of the one being staged
+    static constexpr int PIECES = KCX * H / 4 / (32 * WPC);   // 16-byte pieces per lane per chunk (16)
+    static constexpr uint32_t FULL = BT ? Bar::FULL_B : Bar::FULL_F, EMPTY = BT ? Bar::EMPTY_B : Bar::EMPTY_F;
+};
+
+// Phase bookkeeping shared by the producer warps and the MMA lane (both walk the same GEMM sequence):
+// how often every stage of each pipe has been used, and how many GEMMs have retired.
+struct PipeState {
+    uint32_t uses_f = 0, uses_b = 0, gemms = 0;
 };
 
 __device__ __forceinline__ float4 ldg_stream(const float* p) {   // volatile: issue order = program order
@@ -210,84 +235,111 @@ __device__ __forceinline__ void sts4(uint32_t a, const float4& v) {
     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// Producer side of a streamed GEMM.  The weight chunks travel global -> registers -> (hi | lo) -> shared
-// memory: the global loads of chunk c + DIST are issued when chunk c is staged, so DIST chunks (about
-// DIST * 384 cycles of MMA time) of L2 / HBM latency are covered by registers, independently of the number
-// of shared-memory stages; the only shared-memory traffic of a chunk is its two 16-byte stores per piece.
-// begin() can be called ahead of the epilogue that produces the A operand, run() after it.
+// Every producer thread calls this once its part of the next GEMM's A operand (shared memory and / or
+// TMEM) is written: generic-proxy writes -> async proxy, tcgen05.st -> tcgen05.mma, one arrival per warp.
+__device__ __forceinline__ void a_ready(uint32_t sbase) {
+    fence_async_smem();
+    tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(sbase + Fwd::BARS + Bar::AREADY);
+}
+
+// Producer side of a streamed GEMM.  Chunks are OWNED by producer groups (one warp forward, a warp pair
+// backward): group g stages chunks g, g + GROUPS, ... on its own -- global -> registers -> (hi | lo) ->
+// shared memory -> one arrival on full[stage] -- and loads its next chunk right after staging the current
+// one, i.e. GROUPS chunk-times (~3000 cycles of MMA work) ahead of its use.  No group waits for another
+// one, so the per-chunk latency chain (empty wait, stores, proxy fence, arrive) of one group overlaps with
+// the chains of the others instead of pacing the whole CTA.
+// begin() can be called ahead of the epilogue that produces the A operand, run() after a_ready().
 template <int PASSES, bool BT>
 struct WStream {
     using P = Pipe<BT>;
-    float4 buf[P::DIST][P::PIECES];
-    const float* src[P::PIECES];
-    uint32_t dst[P::PIECES];
-    int nchunks;
+    float4 buf[P::PIECES];
+    const float* src;             // this lane's piece 0 of chunk 0
+    uint32_t dst;                 // backward: its offset inside a stage
+    int nchunks, grp, lane_mn;
+    // forward : lane l, piece i -> k-row i/2, columns (i%2)*128 + l*4: a warp load covers 512 contiguous bytes
+    // backward: warp s of the pair, lane l, piece i -> row n = s*128 + i*8 + l/4, k piece l%4
 
-    __device__ __forceinline__ void load(int slot, int c) {
-#pragma unroll
-        for (int r = 0; r < P::PIECES; ++r) buf[slot][r] = ldg_stream(src[r] + (BT ? (size_t)c * P::KCX : (size_t)c * P::KCX * H));
+    __device__ __forceinline__ const float* piece_src(int i, int c) const {
+        if (!BT) return src + (size_t)c * P::KCX * H + (size_t)(i >> 1) * H + (i & 1) * 128;
+        return src + (size_t)c * P::KCX + (size_t)i * 8 * H;
     }
-    // W: [K][H] row-major (BT = false) or [H][K] row-major (BT = true); both have leading dimension H here
+    __device__ __forceinline__ uint32_t piece_dst(int i) const {
+        if (!BT) return off_mn(H, i >> 1, (i & 1) * 128 + lane_mn);
+        return dst + (uint32_t)i * 8 * 64;                    // off_k64: 64-byte rows, the xor pattern repeats every 8 rows
+    }
+
+    __device__ __forceinline__ void load(int c) {
+#if TC_EXP == 1
+        return;
+#endif
+#pragma unroll
+        for (int i = 0; i < P::PIECES; ++i) buf[i] = ldg_stream(piece_src(i, TC_EXP == 3 ? 0 : c));
+    }
+    // W: [K][H] row-major (BT = false) or [H][K] row-major with K = H (BT = true)
     __device__ __forceinline__ void begin(const float* __restrict__ W, int K) {
-        const int tid = threadIdx.x;
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         nchunks = K / P::KCX;
-#pragma unroll
-        for (int r = 0; r < P::PIECES; ++r) {
-            const int p = tid + r * NT;
-            if (!BT) {                                            // k-row p/64, column piece p%64
-                src[r] = W + (size_t)(p >> 6) * H + ((p & 63) << 2);
-                dst[r] = off_mn(H, p >> 6, (p & 63) << 2);
-            } else {                                              // row n = p/4, k piece p%4
-                src[r] = W + (size_t)(p >> 2) * H + ((p & 3) << 2);
-                dst[r] = off_k64(H, p >> 2, (p & 3) << 2);
-            }
+        grp = warp / P::WPC;
+        if (!BT) {
+            lane_mn = lane << 2;
+            src = W + lane_mn;
+            dst = 0;
+        } else {
+            const int n0 = (warp % P::WPC) * 128 + (lane >> 2), kp = (lane & 3) << 2;
+            src = W + (size_t)n0 * H + kp;
+            dst = off_k64(H, n0, kp);
         }
-#pragma unroll
-        for (int j = 0; j < P::DIST; ++j)
-            if (j < nchunks) load(j, j);
+        if (grp < nchunks) load(grp);
     }
-    __device__ __forceinline__ bool run(uint32_t sbase, uint32_t (&cnt)[4]) {
-        const uint32_t full0 = sbase + Fwd::BARS, empty0 = full0 + 32;
+    __device__ __forceinline__ bool run(uint32_t sbase, PipeState& ps) {
+        const uint32_t full0 = sbase + Fwd::BARS + P::FULL, empty0 = sbase + Fwd::BARS + P::EMPTY;
+        const uint32_t uses0 = BT ? ps.uses_b : ps.uses_f;
         bool ok = true;
-        for (int c0 = 0; c0 < nchunks; c0 += P::DIST) {
+        // A parity wait is only meaningful for a waiter that is at most one phase behind the barrier, and a
+        // group skips GROUPS / NST - 1 uses of its stage between two of its chunks: it therefore walks the
+        // empty[] phases one by one.  seen = completions of empty[stage] known to this warp (every use of an
+        // earlier GEMM has retired: the DONE wait).  GROUPS % NST == 0, so a group always owns the same stage.
+        static_assert(P::GROUPS % P::NST == 0, "a producer group must stay on one stage");
+        uint32_t seen = uses0;
+        for (int c = grp; c < nchunks; c += P::GROUPS) {
+            const int b = c % P::NST;
+            const uint32_t u = uses0 + (uint32_t)(c / P::NST);                    // this is use number u of stage b
+            for (; seen < u && ok; ++seen) ok &= mbar_wait(empty0 + 8 * b, seen & 1);   // the MMAs of every earlier use are done
+            const uint32_t st = sbase + Fwd::WB + b * (2 * P::HALF);
+#if TC_EXP == 4
 #pragma unroll
-            for (int j = 0; j < P::DIST; ++j) {
-                static_assert(P::DIST == P::NST, "stage index below is the unrolled j");
-                const int c = c0 + j;                             // nchunks is a multiple of DIST
-                const int b = j;
-                float4 x[P::PIECES];
+            for (int i = 0; i < P::PIECES; ++i) asm volatile("" ::"f"(buf[i].x), "f"(buf[i].y), "f"(buf[i].z), "f"(buf[i].w));
+#elif TC_EXP != 1
 #pragma unroll
-                for (int r = 0; r < P::PIECES; ++r) x[r] = buf[j][r];
-                if (c + P::DIST < nchunks) load(j, c + P::DIST);
-                if (cnt[b]) ok &= mbar_wait(empty0 + 8 * b, (cnt[b] - 1) & 1);   // the MMAs that read this stage are done
-                cnt[b] += 1;
-                const uint32_t st = sbase + Fwd::WB + b * (2 * P::HALF);
-#pragma unroll
-                for (int r = 0; r < P::PIECES; ++r) {
-                    float4 hi, lo;
-                    split4<PASSES>(x[r], hi, lo);
-                    sts4(st + dst[r], hi);
-                    if (PASSES == 3) sts4(st + P::HALF + dst[r], lo);
-                }
-                fence_async_smem();                               // generic-proxy writes (this chunk, and the A operand before it)
-                tc_fence_before();
-                __syncwarp();
-                if ((threadIdx.x & 31) == 0) mbar_arrive(full0 + 8 * b);         // one arrival per producer warp
+            for (int i = 0; i < P::PIECES; ++i) {
+                float4 hi, lo;
+                split4<PASSES>(buf[i], hi, lo);
+                const uint32_t o = st + piece_dst(i);
+                sts4(o, hi);
+                if (PASSES == 3) sts4(o + P::HALF, lo);
             }
+#endif
+            if (c + P::GROUPS < nchunks) load(c + P::GROUPS);                     // next own chunk: a whole round of the other groups ahead
+            fence_async_smem();
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) mbar_arrive(full0 + 8 * b);             // WPC arrivals complete the stage
         }
-        // all MMAs of this GEMM complete (a commit tracks every earlier MMA of the issuing thread)
-        constexpr int last = P::NST - 1;                          // nchunks is a multiple of NST
-        ok &= mbar_wait(empty0 + 8 * last, (cnt[last] - 1) & 1);
+        if (ok) ok = mbar_wait(sbase + Fwd::BARS + Bar::DONE, ps.gemms & 1);     // every MMA of this GEMM has retired
         tc_fence_after();
+        (BT ? ps.uses_b : ps.uses_f) += (uint32_t)(nchunks / P::NST);
+        ps.gemms += 1;
         return ok;
     }
 };
 
 template <int PASSES, bool BT>
 __device__ __forceinline__ bool gemm_mma(uint32_t sbase, uint32_t tmem, uint32_t a_hi, uint32_t a_lo_smem,
-                                         uint32_t a_lo_tmem, int K, uint32_t (&cnt)[4]) {
+                                         uint32_t a_lo_tmem, int K, PipeState& ps) {
     using P = Pipe<BT>;
-    const uint32_t full0 = sbase + Fwd::BARS, empty0 = full0 + 32;
+    const uint32_t full0 = sbase + Fwd::BARS + P::FULL, empty0 = sbase + Fwd::BARS + P::EMPTY;
+    const uint32_t uses0 = BT ? ps.uses_b : ps.uses_f;
     const int nchunks = K / P::KCX;
     bool ok = true;
     constexpr uint32_t idesc = make_idesc(false, !BT);
@@ -296,32 +348,37 @@ __device__ __forceinline__ bool gemm_mma(uint32_t sbase, uint32_t tmem, uint32_t
     const uint64_t a_lo0 = make_desc(a_lo_smem, 16, 1024, 2);
     const uint64_t b0 = BT ? make_desc(sbase + Fwd::WB, 16, 512, 4) : make_desc(sbase + Fwd::WB, 512, 4096, 1);
     constexpr uint32_t KSTEP_B = BT ? 32 : 2 * 4096;          // bytes between the k-steps of a chunk in the B stage
-    for (int c0 = 0; c0 < nchunks; c0 += P::NST) {
+    if (ok) ok = mbar_wait(sbase + Fwd::BARS + Bar::AREADY, ps.gemms & 1);   // all 8 producer warps have published the A operand
+    tc_fence_after();
+    for (int c = 0; c < nchunks; ++c) {
+        const int b = c % P::NST;
+        const uint32_t u = uses0 + (uint32_t)(c / P::NST);
+        if (ok) ok = mbar_wait(full0 + 8 * b, u & 1);         // the owning group has staged chunk c
+        tc_fence_after();
 #pragma unroll
-        for (int b = 0; b < P::NST; ++b) {                    // nchunks is a multiple of NST
-            const int c = c0 + b;
-            ok &= mbar_wait(full0 + 8 * b, cnt[b] & 1);       // all 8 producer warps have published chunk c
-            cnt[b] += 1;
-            tc_fence_after();
-#pragma unroll
-            for (int ks = 0; ks < P::KCX / 8; ++ks) {
-                const int kg = c * P::KCX + ks * 8;
-                const uint32_t a_off = ((uint32_t)(kg >> 5) * ATOM + (uint32_t)((kg & 31) >> 3) * 32) >> 4;
-                const uint32_t b_off = ((uint32_t)b * (2 * P::HALF) + ks * KSTEP_B) >> 4;
-                const uint64_t a_hi_d = a_hi0 + a_off;
-                const uint64_t b_hi = b0 + b_off, b_lo = b0 + b_off + (P::HALF >> 4);
-                uint32_t acc = (c | ks) ? 1u : 0u;
-                if (PASSES == 3) {                            // small terms first
-                    if (a_lo_smem) mma_ss(tmem, a_lo0 + a_off, b_hi, idesc, acc);
-                    else mma_ts(tmem, a_lo_tmem + (uint32_t)kg, b_hi, idesc, acc);
-                    mma_ss(tmem, a_hi_d, b_lo, idesc, 1u);
-                    acc = 1u;
-                }
-                mma_ss(tmem, a_hi_d, b_hi, idesc, acc);
+        for (int ks = 0; ks < P::KCX / 8; ++ks) {
+            const int kg = c * P::KCX + ks * 8;
+            const uint32_t a_off = ((uint32_t)(kg >> 5) * ATOM + (uint32_t)((kg & 31) >> 3) * 32) >> 4;
+            const uint32_t b_off = ((uint32_t)b * (2 * P::HALF) + ks * KSTEP_B) >> 4;
+            const uint64_t a_hi_d = a_hi0 + a_off;
+            const uint64_t b_hi = b0 + b_off, b_lo = b0 + b_off + (P::HALF >> 4);
+            uint32_t acc = (c | ks) ? 1u : 0u;
+#if TC_EXP == 2
+            continue;
+#endif
+            if (PASSES == 3) {                                // small terms first
+                if (a_lo_smem) mma_ss(tmem, a_lo0 + a_off, b_hi, idesc, acc);
+                else mma_ts(tmem, a_lo_tmem + (uint32_t)kg, b_hi, idesc, acc);
+                mma_ss(tmem, a_hi_d, b_lo, idesc, 1u);
+                acc = 1u;
             }
-            umma_commit(empty0 + 8 * b);
+            mma_ss(tmem, a_hi_d, b_hi, idesc, acc);
         }
+        umma_commit(empty0 + 8 * b);
     }
+    umma_commit(sbase + Fwd::BARS + Bar::DONE);
+    (BT ? ps.uses_b : ps.uses_f) += (uint32_t)(nchunks / P::NST);
+    ps.gemms += 1;
     return ok;
 }
 
@@ -478,20 +535,26 @@ __device__ __forceinline__ uint32_t tc_prologue(uint32_t sbase) {
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         for (int b = 0; b < 4; ++b) {
-            mbar_init(sbase + Fwd::BARS + 8 * b, NT / 32);     // full[b]: one arrival per producer warp
-            mbar_init(sbase + Fwd::BARS + 32 + 8 * b, 1);      // empty[b]: one tcgen05.commit
+            mbar_init(sbase + Fwd::BARS + Bar::FULL_F + 8 * b, Pipe<false>::WPC);    // full[b]: the owning producer group
+            mbar_init(sbase + Fwd::BARS + Bar::EMPTY_F + 8 * b, 1);                  // empty[b]: one tcgen05.commit
         }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(sbase + Fwd::BARS + Bar::FULL_B + 8 * b, Pipe<true>::WPC);
+            mbar_init(sbase + Fwd::BARS + Bar::EMPTY_B + 8 * b, 1);
+        }
+        mbar_init(sbase + Fwd::BARS + Bar::AREADY, NT / 32);
+        mbar_init(sbase + Fwd::BARS + Bar::DONE, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + Fwd::BARS + 64), "r"(512));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + Fwd::BARS + Bar::TMEM), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     uint32_t tmem;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(sbase + Fwd::BARS + 64));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(sbase + Fwd::BARS + Bar::TMEM));
     return tmem;
 }
 __device__ __forceinline__ void tc_epilogue(uint32_t tmem) {
@@ -514,13 +577,13 @@ __global__ void __launch_bounds__(NT_F, 1) tc_target_kernel(const TcArgs A) {
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int B = A.d.batch, Dp = A.d.obs_stride, r0 = rt * BM;
     const uint32_t tmem = tc_prologue(sbase);
-    uint32_t cnt[4] = {0, 0, 0, 0};
+    PipeState ps;
     bool ok = true;
     if (threadIdx.x >= NT) {
         // ---- MMA warp: lane 0 issues every tcgen05.mma of this CTA ----
         if (threadIdx.x == NT) {
-            ok &= gemm_mma<PASSES, false>(sbase, tmem, sbase + Fwd::R, sbase + Fwd::XLO, 0, Dp, cnt);
-            ok &= gemm_mma<PASSES, false>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, H, cnt);
+            ok = ok && gemm_mma<PASSES, false>(sbase, tmem, sbase + Fwd::R, sbase + Fwd::XLO, 0, Dp, ps);
+            ok = ok && gemm_mma<PASSES, false>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, H, ps);
             if (!ok) atomicExch(A.error, 13);
         }
         __syncwarp();
@@ -528,6 +591,8 @@ __global__ void __launch_bounds__(NT_F, 1) tc_target_kernel(const TcArgs A) {
         const Epi e;
         const float* P = (pass == 0 ? A.nets.theta : A.nets.theta_tgt) + (size_t)g * A.L.stride;
         float q[4];
+        TS_DECL;
+        TS();
         WStream<PASSES, false> ws;
         ws.begin(P + A.L.w1, Dp);                      // first W1 chunks in flight before anything else
         {
@@ -536,13 +601,21 @@ __global__ void __launch_bounds__(NT_F, 1) tc_target_kernel(const TcArgs A) {
             load_small_params(sbase, P, A.L);
             xg.store(sbase);
         }
+        a_ready(sbase);
         prod_sync();   // biases / head weights visible to every epilogue thread
-        ok &= ws.run(sbase, cnt);
+        TS();
+        ok = ok && ws.run(sbase, ps);
+        TS();
         ws.begin(P + A.L.w2, H);                       // W2 chunks travel while the epilogue runs
         uint32_t mask[4];
         epi_hidden<PASSES>(sbase, tmem, e, Fwd::BIAS1, nullptr, 0, mask);
-        ok &= ws.run(sbase, cnt);
+        a_ready(sbase);
+        TS();
+        ok = ok && ws.run(sbase, ps);
+        TS();
         epi_head(sbase, tmem, e, false, mask, q, P + A.L.b3);
+        TS();
+        TS_PRINT("K3 gather L1 epi1 L2 epi2");
         const int gr = r0 + e.row;
         if (e.half == 0 && gr < B) {
             float* out = (pass == 0 ? A.q_next : A.tq_all) + ((size_t)g * B + gr) * 4;
@@ -568,14 +641,14 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A) {
     const int32_t* rows = A.rows + sb;
     const float* P = A.nets.theta + (size_t)g * A.L.stride;
     const uint32_t tmem = tc_prologue(sbase);
-    uint32_t cnt[4] = {0, 0, 0, 0};
+    PipeState ps;
     bool ok = true;
     if (threadIdx.x >= NT) {
         // ---- MMA warp: lane 0 issues every tcgen05.mma of this CTA ----
         if (threadIdx.x == NT) {
-            ok &= gemm_mma<PASSES, false>(sbase, tmem, sbase + Fwd::R, sbase + Fwd::XLO, 0, Dp, cnt);
-            ok &= gemm_mma<PASSES, false>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, H, cnt);
-            ok &= gemm_mma<PASSES, true>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, H, cnt);
+            ok = ok && gemm_mma<PASSES, false>(sbase, tmem, sbase + Fwd::R, sbase + Fwd::XLO, 0, Dp, ps);
+            ok = ok && gemm_mma<PASSES, false>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, H, ps);
+            ok = ok && gemm_mma<PASSES, true>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, H, ps);
             if (!ok) atomicExch(A.error, 14);
         }
         __syncwarp();
@@ -586,6 +659,8 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A) {
     const int gr = r0 + e.row;
     const bool valid = gr < B;
 
+    TS_DECL;
+    TS();
     WStream<PASSES, false> ws;
     ws.begin(P + A.L.w1, Dp);
     {
@@ -612,14 +687,21 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A) {
         yi = A.r_hat[sb + gr] + (A.gamma * (1.0f - A.done_b[sb + gr])) * tq;
         if (e.half == 0) A.y[sb + gr] = yi;
     }
+    a_ready(sbase);
     prod_sync();   // biases / head weights visible to every epilogue thread
-    ok &= ws.run(sbase, cnt);
+    TS();
+    ok = ok && ws.run(sbase, ps);
+    TS();
     ws.begin(P + A.L.w2, H);
     uint32_t mask1[4], mask2[4];
     epi_hidden<PASSES>(sbase, tmem, e, Fwd::BIAS1, valid ? A.h1 + sb * H + gr : nullptr, B, mask1);
-    ok &= ws.run(sbase, cnt);
+    a_ready(sbase);
+    TS();
+    ok = ok && ws.run(sbase, ps);
+    TS();
     float q[4];
     epi_head(sbase, tmem, e, true, mask2, q, P + A.L.b3);
+    TS();
 
     // loss term and dL/dpred of this row (reference :349-352)
     float gi = 0.f, term = 0.f;
@@ -641,35 +723,40 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A) {
             for (int k = 0; k < 4; ++k) A.q_all[(sb + gr) * 4 + k] = q[k];
         }
     }
-    float* rowf = sf + Fwd::ROWF / 4;                     // [0]: loss term, [1..4]: q per row
+    float* rowf = sf + Fwd::ROWF / 4;                     // [0]: loss term, [1..4]: q per row, [5]: action, [6]: g, [7]: warp partials
     if (e.half == 0) {
         rowf[e.row] = term;
         for (int k = 0; k < 4; ++k) rowf[(1 + k) * BM + e.row] = valid ? q[k] : 0.f;
         reinterpret_cast<int*>(rowf)[5 * BM + e.row] = valid ? ai : -1;
         rowf[6 * BM + e.row] = gi;
+        // per-tile loss / metric / db3 partials: butterfly over the 32 rows of this warp (fixed order), then
+        // the four warp partials are added in warp order by thread 0
+        float red[11];
+        red[0] = term;
+        red[1] = 0.f; red[2] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float qq = (valid && k < A.d.n_actions) ? q[k] : 0.f;
+            red[1] += qq;
+            red[2] = fmaf(qq, qq, red[2]);
+            red[3 + k] = (valid && ai == k) ? 1.f : 0.f;
+            red[7 + k] = (valid && ai == k) ? gi : 0.f;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int v = 0; v < 11; ++v) red[v] += __shfl_xor_sync(0xffffffffu, red[v], o);
+        if ((threadIdx.x & 31) == 0)
+#pragma unroll
+            for (int v = 0; v < 11; ++v) rowf[7 * BM + (threadIdx.x >> 5) * 11 + v] = red[v];
     }
     prod_sync();
-    if (threadIdx.x == 0) {                               // per-tile loss / metric partials, rows in order
-        float ls = 0.f, qsum = 0.f, qsq = 0.f, hist[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int i = 0; i < BM && r0 + i < B; ++i) {
-            ls += rowf[i];
-            for (int k = 0; k < A.d.n_actions; ++k) {
-                const float qq = rowf[(1 + k) * BM + i];
-                qsum += qq;
-                qsq = fmaf(qq, qq, qsq);
-            }
-            const int a = reinterpret_cast<int*>(rowf)[5 * BM + i];
-            hist[0] += a == 0; hist[1] += a == 1; hist[2] += a == 2; hist[3] += a == 3;
-        }
-        float* pl = A.part_loss + ((size_t)g * A.tiles + rt) * 8;
-        pl[0] = ls; pl[1] = qsum; pl[2] = qsq; pl[3] = hist[0]; pl[4] = hist[1]; pl[5] = hist[2]; pl[6] = hist[3]; pl[7] = 0.f;
-        float db3[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int i = 0; i < BM && r0 + i < B; ++i) {
-            const int a = reinterpret_cast<int*>(rowf)[5 * BM + i];
-            const float gv = rowf[6 * BM + i];
-            db3[0] += a == 0 ? gv : 0.f; db3[1] += a == 1 ? gv : 0.f; db3[2] += a == 2 ? gv : 0.f; db3[3] += a == 3 ? gv : 0.f;
-        }
-        for (int a = 0; a < 4; ++a) A.part_b3[((size_t)g * A.tiles + rt) * 4 + a] = db3[a];
+    if (threadIdx.x < 11) {
+        const float* wp = rowf + 7 * BM + threadIdx.x;
+        const float tot = ((wp[0] + wp[11]) + wp[22]) + wp[33];
+        const size_t pt = (size_t)g * A.tiles + rt;
+        if (threadIdx.x < 7) A.part_loss[pt * 8 + threadIdx.x] = tot;      // loss, q sum, q^2 sum, action histogram
+        else A.part_b3[pt * 4 + (threadIdx.x - 7)] = tot;
     }
     {   // dW3[j][a] = sum_i h2[i][j] g_i [a_i = a] and db2[j] = sum_i dh2[i][j] over this tile's rows (in order):
         // thread = column j, rows read back from the h2 tile left in R by epi_head
@@ -694,6 +781,7 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A) {
         A.part_b2[pt * H + j] = s2;
     }
     prod_sync();          // R is rewritten with dh2 below
+    TS();
 
     WStream<PASSES, true> wsb;
     wsb.begin(P + A.L.w2, H);
@@ -725,9 +813,12 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A) {
         if (PASSES == 3) tmem_st32(tmem + e.lane_addr + 256u + (uint32_t)c0, lo);
     }
     if (PASSES == 3) tmem_st_wait();
+    a_ready(sbase);
 
+    TS();
     // dh1 = (dh2 W2^T) * relu'(h1)
-    ok &= wsb.run(sbase, cnt);
+    ok = ok && wsb.run(sbase, ps);
+    TS();
 #pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {
         const int c0 = e.half * 128 + cc * 32;
@@ -739,6 +830,8 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A) {
                 A.dh1[sb * H + (size_t)(c0 + j) * B + gr] = ((mask1[cc] >> j) & 1u) ? v[j] : 0.f;
         }
     }
+    TS();
+    TS_PRINT("K4a gather L1 epi1 L2 epi2 loss+dW3 dh2 bwdGEMM dh1store");
     if (!ok && threadIdx.x == 0) atomicExch(A.error, 4);
     tc_epilogue(tmem);
 }
@@ -859,100 +952,118 @@ __global__ void __launch_bounds__(NT, 2) tc_wgrad_kernel(const TcArgs A) {
     uint32_t tmem;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(sbase + Wg::BARS + 32));
 
+    TS_DECL;
+    TS();
     const int nchunks = (B + KC - 1) / KC;
-    uint32_t uses[Wg::STAGES] = {0, 0};
     bool ok = true;
-    // piece -> smem offset (same mapping for the copy and for the hi/lo split)
-    auto a_off = [&](int p) -> uint32_t {                     // 512 pieces
-        if (is_w2) return off_k64(BM, p >> 2, (p & 3) << 2);  // row m = p/4, 4 k-pieces per row
-        return off_mn(BM, p >> 5, (p & 31) << 2);             // k = p/32, 32 m-pieces per k-row
-    };
-    auto b_off = [&](int p) -> uint32_t { return 2 * Wg::A_BYTES + off_k64(H, p >> 2, (p & 3) << 2); };   // 1024 pieces
-    auto issue = [&](int c) {
-        const uint32_t st = sbase + (c % Wg::STAGES) * Wg::STG;
+    // Operand chunks (16 batch rows) travel global -> registers -> (hi | lo) -> shared memory; the loads of
+    // chunk c + 2 are issued when chunk c is staged, so two chunks of latency are covered by registers and
+    // the two shared-memory stages only have to cover the MMAs.  piece -> offset inside a stage:
+    uint32_t a_dst[2], b_dst[4];
+    const float* a_src[2];
+    const float* b_src[4];
+    int a_k[2], b_k[4];           // k offset of the piece inside its chunk
+    bool a_ones[2], a_live[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int p = tid + r * NT;
+        if (is_w2) {                                          // row m = p/4, 4 k-pieces per row (K-major SW64)
+            a_dst[r] = off_k64(BM, p >> 2, (p & 3) << 2);
+            a_k[r] = (p & 3) << 2;
+            a_src[r] = AsrcT + (size_t)(m0 + (p >> 2)) * B + a_k[r];
+            a_ones[r] = false; a_live[r] = true;
+        } else {                                              // k = p/32, 32 m-pieces per k-row (MN-major)
+            const int m = (p & 31) << 2;
+            a_dst[r] = off_mn(BM, p >> 5, m);
+            a_k[r] = p >> 5;
+            a_src[r] = A.rp.obs + m;
+            a_ones[r] = m == Dp;                              // the "ones" column: tile row Dp accumulates sum_k dh1[k][:] = db1
+            a_live[r] = m < m_valid;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int p = tid + r * NT;
+        b_dst[r] = 2 * Wg::A_BYTES + off_k64(H, p >> 2, (p & 3) << 2);
+        b_k[r] = (p & 3) << 2;
+        b_src[r] = DsrcT + (size_t)(p >> 2) * B + b_k[r];
+    }
+    float4 ra[2][2], rb[2][4];
+    auto load = [&](int slot, int c) {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-            const int p = tid + r * NT;
+            const int k = c * KC + a_k[r];
+            ra[slot][r] = z;
             if (is_w2) {
-                const int m = p >> 2, k = c * KC + ((p & 3) << 2);
-                const bool v = k < B;
-                cp16(st + a_off(p), AsrcT + (size_t)(m0 + m) * B + (v ? k : 0), v);
-            } else {
-                const int kr = c * KC + (p >> 5), m = (p & 31) << 2;
-                const bool v = kr < B && m < m_valid;
-                if (m == Dp)      // the "ones" column: tile row Dp accumulates sum_k dh1[k][:] = db1
-                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%2,%2};" ::"r"(st + a_off(p)), "f"(kr < B ? 1.f : 0.f), "f"(0.f) : "memory");
-                else
-                    cp16(st + a_off(p), A.rp.obs + (v ? (size_t)rows[kr] * Dp + m : 0), v);
+                if (k < B) ra[slot][r] = ldg_stream(a_src[r] + (size_t)c * KC);
+            } else if (a_ones[r]) {
+                ra[slot][r].x = k < B ? 1.f : 0.f;
+            } else if (a_live[r] && k < B) {
+                ra[slot][r] = ldg_stream(a_src[r] + (size_t)__ldg(rows + k) * Dp);
             }
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            const int p = tid + r * NT;
-            const int n = p >> 2, k = c * KC + ((p & 3) << 2);
-            const bool v = k < B;
-            cp16(st + b_off(p), DsrcT + (size_t)n * B + (v ? k : 0), v);
+            rb[slot][r] = z;
+            if (c * KC + b_k[r] < B) rb[slot][r] = ldg_stream(b_src[r] + (size_t)c * KC);
         }
     };
-    issue(0);
-    cp_commit();
-    for (int c = 0; c < nchunks; ++c) {
-        cp_wait<0>();
-        const uint32_t st = sbase + (c % Wg::STAGES) * Wg::STG;
-        if (PASSES == 3) {
+    load(0, 0);
+    if (nchunks > 1) load(1, 1);
+    for (int c0 = 0; c0 < nchunks; c0 += 2) {
 #pragma unroll
-            for (int r = 0; r < 6; ++r) {
-                const uint32_t o = r < 2 ? a_off(tid + r * NT) : b_off(tid + (r - 2) * NT);
-                const uint32_t lo_off = r < 2 ? Wg::A_BYTES : Wg::B_BYTES;
-                float4 x, hi, lo;
-                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(st + o));
-                split4<3>(x, hi, lo);
-                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(st + o), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
-                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(st + lo_off + o), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+        for (int j = 0; j < 2; ++j) {
+            const int c = c0 + j;
+            if (c < nchunks) {                                // uniform across the CTA
+                const uint32_t st = sbase + j * Wg::STG;
+                if (c >= 2 && ok) ok = mbar_wait(sbase + Wg::BARS + 8 * j, ((c >> 1) - 1) & 1);   // MMAs of chunk c - 2 are done
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    float4 hi, lo;
+                    split4<PASSES>(r < 2 ? ra[j][r] : rb[j][r - 2], hi, lo);
+                    const uint32_t o = st + (r < 2 ? a_dst[r] : b_dst[r - 2]);
+                    sts4(o, hi);
+                    if (PASSES == 3) sts4(o + (r < 2 ? Wg::A_BYTES : Wg::B_BYTES), lo);
+                }
+                if (c + 2 < nchunks) load(j, c + 2);
+                fence_async_smem();
+                __syncthreads();
+                if (tid == 0) {
+                    tc_fence_after();
+                    const uint32_t idesc = make_idesc(!is_w2, false);
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        uint64_t a_hi, a_lo;
+                        if (is_w2) {
+                            a_hi = make_desc(st + ks * 32, 16, 512, 4);
+                            a_lo = make_desc(st + Wg::A_BYTES + ks * 32, 16, 512, 4);
+                        } else {      // MN-major: 4 m-groups per k-group -> k-group stride 2048 B
+                            a_hi = make_desc(st + ks * 2 * 2048, 512, 2048, 1);
+                            a_lo = make_desc(st + Wg::A_BYTES + ks * 2 * 2048, 512, 2048, 1);
+                        }
+                        const uint64_t b_hi = make_desc(st + 2 * Wg::A_BYTES + ks * 32, 16, 512, 4);
+                        const uint64_t b_lo = make_desc(st + 2 * Wg::A_BYTES + Wg::B_BYTES + ks * 32, 16, 512, 4);
+                        uint32_t acc = (c | ks) ? 1u : 0u;
+                        if (PASSES == 3) {
+                            mma_ss(tmem, a_lo, b_hi, idesc, acc);
+                            mma_ss(tmem, a_hi, b_lo, idesc, 1u);
+                            acc = 1u;
+                        }
+                        mma_ss(tmem, a_hi, b_hi, idesc, acc);
+                    }
+                    umma_commit(sbase + Wg::BARS + 8 * j);
+                }
             }
         }
-        fence_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            const uint32_t idesc = make_idesc(!is_w2, false);
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-                uint64_t a_hi, a_lo;
-                if (is_w2) {
-                    a_hi = make_desc(st + ks * 32, 16, 512, 4);
-                    a_lo = make_desc(st + Wg::A_BYTES + ks * 32, 16, 512, 4);
-                } else {      // MN-major: 4 m-groups per k-group -> k-group stride 2048 B
-                    a_hi = make_desc(st + ks * 2 * 2048, 512, 2048, 1);
-                    a_lo = make_desc(st + Wg::A_BYTES + ks * 2 * 2048, 512, 2048, 1);
-                }
-                const uint64_t b_hi = make_desc(st + 2 * Wg::A_BYTES + ks * 32, 16, 512, 4);
-                const uint64_t b_lo = make_desc(st + 2 * Wg::A_BYTES + Wg::B_BYTES + ks * 32, 16, 512, 4);
-                uint32_t acc = (c | ks) ? 1u : 0u;
-                if (PASSES == 3) {
-                    mma_ss(tmem, a_lo, b_hi, idesc, acc);
-                    mma_ss(tmem, a_hi, b_lo, idesc, 1u);
-                    acc = 1u;
-                }
-                mma_ss(tmem, a_hi, b_hi, idesc, acc);
-            }
-            umma_commit(sbase + Wg::BARS + 8 * (c % Wg::STAGES));
-        }
-        uses[c % Wg::STAGES] += 1;
-        // refill the other stage (read by the MMAs of chunk c-1) while the MMAs of chunk c run
-        if (c + 1 < nchunks) {
-            const int b = (c + 1) % Wg::STAGES;
-            if (uses[b]) ok &= mbar_wait(sbase + Wg::BARS + 8 * b, (uses[b] - 1) & 1);
-            issue(c + 1);
-        }
-        cp_commit();
     }
-    {
-        const int last = (nchunks - 1) % Wg::STAGES;
-        ok &= mbar_wait(sbase + Wg::BARS + 8 * last, (uses[last] - 1) & 1);
+    {   // the last commit tracks every earlier MMA of the issuing thread
+        const int last = nchunks - 1;
+        ok &= mbar_wait(sbase + Wg::BARS + 8 * (last & 1), (last >> 1) & 1);
         tc_fence_after();
     }
     __syncthreads();      // every thread has seen the GEMM finish: the stage memory becomes the transpose tiles
+    TS();
 
     // epilogue: TMEM (lane = weight row) -> per-warp smem tile -> 8 lanes per 128-byte row segment, so the
     // Adam read-modify-write of theta / m / v / theta_tgt is fully coalesced.
@@ -1009,6 +1120,8 @@ __global__ void __launch_bounds__(NT, 2) tc_wgrad_kernel(const TcArgs A) {
             }
         }
     }
+    TS();
+    TS_PRINT("K4b gemm adam");
     if (!ok && tid == 0) atomicExch(A.error, 5);
     tc_fence_before();
     __syncthreads();

@@ -30,7 +30,8 @@ def main():
     anames = {0: "A K-major", 1: "A MN-major", 2: "A_lo via TMEM"}
     for K, N, b_mn, three, a_mode in [(64, 256, 0, 0, 0), (64, 256, 1, 0, 0), (64, 256, 2, 0, 0), (32, 256, 2, 0, 0),
                                       (64, 256, 0, 0, 1), (64, 256, 1, 0, 1), (64, 256, 0, 1, 0), (64, 256, 1, 1, 0),
-                                      (64, 256, 2, 1, 0), (64, 256, 1, 1, 1), (64, 256, 1, 1, 2), (64, 256, 2, 1, 2)]:
+                                      (64, 256, 2, 1, 0), (64, 256, 1, 1, 1), (64, 256, 1, 1, 2), (64, 256, 2, 1, 2),
+                                      (64, 256, 1, 2, 0), (64, 256, 1, 2, 2), (64, 256, 2, 2, 2)]:
         A = torch.randn(128, K, device="cuda")
         B = torch.randn((K, N) if b_mn == 1 else (N, K), device="cuda")
         D = torch.full((128, N), float("nan"), device="cuda")
@@ -47,7 +48,7 @@ def main():
         torch.cuda.synchronize()
         cyc = (int(t2[1]) - int(t1[1])) / max(1, int(t2[2]) - int(t1[2]))
         cyc2 = (int(t2[3]) - int(t1[3])) / ((40 - 8) * 4 * 8)
-        print(f"K={K:3d} N={N:3d} B={names[b_mn]:14s} {anames[a_mode]:14s} {'3xTF32' if three else 'TF32  '} rc={rc} status={int(st[0])} cyc/MMA={cyc:6.1f} back-to-back={cyc2:6.1f} "
+        print(f"K={K:3d} N={N:3d} B={names[b_mn]:14s} {anames[a_mode]:14s} {['TF32  ', '3xTF32', '3xTF32 raw-hi'][three]} rc={rc} status={int(st[0])} cyc/MMA={cyc:6.1f} back-to-back={cyc2:6.1f} "
               f"max_abs_err={err:.3e} rel={rel:.3e}", flush=True)
 
 

@@ -42,6 +42,9 @@ __device__ __forceinline__ float hi_part(float x) {
     return __uint_as_float(r);
 }
 __device__ __forceinline__ float lo_part(float x) { return x - hi_part(x); }
+// three_pass == 2: the raw fp32 word is the "hi" operand (the tensor core drops the low 13 mantissa bits itself)
+// and lo = x - truncate(x)
+__device__ __forceinline__ float lo_trunc(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 // K-major SW64 tile: rows x 16-float atoms (64-byte rows, 8-row groups of 512 B); element (r, k)
 __device__ __forceinline__ uint32_t off_kmajor64(int rows, int r, int k) {
     return (uint32_t)((k >> 4) * rows * 64 + r * 64 + ((((k & 15) >> 2) ^ ((r >> 1) & 3)) << 4) + ((k & 3) << 2));
@@ -76,16 +79,16 @@ probe_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __
         const int r = a_mode == 1 ? i % 128 : i / K, k = a_mode == 1 ? i / 128 : i % K;
         const float v = A[i];
         const uint32_t o = a_mode == 1 ? off_mnmajor(128, k, r) : off_kmajor(128, r, k);
-        *reinterpret_cast<float*>(sA + o) = three_pass ? hi_part(v) : v;
-        *reinterpret_cast<float*>(sAl + o) = lo_part(v);
+        *reinterpret_cast<float*>(sA + o) = three_pass == 1 ? hi_part(v) : v;
+        *reinterpret_cast<float*>(sAl + o) = three_pass == 2 ? lo_trunc(v) : lo_part(v);
     }
     for (int i = tid; i < N * K; i += 128) {
         float v = B[i];
         uint32_t o;
         if (b_mn) { const int k = i / N, n = i % N; o = off_mnmajor(N, k, n); }
         else      { const int n = i / K, k = i % K; o = b_mode == 2 ? off_kmajor64(N, n, k) : off_kmajor(N, n, k); }
-        *reinterpret_cast<float*>(sB + o) = three_pass ? hi_part(v) : v;
-        *reinterpret_cast<float*>(sBl + o) = lo_part(v);
+        *reinterpret_cast<float*>(sB + o) = three_pass == 1 ? hi_part(v) : v;
+        *reinterpret_cast<float*>(sBl + o) = three_pass == 2 ? lo_trunc(v) : lo_part(v);
     }
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
@@ -104,7 +107,7 @@ probe_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __
     if (a_mode == 2) {   // A_lo[row][k] -> TMEM lane row, column 256 + k (thread = row)
         for (int k0 = 0; k0 < K; k0 += 8) {
             uint32_t v[8];
-            for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(lo_part(A[(size_t)tid * K + k0 + j]));
+            for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(three_pass == 2 ? lo_trunc(A[(size_t)tid * K + k0 + j]) : lo_part(A[(size_t)tid * K + k0 + j]));
             const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + 256u + (uint32_t)k0;
             asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]),
                          "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");

@@ -235,6 +235,9 @@ def run_ours(args):
     barrier()
     ms_e2e = e0.elapsed_time(e1)
 
+    tc_err = int(grp.debug_views()["tc_error"][0])
+    if tc_err:
+        raise RuntimeError(f"a tcgen05 kernel timed out on an mbarrier (code {tc_err}): the timings are invalid")
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=grp.device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

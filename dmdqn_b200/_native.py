@@ -40,7 +40,7 @@ class HParams(C.Structure):
 
 
 class DebugViews(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("y", "q_all", "q_next", "tq_all", "rows", "r_hat", "active", "tc_error", "dh1", "dh2")]
+    _fields_ = [(n, C.c_void_p) for n in ("y", "q_all", "q_next", "tq_all", "rows", "r_hat", "active", "tc_error", "dh1", "dh2", "relu2_bits")]
 
 
 # name -> (restype, argtypes); mirrors include/dmdqn_b200.h one to one

@@ -219,6 +219,7 @@ int dmdqn_debug(const dmdqn_dims* dims, void* workspace, size_t workspace_bytes,
     out->tc_error = (const int32_t*)(ws + w.tc_error);
     out->dh1 = (const float*)(ws + w.dh1);
     out->dh2 = (const float*)(ws + w.dh2);
+    out->relu2_bits = (const uint32_t*)(ws + w.mask2);
     return DMDQN_OK;
 }
 

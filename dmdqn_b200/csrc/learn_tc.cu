@@ -151,6 +151,8 @@ struct TcArgs {
     const int32_t *rows, *act_b, *active, *step_t;
     const float *r_hat, *done_b;
     const float4* adam_sc;
+    uint32_t* mask2;              // relu'(h2) bits [n_nets][H/32][B]
+    float* w3_copy;               // [n_nets][H][4]
     float *y, *gcoef, *q_all, *q_next, *tq_all, *h1, *dh1, *dh2, *part_loss, *part_b3, *part_w3, *part_b2, *metrics, *grads;
     int* error;
 };
@@ -208,10 +210,10 @@ template <bool BT>
 struct Pipe {
     static constexpr int KCX = BT ? 16 : 8;                   // k extent of a chunk
     static constexpr int NST = BT ? 2 : 4;                    // shared-memory stages
-    static constexpr int WPC = BT ? 2 : 1;                    // producer warps that stage one chunk together
-    static constexpr int GROUPS = (NT / 32) / WPC;            // chunk c belongs to producer group c % GROUPS
+    static constexpr int GROUPS = NST;                        // one producer group per stage: chunk c belongs to group c % NST
+    static constexpr int WPC = (NT / 32) / GROUPS;            // warps of a group (2 forward, 4 backward)
     static constexpr uint32_t HALF = KCX * H * 4;             // bytes of the hi (or lo) part of a stage
-    static constexpr int PIECES = KCX * H / 4 / (32 * WPC);   // 16-byte pieces per lane per chunk (16)
+    static constexpr int PIECES = KCX * H / 4 / (32 * WPC);   // 16-byte pieces per lane per chunk (8)
     static constexpr uint32_t FULL = BT ? Bar::FULL_B : Bar::FULL_F, EMPTY = BT ? Bar::EMPTY_B : Bar::EMPTY_F;
 };
 
@@ -244,87 +246,89 @@ __device__ __forceinline__ void a_ready(uint32_t sbase) {
     if ((threadIdx.x & 31) == 0) mbar_arrive(sbase + Fwd::BARS + Bar::AREADY);
 }
 
-// Producer side of a streamed GEMM.  Chunks are OWNED by producer groups (one warp forward, a warp pair
-// backward): group g stages chunks g, g + GROUPS, ... on its own -- global -> registers -> (hi | lo) ->
-// shared memory -> one arrival on full[stage] -- and loads its next chunk right after staging the current
-// one, i.e. GROUPS chunk-times (~3000 cycles of MMA work) ahead of its use.  No group waits for another
-// one, so the per-chunk latency chain (empty wait, stores, proxy fence, arrive) of one group overlaps with
-// the chains of the others instead of pacing the whole CTA.
+// Producer side of a streamed GEMM.  Every shared-memory stage is OWNED by one producer group (a warp pair
+// forward, four warps backward): group g stages chunks g, g + NST, ... on its own -- global -> registers ->
+// (hi | lo) -> shared memory -> one arrival per warp on full[g] -- and keeps its next TWO chunks in
+// registers, i.e. the loads of a chunk are issued 2 * NST chunk-times (~3500 cycles of MMA work) before it
+// is staged.  Groups never wait for each other, so the per-chunk latency chain (empty wait, stores, proxy
+// fence, arrive) of one group overlaps with the chains of the others instead of pacing the whole CTA.
+// Because a group sees every phase of its own stage's empty[] barrier, its parity waits are never more than
+// one phase behind (a waiter that skips phases cannot tell "two ahead" from "not yet": that deadlocked an
+// earlier version in which a stage was shared by two groups).
 // begin() can be called ahead of the epilogue that produces the A operand, run() after a_ready().
 template <int PASSES, bool BT>
 struct WStream {
     using P = Pipe<BT>;
-    float4 buf[P::PIECES];
+    float4 buf[2][P::PIECES];
     const float* src;             // this lane's piece 0 of chunk 0
-    uint32_t dst;                 // backward: its offset inside a stage
-    int nchunks, grp, lane_mn;
-    // forward : lane l, piece i -> k-row i/2, columns (i%2)*128 + l*4: a warp load covers 512 contiguous bytes
-    // backward: warp s of the pair, lane l, piece i -> row n = s*128 + i*8 + l/4, k piece l%4
+    uint32_t dst;                 // its offset inside a stage
+    int nchunks, grp;
+    // forward : lane L of the pair (0..63), piece i -> k-row i, columns 4L: a pair load covers one whole 1 KB row
+    // backward: lane L of the four warps (0..127), piece i -> row n = 32 i + L/4, k piece L%4
 
     __device__ __forceinline__ const float* piece_src(int i, int c) const {
-        if (!BT) return src + (size_t)c * P::KCX * H + (size_t)(i >> 1) * H + (i & 1) * 128;
-        return src + (size_t)c * P::KCX + (size_t)i * 8 * H;
+        if (!BT) return src + (size_t)c * P::KCX * H + (size_t)i * H;
+        return src + (size_t)c * P::KCX + (size_t)i * 32 * H;
     }
     __device__ __forceinline__ uint32_t piece_dst(int i) const {
-        if (!BT) return off_mn(H, i >> 1, (i & 1) * 128 + lane_mn);
-        return dst + (uint32_t)i * 8 * 64;                    // off_k64: 64-byte rows, the xor pattern repeats every 8 rows
+        // forward: off_mn(H, k = i, mn): k/4 selects a 4 KB block of 8 atoms, k%4 the 128-byte row and the 32-byte xor
+        if (!BT) return (dst + (uint32_t)(i >> 2) * (H >> 5) * 512 + (uint32_t)(i & 3) * 128) ^ ((uint32_t)(i & 3) << 5);
+        return dst + (uint32_t)i * 32 * 64;                   // off_k64: 64-byte rows, the xor pattern repeats every 8 rows
     }
-
-    __device__ __forceinline__ void load(int c) {
+    __device__ __forceinline__ void load(int slot, int c) {
 #if TC_EXP == 1
         return;
 #endif
 #pragma unroll
-        for (int i = 0; i < P::PIECES; ++i) buf[i] = ldg_stream(piece_src(i, TC_EXP == 3 ? 0 : c));
+        for (int i = 0; i < P::PIECES; ++i) buf[slot][i] = ldg_stream(piece_src(i, TC_EXP == 3 ? 0 : c));
     }
     // W: [K][H] row-major (BT = false) or [H][K] row-major with K = H (BT = true)
     __device__ __forceinline__ void begin(const float* __restrict__ W, int K) {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int L = (warp % P::WPC) * 32 + lane;
         nchunks = K / P::KCX;
         grp = warp / P::WPC;
         if (!BT) {
-            lane_mn = lane << 2;
-            src = W + lane_mn;
-            dst = 0;
+            src = W + (L << 2);
+            dst = off_mn(H, 0, L << 2);                       // k = 0: no xor yet
         } else {
-            const int n0 = (warp % P::WPC) * 128 + (lane >> 2), kp = (lane & 3) << 2;
-            src = W + (size_t)n0 * H + kp;
-            dst = off_k64(H, n0, kp);
+            src = W + (size_t)(L >> 2) * H + ((L & 3) << 2);
+            dst = off_k64(H, L >> 2, (L & 3) << 2);
         }
-        if (grp < nchunks) load(grp);
+        if (grp < nchunks) load(0, grp);
+        if (grp + P::NST < nchunks) load(1, grp + P::NST);
     }
     __device__ __forceinline__ bool run(uint32_t sbase, PipeState& ps) {
-        const uint32_t full0 = sbase + Fwd::BARS + P::FULL, empty0 = sbase + Fwd::BARS + P::EMPTY;
-        const uint32_t uses0 = BT ? ps.uses_b : ps.uses_f;
+        const uint32_t full = sbase + Fwd::BARS + P::FULL + 8 * grp, empty = sbase + Fwd::BARS + P::EMPTY + 8 * grp;
+        const uint32_t st = sbase + Fwd::WB + grp * (2 * P::HALF);
+        uint32_t u = BT ? ps.uses_b : ps.uses_f;              // use number of this group's stage
         bool ok = true;
-        // A parity wait is only meaningful for a waiter that is at most one phase behind the barrier, and a
-        // group skips GROUPS / NST - 1 uses of its stage between two of its chunks: it therefore walks the
-        // empty[] phases one by one.  seen = completions of empty[stage] known to this warp (every use of an
-        // earlier GEMM has retired: the DONE wait).  GROUPS % NST == 0, so a group always owns the same stage.
-        static_assert(P::GROUPS % P::NST == 0, "a producer group must stay on one stage");
-        uint32_t seen = uses0;
-        for (int c = grp; c < nchunks; c += P::GROUPS) {
-            const int b = c % P::NST;
-            const uint32_t u = uses0 + (uint32_t)(c / P::NST);                    // this is use number u of stage b
-            for (; seen < u && ok; ++seen) ok &= mbar_wait(empty0 + 8 * b, seen & 1);   // the MMAs of every earlier use are done
-            const uint32_t st = sbase + Fwd::WB + b * (2 * P::HALF);
+        for (int c0 = grp; c0 < nchunks; c0 += 2 * P::NST) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int c = c0 + j * P::NST;
+                if (c < nchunks) {                            // uniform across the group
+                    if (u && ok) ok = mbar_wait(empty, (u - 1) & 1);            // the MMAs of the previous use are done
+                    ++u;
 #if TC_EXP == 4
 #pragma unroll
-            for (int i = 0; i < P::PIECES; ++i) asm volatile("" ::"f"(buf[i].x), "f"(buf[i].y), "f"(buf[i].z), "f"(buf[i].w));
+                    for (int i = 0; i < P::PIECES; ++i) asm volatile("" ::"f"(buf[j][i].x), "f"(buf[j][i].y), "f"(buf[j][i].z), "f"(buf[j][i].w));
 #elif TC_EXP != 1
 #pragma unroll
-            for (int i = 0; i < P::PIECES; ++i) {
-                float4 hi, lo;
-                split4<PASSES>(buf[i], hi, lo);
-                const uint32_t o = st + piece_dst(i);
-                sts4(o, hi);
-                if (PASSES == 3) sts4(o + P::HALF, lo);
-            }
+                    for (int i = 0; i < P::PIECES; ++i) {
+                        float4 hi, lo;
+                        split4<PASSES>(buf[j][i], hi, lo);
+                        const uint32_t o = st + piece_dst(i);
+                        sts4(o, hi);
+                        if (PASSES == 3) sts4(o + P::HALF, lo);
+                    }
 #endif
-            if (c + P::GROUPS < nchunks) load(c + P::GROUPS);                     // next own chunk: a whole round of the other groups ahead
-            fence_async_smem();
-            __syncwarp();
-            if ((threadIdx.x & 31) == 0) mbar_arrive(full0 + 8 * b);             // WPC arrivals complete the stage
+                    if (c + 2 * P::NST < nchunks) load(j, c + 2 * P::NST);      // two own chunks ahead
+                    fence_async_smem();
+                    __syncwarp();
+                    if ((threadIdx.x & 31) == 0) mbar_arrive(full);             // WPC arrivals complete the stage
+                }
+            }
         }
         if (ok) ok = mbar_wait(sbase + Fwd::BARS + Bar::DONE, ps.gemms & 1);     // every MMA of this GEMM has retired
         tc_fence_after();
@@ -785,7 +789,15 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A) {
 
     WStream<PASSES, true> wsb;
     wsb.begin(P + A.L.w2, H);
-    // dh2[j] = relu'(h2[j]) * g * W3[j][a]  (dq has one non-zero per row): hi -> R, lo -> TMEM, raw -> scratch
+    // dh2[j] = relu'(h2[j]) * g * W3[j][a]  (dq has one non-zero per row): hi -> R, lo -> TMEM.  It is not
+    // written to global memory: K4b rebuilds its dh2^T operand from relu'(h2) bits, g, the action and W3.
+    if (valid) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) A.mask2[((size_t)g * (H / 32) + e.half * 4 + cc) * B + gr] = mask2[cc];
+    }
+    if (rt == 0)    // W3 as this step saw it (K4b updates W3 while other CTAs of the network still need the old values)
+        reinterpret_cast<float4*>(A.w3_copy + (size_t)g * H * 4)[threadIdx.x] =
+            *reinterpret_cast<const float4*>(sf + Fwd::W3S / 4 + threadIdx.x * 4);
 #pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {
         const int c0 = e.half * 128 + cc * 32;
@@ -800,10 +812,6 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A) {
                 x[t] = ((mask2[cc] >> (j + t)) & 1u) ? gi * w : 0.f;
             }
             const float4 x4 = make_float4(x[0], x[1], x[2], x[3]);
-            if (valid) {
-                float* o = A.dh2 + sb * H + (size_t)(c0 + j) * B + gr;
-                o[0] = x[0]; o[B] = x[1]; o[2 * (size_t)B] = x[2]; o[3 * (size_t)B] = x[3];
-            }
             float4 hi, l4;
             split4<PASSES>(x4, hi, l4);
             asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sbase + Fwd::R + off_k128(BM, e.row, c0 + j)), "f"(hi.x),
@@ -935,7 +943,7 @@ __global__ void __launch_bounds__(NT, 2) tc_wgrad_kernel(const TcArgs A) {
     const int m0 = is_w2 ? t * BM : 0;
     const int m_valid = is_w2 ? H : Dp;
     const float* AsrcT = A.h1 + sb * H;                       // [H][B]
-    const float* DsrcT = (is_w2 ? A.dh2 : A.dh1) + sb * H;    // [H][B]
+    const float* DsrcT = A.dh1 + sb * H;                      // [H][B] (dW1 tile only)
     const int32_t* rows = A.rows + sb;
 
     if (tid == 0) {
@@ -988,6 +996,32 @@ __global__ void __launch_bounds__(NT, 2) tc_wgrad_kernel(const TcArgs A) {
         b_k[r] = (p & 3) << 2;
         b_src[r] = DsrcT + (size_t)(p >> 2) * B + b_k[r];
     }
+    // dW2 tiles: thread = dh2 column n; dh2[k][n] = relu'(h2)[k][n] ? g_k * W3[n][a_k] : 0 is rebuilt per chunk from
+    // 16 rows of (g, action, one mask word per warp): warp-uniform, L1 / L2-resident loads instead of a B x H read
+    const float4 w3n = is_w2 ? __ldg(reinterpret_cast<const float4*>(A.w3_copy + (size_t)g * H * 4) + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t* mrow = A.mask2 + ((size_t)g * (H / 32) + warp) * B;
+    const uint32_t b_dst_n = 2 * Wg::A_BYTES + off_k64(H, tid, 0);    // piece kp of row n: 16-byte slot index ^= kp
+    auto build_b = [&](int c, float4 (&out)[4]) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k0 = c * KC + q * 4;
+            float x[4] = {0.f, 0.f, 0.f, 0.f};
+            if (k0 < B) {                                     // B % 4 == 0: a group of four rows is valid or not as a whole
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(A.gcoef + sb + k0));
+                const int4 a4 = __ldg(reinterpret_cast<const int4*>(A.act_b + sb + k0));
+                const uint4 m4 = __ldg(reinterpret_cast<const uint4*>(mrow + k0));
+                const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+                const int aa[4] = {a4.x, a4.y, a4.z, a4.w};
+                const uint32_t mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float w = aa[u] == 0 ? w3n.x : aa[u] == 1 ? w3n.y : aa[u] == 2 ? w3n.z : w3n.w;
+                    x[u] = ((mm[u] >> lane) & 1u) ? gg[u] * w : 0.f;
+                }
+            }
+            out[q] = make_float4(x[0], x[1], x[2], x[3]);
+        }
+    };
     float4 ra[2][2], rb[2][4];
     auto load = [&](int slot, int c) {
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1003,10 +1037,12 @@ __global__ void __launch_bounds__(NT, 2) tc_wgrad_kernel(const TcArgs A) {
                 ra[slot][r] = ldg_stream(a_src[r] + (size_t)__ldg(rows + k) * Dp);
             }
         }
+        if (!is_w2) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            rb[slot][r] = z;
-            if (c * KC + b_k[r] < B) rb[slot][r] = ldg_stream(b_src[r] + (size_t)c * KC);
+            for (int r = 0; r < 4; ++r) {
+                rb[slot][r] = z;
+                if (c * KC + b_k[r] < B) rb[slot][r] = ldg_stream(b_src[r] + (size_t)c * KC);
+            }
         }
     };
     load(0, 0);
@@ -1018,11 +1054,13 @@ __global__ void __launch_bounds__(NT, 2) tc_wgrad_kernel(const TcArgs A) {
             if (c < nchunks) {                                // uniform across the CTA
                 const uint32_t st = sbase + j * Wg::STG;
                 if (c >= 2 && ok) ok = mbar_wait(sbase + Wg::BARS + 8 * j, ((c >> 1) - 1) & 1);   // MMAs of chunk c - 2 are done
+                if (is_w2) build_b(c, rb[j]);                 // pieces kp = 0..3 of row n = tid
 #pragma unroll
                 for (int r = 0; r < 6; ++r) {
                     float4 hi, lo;
                     split4<PASSES>(r < 2 ? ra[j][r] : rb[j][r - 2], hi, lo);
-                    const uint32_t o = st + (r < 2 ? a_dst[r] : b_dst[r - 2]);
+                    const uint32_t bo = is_w2 ? b_dst_n ^ (uint32_t)((r - 2) << 4) : b_dst[r < 2 ? 0 : r - 2];
+                    const uint32_t o = st + (r < 2 ? a_dst[r] : bo);
                     sts4(o, hi);
                     if (PASSES == 3) sts4(o + (r < 2 ? Wg::A_BYTES : Wg::B_BYTES), lo);
                 }
@@ -1182,6 +1220,8 @@ int launch_learn_tc(const dmdqn_dims& d, const dmdqn_hparams& hp, const dmdqn_re
     A.active = reinterpret_cast<const int32_t*>(ws + w.active);
     A.step_t = reinterpret_cast<const int32_t*>(ws + w.step_t);
     A.adam_sc = reinterpret_cast<const float4*>(ws + w.adam_sc);
+    A.mask2 = reinterpret_cast<uint32_t*>(ws + w.mask2);
+    A.w3_copy = reinterpret_cast<float*>(ws + w.w3_copy);
     A.r_hat = reinterpret_cast<const float*>(ws + w.r_hat);
     A.done_b = reinterpret_cast<const float*>(ws + w.done_b);
     A.y = reinterpret_cast<float*>(ws + w.y);

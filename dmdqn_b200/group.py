@@ -344,13 +344,21 @@ class AgentGroup:
             off = ptr - base
             nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
             return self.workspace[off:off + nbytes].view(dtype).view(*shape)
-        return {"y": view(v.y, torch.float32, (g, b)), "q_all": view(v.q_all, torch.float32, (g, b, 4)),
-                "q_next": view(v.q_next, torch.float32, (g, b, 4)), "tq_all": view(v.tq_all, torch.float32, (g, b, 4)),
-                "rows": view(v.rows, torch.int32, (g, b)), "r_hat": view(v.r_hat, torch.float32, (g, b)),
-                "active": view(v.active, torch.int32, (g,)), "tc_error": view(v.tc_error, torch.int32, (1,)),
-                # the tcgen05 path keeps its activation scratch transposed ([feature][batch])
-                **{k_: (view(p_, torch.float32, (g, self.hidden, b)).transpose(1, 2) if self.hp.precision != 0
-                        else view(p_, torch.float32, (g, b, self.hidden))) for k_, p_ in (("dh1", v.dh1), ("dh2", v.dh2))}}
+        out = {"y": view(v.y, torch.float32, (g, b)), "q_all": view(v.q_all, torch.float32, (g, b, 4)),
+               "q_next": view(v.q_next, torch.float32, (g, b, 4)), "tq_all": view(v.tq_all, torch.float32, (g, b, 4)),
+               "rows": view(v.rows, torch.int32, (g, b)), "r_hat": view(v.r_hat, torch.float32, (g, b)),
+               "active": view(v.active, torch.int32, (g,)), "tc_error": view(v.tc_error, torch.int32, (1,))}
+        if self.hp.precision != 0:
+            # the tcgen05 path keeps its activation scratch transposed ([feature][batch]) and never
+            # materialises dh2: "dh2" is relu'(h2) as 0/1 here (its non-zero pattern is what the tests use)
+            out["dh1"] = view(v.dh1, torch.float32, (g, self.hidden, b)).transpose(1, 2)
+            bits = view(v.relu2_bits, torch.int32, (g, self.hidden // 32, b))
+            sh = torch.arange(32, device=bits.device, dtype=torch.int32).view(1, 1, 32, 1)
+            out["dh2"] = ((bits.unsqueeze(2) >> sh) & 1).reshape(g, self.hidden, b).transpose(1, 2).float()
+        else:
+            out["dh1"] = view(v.dh1, torch.float32, (g, b, self.hidden))
+            out["dh2"] = view(v.dh2, torch.float32, (g, b, self.hidden))
+        return out
 
     def sync_target(self, mask=None, tau: float | None = None) -> None:
         """update_target_network (tau None, dqn_agent.py:382-384) / soft update (:389-399)."""

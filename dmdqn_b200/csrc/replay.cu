@@ -37,11 +37,7 @@ push_kernel(dmdqn_dims d, dmdqn_replay rp, const float* __restrict__ obs, const 
 }
 
 // ---------------------------------------------------------------- sample ----------------
-constexpr int kEmpty = -1;
-
-__device__ __forceinline__ unsigned hash_slot(int key, int log2t) {
-    return ((unsigned)key * 2654435761u) >> (32 - log2t);
-}
+constexpr int kSampleThreads = 256;
 
 // Canonical float64 tree sum over a batch held in shared memory: lane l adds elements
 // l, l+32, ... in order, then an xor butterfly (16,8,4,2,1).  oracle/replay.py
@@ -54,20 +50,32 @@ __device__ __forceinline__ double tree_sum(int n, int lane, F elem) {
     return acc;
 }
 
-// One warp per network.  smem: keys[T] vals[T] (sparse Fisher-Yates pool), words[B], rs[B].
-__global__ void __launch_bounds__(32)
+// One CTA per network.  smem: js[B] (draws in, then j_i), pt[B], words[B] (logical indices out), rs[B].
+//
+// Draw without replacement = CPython random.sample's pool path with randbelow(m) := (w*m) >> 32
+// (reference dqn_agent.py:63):   for i in 0..B-1:  j_i = randbelow(n-i); result[i] = pool[j_i];
+// pool[j_i] = pool[t_i], t_i = n-i-1, pool = identity at the start.  The loop is sequential only through
+// the <= B displaced pool entries, so it is resolved in parallel instead of replayed:
+//   W_k := the value step k writes to pool[j_k] = pool_k[t_k] = W_{pt[k]} if pt[k] >= 0 else t_k,
+//          pt[k] = latest k' < k with j_k' == t_k  (the only way position t_k was displaced before step k)
+//   result[i] = W_{pj[i]} if pj[i] >= 0 else j_i,   pj[i] = latest k < i with j_k == j_i.
+// pj / pt come from a B x B compare (thread i scans k < i; every read is a shared-memory broadcast) and
+// the W chains (almost always of length 0 or 1) are chased read-only.  Same integers as the sequential
+// loop for every input (oracle/replay.py fisher_yates_indices replays the loop itself).
+__global__ void __launch_bounds__(kSampleThreads)
 sample_kernel(dmdqn_dims d, dmdqn_hparams hp, dmdqn_replay rp, int32_t* __restrict__ learn_step,
               const uint32_t* __restrict__ draws, const uint8_t* __restrict__ learn_mask, int advance,
               int32_t* __restrict__ rows, float* __restrict__ r_hat, int32_t* __restrict__ act_b,
               float* __restrict__ done_b, int32_t* __restrict__ active, int32_t* __restrict__ step_t,
-              float4* __restrict__ adam_sc, int log2t) {
+              float4* __restrict__ adam_sc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int B = d.batch, T = 1 << log2t;
-    int* keys = reinterpret_cast<int*>(smem_raw);
-    int* vals = keys + T;
-    int* words = vals + T;                         // draws in, logical indices out
-    double* rs = reinterpret_cast<double*>(words + ((B + 1) & ~1));
-    const int g = blockIdx.x, lane = threadIdx.x;
+    const int B = d.batch, Bp = (B + 1) & ~1;
+    int* js = reinterpret_cast<int*>(smem_raw);
+    int* pt = js + Bp;
+    int* words = pt + Bp;
+    double* rs = reinterpret_cast<double*>(words + Bp);
+    __shared__ double stat[2];
+    const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const bool shared_net = d.n_nets == 1 && d.n_agents > 1;
 
     // Population: this agent's ring, or (shared parameters) all rings of this GPU, which the
@@ -76,7 +84,7 @@ sample_kernel(dmdqn_dims d, dmdqn_hparams hp, dmdqn_replay rp, int32_t* __restri
     const int size0 = (int)(nw0 < d.capacity ? nw0 : d.capacity);
     const long long pop = shared_net ? (long long)size0 * d.n_agents : size0;
     const bool on = (learn_mask == nullptr || learn_mask[g]) && pop >= B;  // dqn_agent.py:61-62
-    if (lane == 0) {
+    if (tid == 0) {
         active[g] = on ? 1 : 0;
         int t = learn_step[g];
         if (on && advance) learn_step[g] = ++t;    // dqn_agent.py:359
@@ -94,52 +102,50 @@ sample_kernel(dmdqn_dims d, dmdqn_hparams hp, dmdqn_replay rp, int32_t* __restri
     }
     if (!on) return;
 
-    for (int i = lane; i < B; i += 32) words[i] = (int)draws[(size_t)g * B + i];
     if (hp.sample_mode == DMDQN_SAMPLE_FISHER_YATES) {
-        for (int i = lane; i < T; i += 32) keys[i] = kEmpty;
-        __syncwarp();
-        if (lane == 0) {
-            // CPython random.sample pool path with randbelow(m) := (w*m) >> 32:
-            //   j = randbelow(n-i); result[i] = pool[j]; pool[j] = pool[n-i-1]
-            // pool is the identity except for <= B displaced entries kept in the hash map.
-            for (int i = 0; i < B; ++i) {
-                const unsigned m = (unsigned)(pop - i);
-                const int j = (int)__umulhi((unsigned)words[i], m);
-                const int t = (int)m - 1;
-                unsigned sj = hash_slot(j, log2t), st = hash_slot(t, log2t);
-                int vj = j, vt = t;
-                for (;; sj = (sj + 1) & (T - 1)) {      // lookup j; remember its slot for the put
-                    const int k = keys[sj];
-                    if (k == j) { vj = vals[sj]; break; }
-                    if (k == kEmpty) break;
-                }
-                for (;; st = (st + 1) & (T - 1)) {
-                    const int k = keys[st];
-                    if (k == t) { vt = vals[st]; break; }
-                    if (k == kEmpty) break;
-                }
-                words[i] = vj;
-                keys[sj] = j;                           // sj is j's slot, or the first empty one
-                vals[sj] = vt;
+        const int n = (int)pop;
+        for (int i = tid; i < B; i += kSampleThreads)
+            js[i] = (int)__umulhi(draws[(size_t)g * B + i], (unsigned)(n - i));
+        __syncthreads();
+        for (int i0 = 0; i0 < B; i0 += kSampleThreads) {   // the warp's trip count is its largest i: keep the loop warp-uniform
+            const int i = i0 + tid;
+            const int ji = i < B ? js[i] : -1, ti = i < B ? n - i - 1 : -1;
+            int pj = -1, ptk = -1;
+            const int kend = min(B, i0 + (tid | 31));       // every lane of the warp scans up to the warp's last i (extra k >= i are masked)
+#pragma unroll 4
+            for (int k = 0; k < kend; ++k) {
+                const int jk = js[k];
+                const bool before = k < i;
+                pj = (before && jk == ji) ? k : pj;
+                ptk = (before && jk == ti) ? k : ptk;
             }
+            if (i < B) { pt[i] = ptk; words[i] = pj; }
         }
-        __syncwarp();
+        __syncthreads();
+        for (int i = tid; i < B; i += kSampleThreads) {    // words[i] is read and rewritten by its own thread only
+            int k = words[i];
+            int v = js[i];
+            if (k >= 0) {
+                while (pt[k] >= 0) k = pt[k];
+                v = n - k - 1;
+            }
+            words[i] = v;
+        }
     } else if (hp.sample_mode == DMDQN_SAMPLE_REPLACEMENT) {
-        for (int i = lane; i < B; i += 32) words[i] = (int)__umulhi((unsigned)words[i], (unsigned)pop);
-        __syncwarp();
+        for (int i = tid; i < B; i += kSampleThreads) words[i] = (int)__umulhi(draws[(size_t)g * B + i], (unsigned)pop);
     } else {                                            // explicit logical indices, clamped
-        for (int i = lane; i < B; i += 32) {
-            const int v = words[i];
+        for (int i = tid; i < B; i += kSampleThreads) {
+            const int v = (int)draws[(size_t)g * B + i];
             words[i] = v < 0 ? 0 : (v >= pop ? (int)pop - 1 : v);
         }
-        __syncwarp();
     }
+    __syncthreads();
 
-    for (int i = lane; i < B; i += 32) {
+    for (int i = tid; i < B; i += kSampleThreads) {
         const int logical = words[i];
         const int agent = shared_net ? logical / size0 : g;
         const int lj = shared_net ? logical % size0 : logical;
-        const long long nw = rp.n_written[agent];
+        const long long nw = shared_net ? rp.n_written[agent] : nw0;
         const long long sz = nw < d.capacity ? nw : d.capacity;
         const int slot = (int)((nw - sz + lj) % d.capacity);
         const int row = agent * d.capacity + slot;
@@ -155,18 +161,22 @@ sample_kernel(dmdqn_dims d, dmdqn_hparams hp, dmdqn_replay rp, int32_t* __restri
         done_b[(size_t)g * B + i] = rp.done[row] ? 1.f : 0.f;
         rs[i] = rp.rew[row];
     }
-    __syncwarp();
-    if (hp.normalize_rewards) {                         // dqn_agent.py:66-69, float64
-        const double mean = __ddiv_rn(tree_sum(B, lane, [&](int i) { return rs[i]; }), (double)B);
-        const double var = __ddiv_rn(tree_sum(B, lane, [&](int i) {
-                                         const double dv = __dsub_rn(rs[i], mean);
-                                         return __dmul_rn(dv, dv);
-                                     }), (double)B);
-        const double denom = __dadd_rn(__dsqrt_rn(var), 1e-8);
-        for (int i = lane; i < B; i += 32)
+    __syncthreads();
+    if (hp.normalize_rewards) {                         // dqn_agent.py:66-69, float64; warp 0 keeps the canonical tree
+        if (tid < 32) {
+            const double mean = __ddiv_rn(tree_sum(B, lane, [&](int i) { return rs[i]; }), (double)B);
+            const double var = __ddiv_rn(tree_sum(B, lane, [&](int i) {
+                                             const double dv = __dsub_rn(rs[i], mean);
+                                             return __dmul_rn(dv, dv);
+                                         }), (double)B);
+            if (lane == 0) { stat[0] = mean; stat[1] = __dadd_rn(__dsqrt_rn(var), 1e-8); }
+        }
+        __syncthreads();
+        const double mean = stat[0], denom = stat[1];
+        for (int i = tid; i < B; i += kSampleThreads)
             r_hat[(size_t)g * B + i] = (float)__ddiv_rn(__dsub_rn(rs[i], mean), denom);
     } else {
-        for (int i = lane; i < B; i += 32) r_hat[(size_t)g * B + i] = (float)rs[i];
+        for (int i = tid; i < B; i += kSampleThreads) r_hat[(size_t)g * B + i] = (float)rs[i];
     }
 }
 
@@ -210,20 +220,19 @@ int launch_push(const dmdqn_dims& d, const dmdqn_replay& rp, const float* obs, c
 int launch_sample(const dmdqn_dims& d, const dmdqn_hparams& hp, const dmdqn_replay& rp, const dmdqn_nets& nets,
                   const void* draws, const uint8_t* learn_mask, int advance, char* ws, const Workspace& w,
                   cudaStream_t s) {
-    int log2t = 1;
-    while ((1 << log2t) < 2 * d.batch) ++log2t;
-    const size_t smem = (size_t)(2 << log2t) * 4 + (size_t)((d.batch + 1) & ~1) * 4 + (size_t)d.batch * 8;
+    DMDQN_CHECK_ARG(d.batch <= 4096, "batch %d: the sample kernel serves batches up to 4096", d.batch);
+    const size_t smem = (size_t)((d.batch + 1) & ~1) * (3 * 4 + 8);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         DMDQN_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    sample_kernel<<<d.n_nets, 32, smem, s>>>(
+    sample_kernel<<<d.n_nets, kSampleThreads, smem, s>>>(
         d, hp, rp, nets.learn_step, static_cast<const uint32_t*>(draws), learn_mask, advance,
         reinterpret_cast<int32_t*>(ws + w.rows), reinterpret_cast<float*>(ws + w.r_hat),
         reinterpret_cast<int32_t*>(ws + w.act_b), reinterpret_cast<float*>(ws + w.done_b),
         reinterpret_cast<int32_t*>(ws + w.active), reinterpret_cast<int32_t*>(ws + w.step_t),
-        reinterpret_cast<float4*>(ws + w.adam_sc), log2t);
+        reinterpret_cast<float4*>(ws + w.adam_sc));
     DMDQN_CUDA(cudaGetLastError());
     return DMDQN_OK;
 }

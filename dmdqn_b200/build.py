@@ -38,6 +38,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if os.environ.get("DMDQN_TC_TIMING"):          # phase stamps printed by a few CTAs (profiling aid only)
         cmd.insert(1, "-DTC_TIMING")
         cmd.insert(1, "-DTC_EXP=" + os.environ.get("DMDQN_TC_EXP", "0"))
+    if os.environ.get("DMDQN_TC_EXP_ONLY"):        # experiment switch without the stamps (results are wrong by design)
+        cmd.insert(1, "-DWG_EXP=" + os.environ["DMDQN_TC_EXP_ONLY"])
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -112,11 +112,12 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// x = hi + lo, hi = x rounded to tf32 (nearest, ties away), lo exact in fp32
+// x = hi + lo, hi = x truncated to tf32 (the top 19 bits), lo = x - hi exact in fp32.  Truncation is one LOP3
+// where cvt.rna.tf32 is a four-instruction sequence on sm_100a (add, mask, inf/nan test, select); |lo| < 2^-10 |x|
+// instead of <= 2^-11 |x|, so the term the tensor core drops when it truncates lo is < 2^-20 |x| -- measured
+// against the fp32 bar in tests/test_gpu_parity.py like before.
 __device__ __forceinline__ float tf32_hi(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return __uint_as_float(__float_as_uint(x) & 0xffffe000u);
 }
 template <int PASSES>
 __device__ __forceinline__ void split4(const float4& x, float4& hi, float4& lo) {
@@ -161,6 +162,9 @@ struct TcArgs {
 #ifndef TC_EXP
 #define TC_EXP 0
 #endif
+#ifndef WG_EXP
+#define WG_EXP 0      // K4b experiment bits (profiling aid; results are wrong by design)
+#endif
 #ifdef TC_TIMING
 #define TS_DECL long long ts_[16]; int tsi_ = 0
 #define TS() do { if (tsi_ < 16) ts_[tsi_++] = clock64(); } while (0)
@@ -172,6 +176,19 @@ struct TcArgs {
 #define TS_DECL
 #define TS()
 #define TS_PRINT(name)
+#endif
+
+#ifdef TC_TIMING
+#define WG_TS_DECL long long wts_[20]; int wtsi_ = 0
+#define WG_TS() do { if (wtsi_ < 20) wts_[wtsi_++] = clock64(); } while (0)
+#define WG_D(i) ((i) < wtsi_ ? wts_[i] - wts_[(i) - 1] : 0LL)
+#define WG_TS_PRINT(name, cond) do { if ((cond) && (blockIdx.x == 0 || blockIdx.x == 100)) \
+        printf("%s cta %d: %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld\n", name, blockIdx.x, WG_D(1), WG_D(2), WG_D(3), WG_D(4), \
+               WG_D(5), WG_D(6), WG_D(7), WG_D(8), WG_D(9), WG_D(10), WG_D(11), WG_D(12), WG_D(13), WG_D(14)); } while (0)
+#else
+#define WG_TS_DECL
+#define WG_TS()
+#define WG_TS_PRINT(name, cond)
 #endif
 
 // Shared-memory carve-up of the K3 / K4a kernels (offsets from a 1024-byte aligned base).
@@ -863,307 +880,429 @@ __device__ __forceinline__ AdamK adam_k(const TcArgs& A, int g) {   // scalars p
     return k;
 }
 __device__ __forceinline__ void adam1(const AdamK& k, float g, float& th, float& m, float& v, float& tg) {
+#if WG_EXP & 1
+    th -= g; m += g; v += g; return;
+#endif
     m = m + (g - m) * k.omb1;
     v = v + (g * g - v) * k.omb2;
-    th = th - (m * k.alpha) / (sqrtf(v) + k.eps);
+    // MUFU square root and reciprocal (each within ~2 ulp): the quotient is a step of at most ~lr, so a few
+    // ulp of it are far below one ulp of the weight it is subtracted from; the IEEE sequences cost ~60
+    // dependent instructions per element and made the epilogue issue-bound
+    float sq;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(v));
+    th = th - __fdividef(m * k.alpha, sq + k.eps);
     if (k.sync == 1) tg = th;
     else if (k.sync == 2) tg = k.tau * th + (1.0f - k.tau) * tg;
 }
 
-struct Wg {     // shared-memory carve-up of the wgrad kernel: 2 stages of (A hi|lo 16 KB, B hi|lo 32 KB); 2 CTAs / SM
-    static constexpr int STAGES = 2;
+struct Wg {     // persistent wgrad kernel, one CTA per SM
+    static constexpr int STAGES = 3;
     static constexpr uint32_t A_BYTES = KC * BM * 4;          // 8 KB
     static constexpr uint32_t B_BYTES = KC * H * 4;           // 16 KB
-    static constexpr uint32_t STG = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr uint32_t BARS = STAGES * STG;
-    static constexpr uint32_t TOTAL = BARS + 64;
+    static constexpr uint32_t STG = 2 * A_BYTES + 2 * B_BYTES;   // A hi|lo, B hi|lo: 48 KB
     static constexpr int TLD = 36;                            // floats per row of an epilogue transpose tile
+    static constexpr uint32_t TILES = STAGES * STG;           // 8 epilogue warps x 32 x TLD floats
+    static constexpr uint32_t W3T = TILES + 8 * 32 * TLD * 4; // W3^T [2 item parities][4 actions][256] floats
+    static constexpr uint32_t BARS = W3T + 2 * 4 * H * 4;
+    static constexpr uint32_t FULL = 0, EMPTY = 24, ACC_FULL = 48, ACC_FREE = 64, TMEM = 80;   // byte offsets from BARS
+    static constexpr uint32_t TOTAL = BARS + 128;
+    static constexpr int NTW = 16 * 32;                       // 8 producer warps (lane 0 of warp 0 also issues the MMAs), 8 epilogue warps
 };
 
+// Work items of K4b: per network two dW2 tiles (rows t*128..) and one dW1 tile.  The dW2 tiles come first in
+// the item order (they are the longer ones), so a static round-robin over the CTAs ends on the short items.
+__device__ __forceinline__ void wg_item(int q, int G, int& g, int& t) {
+    if (q < 2 * G) { g = q >> 1; t = q & 1; }
+    else { g = q - 2 * G; t = 2; }
+}
+
 // dW tile: D[128 x 256] = A^T-operand * D-operand over K = batch, Adam in the epilogue.
-//   t = 0,1: dW2 rows t*128.. : A = h1^T scratch [m][k] (K-major SW64), B = dh2^T scratch [n][k] (K-major SW64)
+//   t = 0,1: dW2 rows t*128.. : A = h1^T scratch [m][k] (K-major SW64), B = dh2^T rebuilt [n][k] (K-major SW64)
 //   t = 2  : dW1 rows 0..95   : A = s gathered from the ring [k][m] (MN-major),  B = dh1^T scratch (K-major SW64);
 //            A column m = obs_stride is set to 1, so row obs_stride of the tile is db1 = sum_k dh1[k][:] for free;
-//            this CTA also folds the per-row-tile partials of db2 / dW3 / db3 (from K4a) and emits the metrics.
+//            the epilogue of this item also folds the per-row-tile partials of db2 / dW3 / db3 (from K4a) and
+//            emits the metrics.
+// Persistent and warp-specialised: a CTA walks its items q = blockIdx.x, + gridDim.x, ...;
+//   warps 0-7  stage operand chunks (global -> registers -> hi | lo -> shared memory, 3 stages) and run ahead
+//              into the next item while
+//   warp 16    (one lane) issues the tcgen05.mma of a chunk as soon as it is staged, alternating between two
+//              TMEM accumulators (columns 0..255 / 256..511), and
+//   warps 8-15 read a finished accumulator and do the Adam read-modify-write of theta / m / v / theta_tgt.
+// The epilogue is pure HBM traffic (24 bytes per parameter) and the GEMM needs almost none, so running them
+// concurrently on every SM keeps HBM busy for the whole kernel instead of only during the epilogue phase of a
+// wave of lock-stepped CTAs.
 template <int PASSES>
-__global__ void __launch_bounds__(NT, 2) tc_wgrad_kernel(const TcArgs A) {
+__global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A) {
     extern __shared__ uint8_t smem_raw[];
-    const int B = A.d.batch, Dp = A.d.obs_stride;
-    constexpr int per_net = 3;
-    const int g = blockIdx.x / per_net, t = blockIdx.x % per_net;
+    const int B = A.d.batch, Dp = A.d.obs_stride, G = A.d.n_nets;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (!A.active[g]) {
-        if (t == 2 && tid < DMDQN_METRICS_STRIDE && A.metrics) A.metrics[g * DMDQN_METRICS_STRIDE + tid] = 0.f;
-        return;
-    }
-    const size_t sb = (size_t)g * B, pb = (size_t)g * A.L.stride;
-    float* th = A.nets.theta + pb;
-    float* tg = A.nets.theta_tgt + pb;
-    float* am = A.nets.adam_m + pb;
-    float* av = A.nets.adam_v + pb;
-    const AdamK k = adam_k(A, g);
-    if (t == 2) {
-        // head / bias gradients: per-row-tile partials from K4a summed in tile order, then Adam
-        auto upd = [&](int64_t off, float grad) {
-            if (A.grads) { A.grads[pb + off] = grad; return; }
-            float tgv = k.sync == 2 ? tg[off] : 0.f;
-            adam1(k, grad, th[off], am[off], av[off], tgv);
-            if (k.sync) tg[off] = tgv;
-        };
-        const size_t p0 = (size_t)g * A.tiles;
-        float s2 = 0.f, w[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int r = 0; r < A.tiles; ++r) {
-            s2 += A.part_b2[(p0 + r) * H + tid];
-            const float4 pw = reinterpret_cast<const float4*>(A.part_w3 + (p0 + r) * H * 4)[tid];
-            w[0] += pw.x; w[1] += pw.y; w[2] += pw.z; w[3] += pw.w;
-        }
-        upd(A.L.b2 + tid, s2);
-        for (int a = 0; a < 4; ++a) upd(A.L.w3 + (int64_t)tid * 4 + a, w[a]);
-        if (tid < 4) {
-            float s3 = 0.f;
-            for (int r = 0; r < A.tiles; ++r) s3 += A.part_b3[(p0 + r) * 4 + tid];
-            upd(A.L.b3 + tid, s3);
-        }
-        if (tid == 0 && A.metrics) {
-            double ls = 0, qs = 0, qq = 0, hist[4] = {0, 0, 0, 0};
-            for (int r = 0; r < A.tiles; ++r) {
-                const float* pl = A.part_loss + (p0 + r) * 8;
-                ls += pl[0]; qs += pl[1]; qq += pl[2];
-                for (int a = 0; a < 4; ++a) hist[a] += pl[3 + a];
-            }
-            const double cnt = (double)B * A.d.n_actions, mean = qs / cnt, var = fmax(qq / cnt - mean * mean, 0.0);
-            float* m = A.metrics + g * DMDQN_METRICS_STRIDE;
-            m[0] = (float)(ls / A.loss_batch); m[1] = (float)mean; m[2] = (float)sqrt(var);
-            for (int a = 0; a < 4; ++a) m[3 + a] = (float)hist[a];
-            m[7] = 1.f;
-        }
-    }
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const bool is_w2 = t < 2;
-    const int m0 = is_w2 ? t * BM : 0;
-    const int m_valid = is_w2 ? H : Dp;
-    const float* AsrcT = A.h1 + sb * H;                       // [H][B]
-    const float* DsrcT = A.dh1 + sb * H;                      // [H][B] (dW1 tile only)
-    const int32_t* rows = A.rows + sb;
+    const uint32_t bars = sbase + Wg::BARS;
+    const int n_items = 3 * G;
+    const int nchunks = (B + KC - 1) / KC;
 
     if (tid == 0) {
-        for (int s = 0; s < Wg::STAGES; ++s) mbar_init(sbase + Wg::BARS + 8 * s, 1);
+        for (int s = 0; s < Wg::STAGES; ++s) {
+            mbar_init(bars + Wg::FULL + 8 * s, 8);            // one arrival per producer warp
+            mbar_init(bars + Wg::EMPTY + 8 * s, 1);           // one tcgen05.commit
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bars + Wg::ACC_FULL + 8 * b, 1);        // one tcgen05.commit
+            mbar_init(bars + Wg::ACC_FREE + 8 * b, 8);        // one arrival per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + Wg::BARS + 32), "r"(256));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars + Wg::TMEM), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     uint32_t tmem;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(sbase + Wg::BARS + 32));
-
-    TS_DECL;
-    TS();
-    const int nchunks = (B + KC - 1) / KC;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(bars + Wg::TMEM));
     bool ok = true;
-    // Operand chunks (16 batch rows) travel global -> registers -> (hi | lo) -> shared memory; the loads of
-    // chunk c + 2 are issued when chunk c is staged, so two chunks of latency are covered by registers and
-    // the two shared-memory stages only have to cover the MMAs.  piece -> offset inside a stage:
-    uint32_t a_dst[2], b_dst[4];
-    const float* a_src[2];
-    const float* b_src[4];
-    int a_k[2], b_k[4];           // k offset of the piece inside its chunk
-    bool a_ones[2], a_live[2];
+
+    if (warp < 8) {
+        // ------------------------------------------------------------------ producers ------------------
+        // Operand chunks (16 batch rows) travel global -> registers -> (hi | lo) -> shared memory; the loads of
+        // chunk c + 2 are issued when chunk c is staged, so two chunks of latency are covered by registers and
+        // the shared-memory stages only have to cover the MMAs.
+        uint32_t stage = 0, ph = 0, used = 0;
+        // Lane 0 of warp 0 is also the MMA issuer: after staging chunk c it issues the tcgen05.mma of chunk
+        // c - 1 (which the other warps have normally finished staging by then), so no thread sits in a wait
+        // that paces the others.  pend_* describe the chunk whose MMAs are still to be issued.
+        bool pend = false, pend_w2 = false, pend_first = false, pend_last = false;
+        uint32_t pend_stage = 0, pend_ph = 0;
+        int pend_n = 0, n = 0;
+        auto issue_pending = [&]() {
+            if (lane == 0) {
+                const uint32_t acc_buf = (uint32_t)(pend_n & 1);
+                if (pend_first && pend_n >= 2 && ok)              // the epilogue has read item n - 2 out of this accumulator
+                    ok = mbar_wait(bars + Wg::ACC_FREE + 8 * acc_buf, (uint32_t)((pend_n >> 1) - 1) & 1u);
+                if (ok) ok = mbar_wait(bars + Wg::FULL + 8 * pend_stage, pend_ph);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem + acc_buf * 256u;
+                const uint32_t idesc = make_idesc(!pend_w2, pend_w2);
+                const uint32_t st = sbase + pend_stage * Wg::STG;
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const int p = tid + r * NT;
-        if (is_w2) {                                          // row m = p/4, 4 k-pieces per row (K-major SW64)
-            a_dst[r] = off_k64(BM, p >> 2, (p & 3) << 2);
-            a_k[r] = (p & 3) << 2;
-            a_src[r] = AsrcT + (size_t)(m0 + (p >> 2)) * B + a_k[r];
-            a_ones[r] = false; a_live[r] = true;
-        } else {                                              // k = p/32, 32 m-pieces per k-row (MN-major)
-            const int m = (p & 31) << 2;
-            a_dst[r] = off_mn(BM, p >> 5, m);
-            a_k[r] = p >> 5;
-            a_src[r] = A.rp.obs + m;
-            a_ones[r] = m == Dp;                              // the "ones" column: tile row Dp accumulates sum_k dh1[k][:] = db1
-            a_live[r] = m < m_valid;
-        }
-    }
+                for (int ks = 0; ks < 2; ++ks) {
+                    uint64_t a_hi, a_lo;
+                    if (pend_w2) {
+                        a_hi = make_desc(st + ks * 32, 16, 512, 4);
+                        a_lo = make_desc(st + Wg::A_BYTES + ks * 32, 16, 512, 4);
+                    } else {      // MN-major: 4 m-groups per k-group -> k-group stride 2048 B
+                        a_hi = make_desc(st + ks * 2 * 2048, 512, 2048, 1);
+                        a_lo = make_desc(st + Wg::A_BYTES + ks * 2 * 2048, 512, 2048, 1);
+                    }
+                    uint64_t b_hi, b_lo;
+                    if (pend_w2) {    // MN-major: 8 n-groups per k-group -> k-group stride 4096 B, a k-step is two k-groups
+                        b_hi = make_desc(st + 2 * Wg::A_BYTES + ks * 2 * 4096, 512, 4096, 1);
+                        b_lo = make_desc(st + 2 * Wg::A_BYTES + Wg::B_BYTES + ks * 2 * 4096, 512, 4096, 1);
+                    } else {
+                        b_hi = make_desc(st + 2 * Wg::A_BYTES + ks * 32, 16, 512, 4);
+                        b_lo = make_desc(st + 2 * Wg::A_BYTES + Wg::B_BYTES + ks * 32, 16, 512, 4);
+                    }
+                    uint32_t acc = (!pend_first || ks) ? 1u : 0u;
+                    if (PASSES == 3) {
+                        mma_ss(d_tmem, a_lo, b_hi, idesc, acc);
+                        mma_ss(d_tmem, a_hi, b_lo, idesc, 1u);
+                        acc = 1u;
+                    }
+                    mma_ss(d_tmem, a_hi, b_hi, idesc, acc);
+                }
+                umma_commit(bars + Wg::EMPTY + 8 * pend_stage);
+                if (pend_last) umma_commit(bars + Wg::ACC_FULL + 8 * acc_buf);
+            }
+            __syncwarp();
+        };
+        WG_TS_DECL;
+        for (int q = blockIdx.x; q < n_items; q += gridDim.x) {
+            int g, t;
+            wg_item(q, G, g, t);
+            if (!A.active[g]) continue;
+            WG_TS();
+            const size_t sb = (size_t)g * B;
+            const bool is_w2 = t < 2;
+            const int m0 = is_w2 ? t * BM : 0;
+            const int m_valid = is_w2 ? H : Dp;
+            const float* AsrcT = A.h1 + sb * H;                   // [H][B]
+            const float* DsrcT = A.dh1 + sb * H;                  // [H][B] (dW1 tile only)
+            const int32_t* rows = A.rows + sb;
+            uint32_t a_dst[2], b_dst[4];
+            const float* a_src[2];
+            const float* b_src[4];
+            int a_k[2], b_k[4];                                   // k offset of the piece inside its chunk
+            bool a_ones[2], a_live[2];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int p = tid + r * NT;
-        b_dst[r] = 2 * Wg::A_BYTES + off_k64(H, p >> 2, (p & 3) << 2);
-        b_k[r] = (p & 3) << 2;
-        b_src[r] = DsrcT + (size_t)(p >> 2) * B + b_k[r];
-    }
-    // dW2 tiles: thread = dh2 column n; dh2[k][n] = relu'(h2)[k][n] ? g_k * W3[n][a_k] : 0 is rebuilt per chunk from
-    // 16 rows of (g, action, one mask word per warp): warp-uniform, L1 / L2-resident loads instead of a B x H read
-    const float4 w3n = is_w2 ? __ldg(reinterpret_cast<const float4*>(A.w3_copy + (size_t)g * H * 4) + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const uint32_t* mrow = A.mask2 + ((size_t)g * (H / 32) + warp) * B;
-    const uint32_t b_dst_n = 2 * Wg::A_BYTES + off_k64(H, tid, 0);    // piece kp of row n: 16-byte slot index ^= kp
-    auto build_b = [&](int c, float4 (&out)[4]) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int k0 = c * KC + q * 4;
-            float x[4] = {0.f, 0.f, 0.f, 0.f};
-            if (k0 < B) {                                     // B % 4 == 0: a group of four rows is valid or not as a whole
-                const float4 g4 = __ldg(reinterpret_cast<const float4*>(A.gcoef + sb + k0));
-                const int4 a4 = __ldg(reinterpret_cast<const int4*>(A.act_b + sb + k0));
-                const uint4 m4 = __ldg(reinterpret_cast<const uint4*>(mrow + k0));
-                const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
-                const int aa[4] = {a4.x, a4.y, a4.z, a4.w};
-                const uint32_t mm[4] = {m4.x, m4.y, m4.z, m4.w};
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float w = aa[u] == 0 ? w3n.x : aa[u] == 1 ? w3n.y : aa[u] == 2 ? w3n.z : w3n.w;
-                    x[u] = ((mm[u] >> lane) & 1u) ? gg[u] * w : 0.f;
+            for (int r = 0; r < 2; ++r) {
+                const int p = tid + r * NT;
+                if (is_w2) {                                      // row m = p/4, 4 k-pieces per row (K-major SW64)
+                    a_dst[r] = off_k64(BM, p >> 2, (p & 3) << 2);
+                    a_k[r] = (p & 3) << 2;
+                    a_src[r] = AsrcT + (size_t)(m0 + (p >> 2)) * B + a_k[r];
+                    a_ones[r] = false; a_live[r] = true;
+                } else {                                          // k = p/32, 32 m-pieces per k-row (MN-major)
+                    const int m = (p & 31) << 2;
+                    a_dst[r] = off_mn(BM, p >> 5, m);
+                    a_k[r] = p >> 5;
+                    a_src[r] = A.rp.obs + m;
+                    a_ones[r] = m == Dp;                          // the "ones" column: tile row Dp accumulates sum_k dh1[k][:] = db1
+                    a_live[r] = m < m_valid;
                 }
             }
-            out[q] = make_float4(x[0], x[1], x[2], x[3]);
-        }
-    };
-    float4 ra[2][2], rb[2][4];
-    auto load = [&](int slot, int c) {
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int k = c * KC + a_k[r];
-            ra[slot][r] = z;
-            if (is_w2) {
-                if (k < B) ra[slot][r] = ldg_stream(a_src[r] + (size_t)c * KC);
-            } else if (a_ones[r]) {
-                ra[slot][r].x = k < B ? 1.f : 0.f;
-            } else if (a_live[r] && k < B) {
-                ra[slot][r] = ldg_stream(a_src[r] + (size_t)__ldg(rows + k) * Dp);
-            }
-        }
-        if (!is_w2) {
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                rb[slot][r] = z;
-                if (c * KC + b_k[r] < B) rb[slot][r] = ldg_stream(b_src[r] + (size_t)c * KC);
+                const int p = tid + r * NT;
+                b_dst[r] = 2 * Wg::A_BYTES + off_k64(H, p >> 2, (p & 3) << 2);
+                b_k[r] = (p & 3) << 2;
+                b_src[r] = DsrcT + (size_t)(p >> 2) * B + b_k[r];
             }
-        }
-    };
-    load(0, 0);
-    if (nchunks > 1) load(1, 1);
-    for (int c0 = 0; c0 < nchunks; c0 += 2) {
+            // dW2 tiles: dh2[k][n] = relu'(h2)[k][n] ? g_k * W3[n][a_k] : 0 is rebuilt per chunk, staged MN-major
+            // ([k][n], n contiguous): thread = (k-row u of the chunk, 16 columns n = 64 i + 4 ng + 0..3, i = 0..3), so
+            // one (g, action) pair and four mask words serve 16 values, W3^T comes from shared memory as four
+            // conflict-free 16-byte loads, and every store is a 16-byte piece of the UMMA layout.
+            const int bu = tid >> 4, ng = tid & 15;
+            const uint32_t w3t = sbase + Wg::W3T + (uint32_t)(n & 1) * (4 * H * 4);
+            if (is_w2) {
+                const float4 w3n = __ldg(reinterpret_cast<const float4*>(A.w3_copy + (size_t)g * H * 4) + tid);
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(w3t + (uint32_t)(0 * H + tid) * 4), "f"(w3n.x) : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(w3t + (uint32_t)(1 * H + tid) * 4), "f"(w3n.y) : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(w3t + (uint32_t)(2 * H + tid) * 4), "f"(w3n.z) : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(w3t + (uint32_t)(3 * H + tid) * 4), "f"(w3n.w) : "memory");
+            }
+            prod_sync();          // every item: a warp two items ahead would overwrite the W3^T buffer a slower warp still reads
+            const uint32_t* mrow = A.mask2 + ((size_t)g * (H / 32) + (ng >> 3)) * B;     // word 2 i + ng / 8 -> + 2 i B
+            const int mshift = (ng & 7) << 2;
+            const uint32_t b_dst_u = 2 * Wg::A_BYTES + off_mn(H, bu, ng << 2);          // + i * 1024: two 512-byte atoms per 64 columns
+            float4 ra[2][2], rb[2][4];
+            float gq[2] = {0.f, 0.f};
+            int aq[2] = {0, 0};
+            uint32_t mq[2][4] = {{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}};
+            auto load = [&](int slot, int c) {
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int c = c0 + j;
-            if (c < nchunks) {                                // uniform across the CTA
-                const uint32_t st = sbase + j * Wg::STG;
-                if (c >= 2 && ok) ok = mbar_wait(sbase + Wg::BARS + 8 * j, ((c >> 1) - 1) & 1);   // MMAs of chunk c - 2 are done
-                if (is_w2) build_b(c, rb[j]);                 // pieces kp = 0..3 of row n = tid
-#pragma unroll
-                for (int r = 0; r < 6; ++r) {
-                    float4 hi, lo;
-                    split4<PASSES>(r < 2 ? ra[j][r] : rb[j][r - 2], hi, lo);
-                    const uint32_t bo = is_w2 ? b_dst_n ^ (uint32_t)((r - 2) << 4) : b_dst[r < 2 ? 0 : r - 2];
-                    const uint32_t o = st + (r < 2 ? a_dst[r] : bo);
-                    sts4(o, hi);
-                    if (PASSES == 3) sts4(o + (r < 2 ? Wg::A_BYTES : Wg::B_BYTES), lo);
-                }
-                if (c + 2 < nchunks) load(j, c + 2);
-                fence_async_smem();
-                __syncthreads();
-                if (tid == 0) {
-                    tc_fence_after();
-                    const uint32_t idesc = make_idesc(!is_w2, false);
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {
-                        uint64_t a_hi, a_lo;
-                        if (is_w2) {
-                            a_hi = make_desc(st + ks * 32, 16, 512, 4);
-                            a_lo = make_desc(st + Wg::A_BYTES + ks * 32, 16, 512, 4);
-                        } else {      // MN-major: 4 m-groups per k-group -> k-group stride 2048 B
-                            a_hi = make_desc(st + ks * 2 * 2048, 512, 2048, 1);
-                            a_lo = make_desc(st + Wg::A_BYTES + ks * 2 * 2048, 512, 2048, 1);
-                        }
-                        const uint64_t b_hi = make_desc(st + 2 * Wg::A_BYTES + ks * 32, 16, 512, 4);
-                        const uint64_t b_lo = make_desc(st + 2 * Wg::A_BYTES + Wg::B_BYTES + ks * 32, 16, 512, 4);
-                        uint32_t acc = (c | ks) ? 1u : 0u;
-                        if (PASSES == 3) {
-                            mma_ss(tmem, a_lo, b_hi, idesc, acc);
-                            mma_ss(tmem, a_hi, b_lo, idesc, 1u);
-                            acc = 1u;
-                        }
-                        mma_ss(tmem, a_hi, b_hi, idesc, acc);
+                for (int r = 0; r < 2; ++r) {
+                    const int k = c * KC + a_k[r];
+                    ra[slot][r] = z;
+                    if (WG_EXP & 4) continue;
+                    if (is_w2) {
+                        if (k < B) ra[slot][r] = ldg_stream(a_src[r] + (size_t)c * KC);
+                    } else if (a_ones[r]) {
+                        ra[slot][r].x = k < B ? 1.f : 0.f;
+                    } else if (a_live[r] && k < B) {
+                        ra[slot][r] = ldg_stream(a_src[r] + (size_t)__ldg(rows + k) * Dp);
                     }
-                    umma_commit(sbase + Wg::BARS + 8 * j);
+                }
+                if (!is_w2) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        rb[slot][r] = z;
+                        if (!(WG_EXP & 4) && c * KC + b_k[r] < B) rb[slot][r] = ldg_stream(b_src[r] + (size_t)c * KC);
+                    }
+                } else {
+                    const int k = c * KC + bu;
+                    gq[slot] = 0.f; aq[slot] = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) mq[slot][i] = 0u;
+                    if (!(WG_EXP & 4) && k < B) {
+                        gq[slot] = A.gcoef[sb + k];
+                        aq[slot] = A.act_b[sb + k];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) mq[slot][i] = mrow[(size_t)(2 * i) * B + k];
+                    }
+                }
+            };
+            load(0, 0);
+            if (nchunks > 1) load(1, 1);
+            for (int c0 = 0; c0 < nchunks; c0 += 2) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int c = c0 + j;
+                    if (c < nchunks) {                            // uniform across the CTA
+                        const uint32_t st = sbase + stage * Wg::STG;
+                        if (used >= (uint32_t)Wg::STAGES && ok) ok = mbar_wait(bars + Wg::EMPTY + 8 * stage, ph ^ 1u);   // MMAs of the previous use are done
+                        if (is_w2) {
+                            if (!(WG_EXP & 8)) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    float4 w4;
+                                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w4.x), "=f"(w4.y), "=f"(w4.z), "=f"(w4.w)
+                                                 : "r"(w3t + (uint32_t)(aq[j] * H + 64 * i + (ng << 2)) * 4));
+                                    const uint32_t bits = mq[j][i] >> mshift;
+                                    const float gg = gq[j];
+                                    rb[j][i] = make_float4((bits & 1u) ? gg * w4.x : 0.f, (bits & 2u) ? gg * w4.y : 0.f,
+                                                           (bits & 4u) ? gg * w4.z : 0.f, (bits & 8u) ? gg * w4.w : 0.f);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int r = 0; r < 6; ++r) {
+                            float4 hi, lo;
+                            split4<PASSES>(r < 2 ? ra[j][r] : rb[j][r - 2], hi, lo);
+                            const uint32_t bo = is_w2 ? b_dst_u + (uint32_t)(r - 2) * 1024u : b_dst[r < 2 ? 0 : r - 2];
+                            const uint32_t o = st + (r < 2 ? a_dst[r] : bo);
+                            sts4(o, hi);
+                            if (PASSES == 3) sts4(o + (r < 2 ? Wg::A_BYTES : Wg::B_BYTES), lo);
+                        }
+                        if (c + 2 < nchunks) load(j, c + 2);
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bars + Wg::FULL + 8 * stage);
+                        if (warp == 0) {
+                            if (pend) issue_pending();
+                            pend = true; pend_w2 = is_w2; pend_first = c == 0; pend_last = c == nchunks - 1;
+                            pend_stage = stage; pend_ph = ph; pend_n = n;
+                        }
+                        ++used;
+                        if (++stage == (uint32_t)Wg::STAGES) { stage = 0; ph ^= 1u; }
+                    }
                 }
             }
+            ++n;
         }
-    }
-    {   // the last commit tracks every earlier MMA of the issuing thread
-        const int last = nchunks - 1;
-        ok &= mbar_wait(sbase + Wg::BARS + 8 * (last & 1), (last >> 1) & 1);
-        tc_fence_after();
-    }
-    __syncthreads();      // every thread has seen the GEMM finish: the stage memory becomes the transpose tiles
-    TS();
-
-    // epilogue: TMEM (lane = weight row) -> per-warp smem tile -> 8 lanes per 128-byte row segment, so the
-    // Adam read-modify-write of theta / m / v / theta_tgt is fully coalesced.
-    const Epi e;
-    float* tile = reinterpret_cast<float*>(__cvta_shared_to_generic((size_t)sbase)) + warp * (32 * Wg::TLD);
-    const int64_t wbase = is_w2 ? A.L.w2 : A.L.w1;
-    const int rsub = lane >> 3, c4 = (lane & 7) << 2;
-#pragma unroll 1
-    for (int cc = 0; cc < 4; ++cc) {
-        const int c0 = e.half * 128 + cc * 32;
-        float v[32];
-        tmem_ld32(tmem + e.lane_addr + (uint32_t)c0, v);
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(tile + lane * Wg::TLD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        __syncwarp();
-        // two batches of four row groups: every load of a batch is issued before its first use, so twelve
-        // (sixteen with Polyak) 16-byte loads per thread are in flight while the HBM latency elapses
-#pragma unroll 1
-        for (int it0 = 0; it0 < 8; it0 += 4) {
-            int64_t off[4];
-            bool live[4];
-            float4 gr4[4], t4[4], m4[4], v4[4], g4[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int r = (it0 + u) * 4 + rsub;
-                const int m = m0 + (warp & 3) * 32 + r;
-                const bool bias_row = !is_w2 && m == Dp;           // db1 from the ones column
-                live[u] = m < m_valid || bias_row;
-                off[u] = bias_row ? A.L.b1 + c0 + c4 : wbase + (int64_t)m * H + c0 + c4;
-                gr4[u] = *reinterpret_cast<const float4*>(tile + r * Wg::TLD + c4);
-                g4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (live[u] && !A.grads) {
-                    t4[u] = ldg_plain(th + off[u]);
-                    m4[u] = ldg_plain(am + off[u]);
-                    v4[u] = ldg_plain(av + off[u]);
-                    if (k.sync == 2) g4[u] = ldg_plain(tg + off[u]);
+        if (warp == 0 && pend) issue_pending();
+        WG_TS();
+        WG_TS_PRINT("K4b producer", tid == 0);
+        if (!ok && tid == 0) atomicExch(A.error, 5);
+    } else {
+        // ------------------------------------------------------------------ epilogue -------------------
+        const int et = tid - NT, ew = warp - 8;                   // 0..255 / 0..7
+        const int ehalf = ew >> 2;                                // TMEM lane = weight row (ew & 3) * 32 + lane of the tile; column half
+        const uint32_t lane_addr = (uint32_t)((ew & 3) * 32) << 16;
+        float* tile = reinterpret_cast<float*>(__cvta_shared_to_generic((size_t)(sbase + Wg::TILES))) + ew * (32 * Wg::TLD);
+        const int rsub = lane >> 3, c4 = (lane & 7) << 2;
+        int n = 0;
+        WG_TS_DECL;
+        for (int q = blockIdx.x; q < n_items; q += gridDim.x) {
+            int g, t;
+            wg_item(q, G, g, t);
+            if (!A.active[g]) {
+                if (t == 2 && et < DMDQN_METRICS_STRIDE && A.metrics) A.metrics[g * DMDQN_METRICS_STRIDE + et] = 0.f;
+                continue;
+            }
+            const size_t pb = (size_t)g * A.L.stride;
+            float* th = A.nets.theta + pb;
+            float* tg = A.nets.theta_tgt + pb;
+            float* am = A.nets.adam_m + pb;
+            float* av = A.nets.adam_v + pb;
+            const AdamK k = adam_k(A, g);
+            const bool is_w2 = t < 2;
+            const int m0 = is_w2 ? t * BM : 0;
+            const int m_valid = is_w2 ? H : Dp;
+            if (t == 2) {
+                // head / bias gradients: per-row-tile partials from K4a summed in tile order, then Adam
+                auto upd = [&](int64_t off, float grad) {
+                    if (A.grads) { A.grads[pb + off] = grad; return; }
+                    float tgv = k.sync == 2 ? tg[off] : 0.f;
+                    adam1(k, grad, th[off], am[off], av[off], tgv);
+                    if (k.sync) tg[off] = tgv;
+                };
+                const size_t p0 = (size_t)g * A.tiles;
+                float s2 = 0.f, w[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int r = 0; r < A.tiles; ++r) {
+                    s2 += A.part_b2[(p0 + r) * H + et];
+                    const float4 pw = reinterpret_cast<const float4*>(A.part_w3 + (p0 + r) * H * 4)[et];
+                    w[0] += pw.x; w[1] += pw.y; w[2] += pw.z; w[3] += pw.w;
+                }
+                upd(A.L.b2 + et, s2);
+                for (int a = 0; a < 4; ++a) upd(A.L.w3 + (int64_t)et * 4 + a, w[a]);
+                if (et < 4) {
+                    float s3 = 0.f;
+                    for (int r = 0; r < A.tiles; ++r) s3 += A.part_b3[(p0 + r) * 4 + et];
+                    upd(A.L.b3 + et, s3);
+                }
+                if (et == 0 && A.metrics) {
+                    double ls = 0, qs = 0, qq = 0, hist[4] = {0, 0, 0, 0};
+                    for (int r = 0; r < A.tiles; ++r) {
+                        const float* pl = A.part_loss + (p0 + r) * 8;
+                        ls += pl[0]; qs += pl[1]; qq += pl[2];
+                        for (int a = 0; a < 4; ++a) hist[a] += pl[3 + a];
+                    }
+                    const double cnt = (double)B * A.d.n_actions, mean = qs / cnt, var = fmax(qq / cnt - mean * mean, 0.0);
+                    float* m = A.metrics + g * DMDQN_METRICS_STRIDE;
+                    m[0] = (float)(ls / A.loss_batch); m[1] = (float)mean; m[2] = (float)sqrt(var);
+                    for (int a = 0; a < 4; ++a) m[3 + a] = (float)hist[a];
+                    m[7] = 1.f;
                 }
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (!live[u]) continue;
-                if (A.grads) {
-                    *reinterpret_cast<float4*>(A.grads + pb + off[u]) = gr4[u];
-                    continue;
+            const uint32_t acc_buf = (uint32_t)(n & 1);
+            WG_TS();
+            if (ok) ok = mbar_wait(bars + Wg::ACC_FULL + 8 * acc_buf, (uint32_t)(n >> 1) & 1u);
+            tc_fence_after();
+            WG_TS();
+            // TMEM (lane = weight row) -> per-warp smem tile -> 8 lanes per 128-byte row segment, so the
+            // Adam read-modify-write of theta / m / v / theta_tgt is fully coalesced.
+            const int64_t wbase = is_w2 ? A.L.w2 : A.L.w1;
+#pragma unroll 1
+            for (int cc = 0; cc < 4; ++cc) {
+                const int c0 = ehalf * 128 + cc * 32;
+                float v[32];
+                tmem_ld32(tmem + acc_buf * 256u + lane_addr + (uint32_t)c0, v);
+                if (cc == 3) {                                    // this warp has read its whole part of the accumulator
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bars + Wg::ACC_FREE + 8 * acc_buf);
                 }
-                adam1(k, gr4[u].x, t4[u].x, m4[u].x, v4[u].x, g4[u].x); adam1(k, gr4[u].y, t4[u].y, m4[u].y, v4[u].y, g4[u].y);
-                adam1(k, gr4[u].z, t4[u].z, m4[u].z, v4[u].z, g4[u].z); adam1(k, gr4[u].w, t4[u].w, m4[u].w, v4[u].w, g4[u].w);
-                *reinterpret_cast<float4*>(th + off[u]) = t4[u];
-                *reinterpret_cast<float4*>(am + off[u]) = m4[u];
-                *reinterpret_cast<float4*>(av + off[u]) = v4[u];
-                if (k.sync) *reinterpret_cast<float4*>(tg + off[u]) = g4[u];
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(tile + lane * Wg::TLD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                __syncwarp();
+                // two batches of four row groups: every load of a batch is issued before its first use, so twelve
+                // (sixteen with Polyak) 16-byte loads per thread are in flight while the HBM latency elapses
+#pragma unroll 1
+                for (int it0 = 0; it0 < 8; it0 += 4) {
+                    int64_t off[4];
+                    bool live[4];
+                    float4 gr4[4], t4[4], m4[4], v4[4], g4[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = (it0 + u) * 4 + rsub;
+                        const int m = m0 + (ew & 3) * 32 + r;
+                        const bool bias_row = !is_w2 && m == Dp;           // db1 from the ones column
+                        live[u] = m < m_valid || bias_row;
+                        off[u] = bias_row ? A.L.b1 + c0 + c4 : wbase + (int64_t)m * H + c0 + c4;
+                        gr4[u] = *reinterpret_cast<const float4*>(tile + r * Wg::TLD + c4);
+                        g4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+#if WG_EXP & 2
+                        t4[u] = gr4[u]; m4[u] = gr4[u]; v4[u] = gr4[u];
+                        live[u] = live[u] && (gr4[u].x == 123.456f);
+#else
+                        if (live[u] && !A.grads) {
+                            t4[u] = ldg_plain(th + off[u]);
+                            m4[u] = ldg_plain(am + off[u]);
+                            v4[u] = ldg_plain(av + off[u]);
+                            if (k.sync == 2) g4[u] = ldg_plain(tg + off[u]);
+                        }
+#endif
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (!live[u]) continue;
+                        if (A.grads) {
+                            *reinterpret_cast<float4*>(A.grads + pb + off[u]) = gr4[u];
+                            continue;
+                        }
+                        adam1(k, gr4[u].x, t4[u].x, m4[u].x, v4[u].x, g4[u].x); adam1(k, gr4[u].y, t4[u].y, m4[u].y, v4[u].y, g4[u].y);
+                        adam1(k, gr4[u].z, t4[u].z, m4[u].z, v4[u].z, g4[u].z); adam1(k, gr4[u].w, t4[u].w, m4[u].w, v4[u].w, g4[u].w);
+                        *reinterpret_cast<float4*>(th + off[u]) = t4[u];
+                        *reinterpret_cast<float4*>(am + off[u]) = m4[u];
+                        *reinterpret_cast<float4*>(av + off[u]) = v4[u];
+                        if (k.sync) *reinterpret_cast<float4*>(tg + off[u]) = g4[u];
+                    }
+                }
+                __syncwarp();                                     // the tile is rewritten by the next column block
             }
+            ++n;
         }
+        WG_TS();
+        WG_TS_PRINT("K4b epilogue (wait, adam)*", et == 0);
+        if (!ok && lane == 0) atomicExch(A.error, 6);
     }
-    TS();
-    TS_PRINT("K4b gemm adam");
-    if (!ok && tid == 0) atomicExch(A.error, 5);
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
 template <int PASSES>
@@ -1186,7 +1325,14 @@ int launch_tc(const TcArgs& A, int stages, cudaStream_t s) {
         DMDQN_CUDA(cudaGetLastError());
     }
     if (stages & DMDQN_STAGE_WGRAD) {
-        tc_wgrad_kernel<PASSES><<<A.d.n_nets * 3, NT, smem_w, s>>>(A);
+        static int n_sm = 0;
+        if (!n_sm) {
+            int dev = 0;
+            DMDQN_CUDA(cudaGetDevice(&dev));
+            DMDQN_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        }
+        const int items = A.d.n_nets * 3;
+        tc_wgrad_kernel<PASSES><<<items < n_sm ? items : n_sm, Wg::NTW, smem_w, s>>>(A);
         DMDQN_CUDA(cudaGetLastError());
     }
     return DMDQN_OK;

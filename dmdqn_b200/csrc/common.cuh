@@ -62,7 +62,8 @@ struct Workspace {
     size_t rows, r_hat, act_b, done_b, active, step_t, y, gcoef, q_all, q_next, tq_all;
     size_t h1, dh1, dh2;              // [n_nets][B][H] floats each ([H][B] per network on the tcgen05 path)
     size_t tc_error;                  // int: set by a tcgen05 kernel whose mbarrier wait timed out
-    size_t mask2;                     // tcgen05 path: relu'(h2) bits, uint32 [n_nets][H/32][B]
+    size_t mask2;                     // tcgen05 path: relu'(h2) bits, uint32 [n_nets][B][H/32]
+    size_t ga;                        // tcgen05 path: float2 [n_nets][B] {dL/dq of the taken action, action bits}
     size_t w3_copy;                   // tcgen05 path: W3 as K4a saw it, [n_nets][H][4] (K4b rebuilds dh2 while W3 is being updated)
     size_t adam_sc;                   // [n_nets] float4 {alpha_t, eps_eff, sync mode bits, -}: written by the sample kernel
     size_t part_loss;                 // [n_nets][T][8]
@@ -95,6 +96,7 @@ inline Workspace make_workspace(const dmdqn_dims& d) {
     w.tc_error = take(4);
     w.adam_sc = take((size_t)d.n_nets * 16);
     w.mask2 = take(nb * (size_t)(d.hidden / 32) * 4);
+    w.ga = take(nb * 8);
     w.w3_copy = take((size_t)d.n_nets * d.hidden * 16);
     w.dh1 = take(nb * d.hidden * 4);
     w.dh2 = take(nb * d.hidden * 4);

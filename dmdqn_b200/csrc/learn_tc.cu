@@ -152,7 +152,8 @@ struct TcArgs {
     const int32_t *rows, *act_b, *active, *step_t;
     const float *r_hat, *done_b;
     const float4* adam_sc;
-    uint32_t* mask2;              // relu'(h2) bits [n_nets][H/32][B]
+    uint32_t* mask2;              // relu'(h2) bits [n_nets][B][H/32]: the eight words of a batch row are adjacent
+    float2* ga;                   // [n_nets][B] {dL/dq of the taken action, action as int bits}: what K4b needs per row
     float* w3_copy;               // [n_nets][H][4]
     float *y, *gcoef, *q_all, *q_next, *tq_all, *h1, *dh1, *dh2, *part_loss, *part_b3, *part_w3, *part_b2, *metrics, *grads;
     int* error;
@@ -741,6 +742,7 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A) {
         }
         if (e.half == 0) {
             A.gcoef[sb + gr] = gi;
+            A.ga[sb + gr] = make_float2(gi, __int_as_float(ai));
             for (int k = 0; k < 4; ++k) A.q_all[(sb + gr) * 4 + k] = q[k];
         }
     }
@@ -809,8 +811,7 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A) {
     // dh2[j] = relu'(h2[j]) * g * W3[j][a]  (dq has one non-zero per row): hi -> R, lo -> TMEM.  It is not
     // written to global memory: K4b rebuilds its dh2^T operand from relu'(h2) bits, g, the action and W3.
     if (valid) {
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) A.mask2[((size_t)g * (H / 32) + e.half * 4 + cc) * B + gr] = mask2[cc];
+        reinterpret_cast<uint4*>(A.mask2)[(sb + gr) * 2 + e.half] = make_uint4(mask2[0], mask2[1], mask2[2], mask2[3]);
     }
     if (rt == 0)    // W3 as this step saw it (K4b updates W3 while other CTAs of the network still need the old values)
         reinterpret_cast<float4*>(A.w3_copy + (size_t)g * H * 4)[threadIdx.x] =
@@ -893,6 +894,18 @@ __device__ __forceinline__ void adam1(const AdamK& k, float g, float& th, float&
     th = th - __fdividef(m * k.alpha, sq + k.eps);
     if (k.sync == 1) tg = th;
     else if (k.sync == 2) tg = k.tau * th + (1.0f - k.tau) * tg;
+}
+
+// Adam on one element without the target sync (the caller applies it per 16-byte group)
+__device__ __forceinline__ void adam_fast(const AdamK& k, float g, float& th, float& m, float& v) {
+#if WG_EXP & 1
+    th -= g; m += g; v += g; return;
+#endif
+    m = m + (g - m) * k.omb1;
+    v = v + (g * g - v) * k.omb2;
+    float sq;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(v));
+    th = th - __fdividef(m * k.alpha, sq + k.eps);
 }
 
 struct Wg {     // persistent wgrad kernel, one CTA per SM
@@ -1004,6 +1017,7 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A) {
                         b_lo = make_desc(st + 2 * Wg::A_BYTES + Wg::B_BYTES + ks * 32, 16, 512, 4);
                     }
                     uint32_t acc = (!pend_first || ks) ? 1u : 0u;
+                    if (WG_EXP & 32) continue;
                     if (PASSES == 3) {
                         mma_ss(d_tmem, a_lo, b_hi, idesc, acc);
                         mma_ss(d_tmem, a_hi, b_lo, idesc, 1u);
@@ -1016,6 +1030,31 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A) {
             }
             __syncwarp();
         };
+        // Called by every producer thread before / after it writes its pieces of a chunk into stage `stage`.
+        auto stage_begin = [&]() -> uint32_t {
+            if (used >= (uint32_t)Wg::STAGES && ok) ok = mbar_wait(bars + Wg::EMPTY + 8 * stage, ph ^ 1u);   // MMAs of the previous use are done
+            return sbase + stage * Wg::STG;
+        };
+        auto stage_end = [&](bool is_w2, int c) {
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + Wg::FULL + 8 * stage);
+            if (warp == 0) {
+                if (pend) issue_pending();
+                pend = true; pend_w2 = is_w2; pend_first = c == 0; pend_last = c == nchunks - 1;
+                pend_stage = stage; pend_ph = ph; pend_n = n;
+            }
+            ++used;
+            if (++stage == (uint32_t)Wg::STAGES) { stage = 0; ph ^= 1u; }
+        };
+        auto put = [&](uint32_t o, uint32_t lo_off, const float4& x) {
+            if (WG_EXP & 64) { asm volatile("" ::"f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w)); return; }
+            float4 hi, lo;
+            split4<PASSES>(x, hi, lo);
+            sts4(o, hi);
+            if (PASSES == 3) sts4(o + lo_off, lo);
+        };
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         WG_TS_DECL;
         for (int q = blockIdx.x; q < n_items; q += gridDim.x) {
             int g, t;
@@ -1023,139 +1062,122 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A) {
             if (!A.active[g]) continue;
             WG_TS();
             const size_t sb = (size_t)g * B;
-            const bool is_w2 = t < 2;
-            const int m0 = is_w2 ? t * BM : 0;
-            const int m_valid = is_w2 ? H : Dp;
-            const float* AsrcT = A.h1 + sb * H;                   // [H][B]
-            const float* DsrcT = A.dh1 + sb * H;                  // [H][B] (dW1 tile only)
-            const int32_t* rows = A.rows + sb;
-            uint32_t a_dst[2], b_dst[4];
-            const float* a_src[2];
-            const float* b_src[4];
-            int a_k[2], b_k[4];                                   // k offset of the piece inside its chunk
-            bool a_ones[2], a_live[2];
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int p = tid + r * NT;
-                if (is_w2) {                                      // row m = p/4, 4 k-pieces per row (K-major SW64)
-                    a_dst[r] = off_k64(BM, p >> 2, (p & 3) << 2);
-                    a_k[r] = (p & 3) << 2;
-                    a_src[r] = AsrcT + (size_t)(m0 + (p >> 2)) * B + a_k[r];
-                    a_ones[r] = false; a_live[r] = true;
-                } else {                                          // k = p/32, 32 m-pieces per k-row (MN-major)
-                    const int m = (p & 31) << 2;
-                    a_dst[r] = off_mn(BM, p >> 5, m);
-                    a_k[r] = p >> 5;
-                    a_src[r] = A.rp.obs + m;
-                    a_ones[r] = m == Dp;                          // the "ones" column: tile row Dp accumulates sum_k dh1[k][:] = db1
-                    a_live[r] = m < m_valid;
+            if (t < 2) {
+                // ---- dW2 rows t*128..: A = h1^T scratch [m][k] (K-major SW64), register prefetch DW2 chunks ahead;
+                // B = dh2 rebuilt, staged MN-major ([k][n], n contiguous): dh2[k][n] = relu'(h2)[k][n] ? g_k * W3[n][a_k] : 0,
+                // thread = (k-row bu of the chunk, 16 columns n = 64 i + 4 ng + 0..3, i = 0..3), so one (g, action) pair
+                // and four mask words serve 16 values, W3^T comes from shared memory as four conflict-free 16-byte
+                // loads, and every store is a 16-byte piece of the UMMA layout.
+                constexpr int DW2 = 2;
+                const int bu = tid >> 4, ng = tid & 15, hh = ng >> 3, l7 = ng & 7;
+                const uint32_t w3t = sbase + Wg::W3T + (uint32_t)(n & 1) * (4 * H * 4);
+                {
+                    const float4 w3n = __ldg(reinterpret_cast<const float4*>(A.w3_copy + (size_t)g * H * 4) + tid);
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(w3t + (uint32_t)(0 * H + tid) * 4), "f"(w3n.x) : "memory");
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(w3t + (uint32_t)(1 * H + tid) * 4), "f"(w3n.y) : "memory");
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(w3t + (uint32_t)(2 * H + tid) * 4), "f"(w3n.z) : "memory");
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(w3t + (uint32_t)(3 * H + tid) * 4), "f"(w3n.w) : "memory");
                 }
-            }
+                prod_sync();      // every item: a warp two items ahead would overwrite the buffer a slower warp still reads
+                // A: pieces p = tid, tid + 256: row m = p/4, k piece p%4.  B: piece i of the thread = columns 32 (4 hh + i) + 4 l7 + 0..3,
+                // i.e. mask words 4 hh .. 4 hh + 3 of its batch row (one 16-byte load), W3^T at + 128 i bytes, stage atom + i.
+                const float* pa = A.h1 + sb * H + (size_t)(t * BM + (tid >> 2)) * B + ((tid & 3) << 2);
+                const size_t a_half = (size_t)64 * B;
+                const uint32_t a_dst = off_k64(BM, tid >> 2, (tid & 3) << 2);       // second piece: + 64 rows = + 4096 B
+                const float2* pga = A.ga + sb + bu;
+                const uint4* pmk = reinterpret_cast<const uint4*>(A.mask2) + (sb + bu) * 2 + hh;
+                const int mshift = l7 << 2, ka0 = (tid & 3) << 2;
+                const uint32_t w3t_thr = w3t + (uint32_t)(128 * hh + 4 * l7) * 4;
+                const uint32_t b_dst = 2 * Wg::A_BYTES + off_mn(H, bu, 128 * hh + 4 * l7);   // piece i: + i atoms of 512 B
+                float4 ra[DW2][2];
+                float2 gq[DW2];
+                uint4 mq[DW2];
+                auto load = [&](int slot, int c) {
+                    ra[slot][0] = z4; ra[slot][1] = z4;
+                    gq[slot] = make_float2(0.f, 0.f);
+                    mq[slot] = make_uint4(0u, 0u, 0u, 0u);
+                    if (WG_EXP & 4) return;
+                    if (c * KC + ka0 < B) {
+                        ra[slot][0] = ldg_stream(pa + c * KC);
+                        ra[slot][1] = ldg_stream(pa + c * KC + a_half);
+                    }
+                    if (c * KC + bu < B) {
+                        gq[slot] = __ldg(pga + c * KC);
+                        mq[slot] = __ldg(pmk + c * (KC * 2));
+                    }
+                };
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int p = tid + r * NT;
-                b_dst[r] = 2 * Wg::A_BYTES + off_k64(H, p >> 2, (p & 3) << 2);
-                b_k[r] = (p & 3) << 2;
-                b_src[r] = DsrcT + (size_t)(p >> 2) * B + b_k[r];
-            }
-            // dW2 tiles: dh2[k][n] = relu'(h2)[k][n] ? g_k * W3[n][a_k] : 0 is rebuilt per chunk, staged MN-major
-            // ([k][n], n contiguous): thread = (k-row u of the chunk, 16 columns n = 64 i + 4 ng + 0..3, i = 0..3), so
-            // one (g, action) pair and four mask words serve 16 values, W3^T comes from shared memory as four
-            // conflict-free 16-byte loads, and every store is a 16-byte piece of the UMMA layout.
-            const int bu = tid >> 4, ng = tid & 15;
-            const uint32_t w3t = sbase + Wg::W3T + (uint32_t)(n & 1) * (4 * H * 4);
-            if (is_w2) {
-                const float4 w3n = __ldg(reinterpret_cast<const float4*>(A.w3_copy + (size_t)g * H * 4) + tid);
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(w3t + (uint32_t)(0 * H + tid) * 4), "f"(w3n.x) : "memory");
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(w3t + (uint32_t)(1 * H + tid) * 4), "f"(w3n.y) : "memory");
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(w3t + (uint32_t)(2 * H + tid) * 4), "f"(w3n.z) : "memory");
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(w3t + (uint32_t)(3 * H + tid) * 4), "f"(w3n.w) : "memory");
-            }
-            prod_sync();          // every item: a warp two items ahead would overwrite the W3^T buffer a slower warp still reads
-            const uint32_t* mrow = A.mask2 + ((size_t)g * (H / 32) + (ng >> 3)) * B;     // word 2 i + ng / 8 -> + 2 i B
-            const int mshift = (ng & 7) << 2;
-            const uint32_t b_dst_u = 2 * Wg::A_BYTES + off_mn(H, bu, ng << 2);          // + i * 1024: two 512-byte atoms per 64 columns
-            float4 ra[2][2], rb[2][4];
-            float gq[2] = {0.f, 0.f};
-            int aq[2] = {0, 0};
-            uint32_t mq[2][4] = {{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}};
-            auto load = [&](int slot, int c) {
-                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int j = 0; j < DW2; ++j)
+                    if (j < nchunks) load(j, j);
+                for (int c0 = 0; c0 < nchunks; c0 += DW2) {
 #pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const int k = c * KC + a_k[r];
-                    ra[slot][r] = z;
-                    if (WG_EXP & 4) continue;
-                    if (is_w2) {
-                        if (k < B) ra[slot][r] = ldg_stream(a_src[r] + (size_t)c * KC);
-                    } else if (a_ones[r]) {
-                        ra[slot][r].x = k < B ? 1.f : 0.f;
-                    } else if (a_live[r] && k < B) {
-                        ra[slot][r] = ldg_stream(a_src[r] + (size_t)__ldg(rows + k) * Dp);
+                    for (int j = 0; j < DW2; ++j) {
+                        const int c = c0 + j;
+                        if (c < nchunks) {                        // uniform across the CTA
+                            const uint32_t st = stage_begin();
+                            put(st + a_dst, Wg::A_BYTES, ra[j][0]);
+                            put(st + a_dst + 4096u, Wg::A_BYTES, ra[j][1]);
+                            const uint32_t wa = w3t_thr + (uint32_t)__float_as_int(gq[j].y) * (H * 4);
+                            const float gg = gq[j].x;
+                            const uint32_t mw[4] = {mq[j].x, mq[j].y, mq[j].z, mq[j].w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                float4 w4;
+                                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w4.x), "=f"(w4.y), "=f"(w4.z), "=f"(w4.w)
+                                             : "r"(wa + (uint32_t)i * 128u));
+                                const uint32_t bits = mw[i] >> mshift;
+                                const float4 x = make_float4((bits & 1u) ? gg * w4.x : 0.f, (bits & 2u) ? gg * w4.y : 0.f,
+                                                             (bits & 4u) ? gg * w4.z : 0.f, (bits & 8u) ? gg * w4.w : 0.f);
+                                put(st + b_dst + (uint32_t)i * 512u, Wg::B_BYTES, x);
+                            }
+                            if (c + DW2 < nchunks) load(j, c + DW2);
+                            stage_end(true, c);
+                        }
                     }
                 }
-                if (!is_w2) {
+            } else {
+                // ---- dW1 (+ db1): A = s rows gathered from the ring [k][m] (MN-major; column m = Dp is the ones column),
+                // B = dh1^T scratch [n][k] (K-major SW64); register prefetch DW1 chunks ahead.  The sampled row ids
+                // of the item are read once (one per thread and pass) instead of once per gathered piece.
+                constexpr int DW1 = 2;
+                const float* b_src = A.dh1 + sb * H + (size_t)(tid >> 2) * B + ((tid & 3) << 2);   // pieces p = tid + 256 r: row n = p/4 = tid/4 + 64 r
+                const uint32_t b_dst = 2 * Wg::A_BYTES + off_k64(H, tid >> 2, (tid & 3) << 2);  // + r * 64 rows * 64 B
+                const int am = (tid & 31) << 2, ak = tid >> 5;                   // pieces p = tid, tid + 256: k = p/32 = ak, ak + 8
+                const bool a_live = am < Dp, a_ones = am == Dp;
+                const uint32_t a_dst = off_mn(BM, ak, am);                       // k + 8: two k-groups further = + 2 * 2048 B
+                const int32_t* rows = A.rows + sb;
+                float4 ra[DW1][2], rb[DW1][4];
+                auto load = [&](int slot, int c) {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const int k = c * KC + ak + 8 * r;
+                        ra[slot][r] = z4;
+                        if (WG_EXP & 4) continue;
+                        if (a_ones) ra[slot][r].x = k < B ? 1.f : 0.f;
+                        else if (a_live && k < B) ra[slot][r] = ldg_stream(A.rp.obs + (size_t)__ldg(rows + k) * Dp + am);
+                    }
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        rb[slot][r] = z;
-                        if (!(WG_EXP & 4) && c * KC + b_k[r] < B) rb[slot][r] = ldg_stream(b_src[r] + (size_t)c * KC);
+                        rb[slot][r] = z4;
+                        if (!(WG_EXP & 4) && c * KC + ((tid & 3) << 2) < B) rb[slot][r] = ldg_stream(b_src + (size_t)c * KC + (size_t)(64 * r) * B);
                     }
-                } else {
-                    const int k = c * KC + bu;
-                    gq[slot] = 0.f; aq[slot] = 0;
+                };
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) mq[slot][i] = 0u;
-                    if (!(WG_EXP & 4) && k < B) {
-                        gq[slot] = A.gcoef[sb + k];
-                        aq[slot] = A.act_b[sb + k];
+                for (int j = 0; j < DW1; ++j)
+                    if (j < nchunks) load(j, j);
+                for (int c0 = 0; c0 < nchunks; c0 += DW1) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) mq[slot][i] = mrow[(size_t)(2 * i) * B + k];
-                    }
-                }
-            };
-            load(0, 0);
-            if (nchunks > 1) load(1, 1);
-            for (int c0 = 0; c0 < nchunks; c0 += 2) {
+                    for (int j = 0; j < DW1; ++j) {
+                        const int c = c0 + j;
+                        if (c < nchunks) {
+                            const uint32_t st = stage_begin();
+                            put(st + a_dst, Wg::A_BYTES, ra[j][0]);
+                            put(st + a_dst + 4096u, Wg::A_BYTES, ra[j][1]);
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int c = c0 + j;
-                    if (c < nchunks) {                            // uniform across the CTA
-                        const uint32_t st = sbase + stage * Wg::STG;
-                        if (used >= (uint32_t)Wg::STAGES && ok) ok = mbar_wait(bars + Wg::EMPTY + 8 * stage, ph ^ 1u);   // MMAs of the previous use are done
-                        if (is_w2) {
-                            if (!(WG_EXP & 8)) {
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    float4 w4;
-                                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w4.x), "=f"(w4.y), "=f"(w4.z), "=f"(w4.w)
-                                                 : "r"(w3t + (uint32_t)(aq[j] * H + 64 * i + (ng << 2)) * 4));
-                                    const uint32_t bits = mq[j][i] >> mshift;
-                                    const float gg = gq[j];
-                                    rb[j][i] = make_float4((bits & 1u) ? gg * w4.x : 0.f, (bits & 2u) ? gg * w4.y : 0.f,
-                                                           (bits & 4u) ? gg * w4.z : 0.f, (bits & 8u) ? gg * w4.w : 0.f);
-                                }
-                            }
+                            for (int r = 0; r < 4; ++r) put(st + b_dst + (uint32_t)r * 4096u, Wg::B_BYTES, rb[j][r]);
+                            if (c + DW1 < nchunks) load(j, c + DW1);
+                            stage_end(false, c);
                         }
-#pragma unroll
-                        for (int r = 0; r < 6; ++r) {
-                            float4 hi, lo;
-                            split4<PASSES>(r < 2 ? ra[j][r] : rb[j][r - 2], hi, lo);
-                            const uint32_t bo = is_w2 ? b_dst_u + (uint32_t)(r - 2) * 1024u : b_dst[r < 2 ? 0 : r - 2];
-                            const uint32_t o = st + (r < 2 ? a_dst[r] : bo);
-                            sts4(o, hi);
-                            if (PASSES == 3) sts4(o + (r < 2 ? Wg::A_BYTES : Wg::B_BYTES), lo);
-                        }
-                        if (c + 2 < nchunks) load(j, c + 2);
-                        fence_async_smem();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bars + Wg::FULL + 8 * stage);
-                        if (warp == 0) {
-                            if (pend) issue_pending();
-                            pend = true; pend_w2 = is_w2; pend_first = c == 0; pend_last = c == nchunks - 1;
-                            pend_stage = stage; pend_ph = ph; pend_n = n;
-                        }
-                        ++used;
-                        if (++stage == (uint32_t)Wg::STAGES) { stage = 0; ph ^= 1u; }
                     }
                 }
             }
@@ -1189,7 +1211,6 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A) {
             const AdamK k = adam_k(A, g);
             const bool is_w2 = t < 2;
             const int m0 = is_w2 ? t * BM : 0;
-            const int m_valid = is_w2 ? H : Dp;
             if (t == 2) {
                 // head / bias gradients: per-row-tile partials from K4a summed in tile order, then Adam
                 auto upd = [&](int64_t off, float grad) {
@@ -1232,8 +1253,11 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A) {
             tc_fence_after();
             WG_TS();
             // TMEM (lane = weight row) -> per-warp smem tile -> 8 lanes per 128-byte row segment, so the
-            // Adam read-modify-write of theta / m / v / theta_tgt is fully coalesced.
-            const int64_t wbase = is_w2 ? A.L.w2 : A.L.w1;
+            // Adam read-modify-write of theta / m / v / theta_tgt is fully coalesced.  Offsets are 32-bit float
+            // indices into the network's parameter block; all mode decisions are made per item, not per element.
+            const int wbase = (int)(is_w2 ? A.L.w2 : A.L.w1) + (m0 + (ew & 3) * 32 + rsub) * H + c4;   // + 4 u' H + c0
+            const int mrow0 = m0 + (ew & 3) * 32 + rsub;                                              // tile row of u' = 0
+            const int sync = k.sync;
 #pragma unroll 1
             for (int cc = 0; cc < 4; ++cc) {
                 const int c0 = ehalf * 128 + cc * 32;
@@ -1249,47 +1273,53 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A) {
                 for (int j = 0; j < 32; j += 4)
                     *reinterpret_cast<float4*>(tile + lane * Wg::TLD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 __syncwarp();
-                // two batches of four row groups: every load of a batch is issued before its first use, so twelve
-                // (sixteen with Polyak) 16-byte loads per thread are in flight while the HBM latency elapses
-#pragma unroll 1
-                for (int it0 = 0; it0 < 8; it0 += 4) {
-                    int64_t off[4];
-                    bool live[4];
-                    float4 gr4[4], t4[4], m4[4], v4[4], g4[4];
+                const float* trow = tile + rsub * Wg::TLD + c4;   // row 4 u' + rsub of the tile
+                if (A.grads) {                                    // shared-parameter mode: raw gradients out, no update
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int r = (it0 + u) * 4 + rsub;
-                        const int m = m0 + (ew & 3) * 32 + r;
-                        const bool bias_row = !is_w2 && m == Dp;           // db1 from the ones column
-                        live[u] = m < m_valid || bias_row;
-                        off[u] = bias_row ? A.L.b1 + c0 + c4 : wbase + (int64_t)m * H + c0 + c4;
-                        gr4[u] = *reinterpret_cast<const float4*>(tile + r * Wg::TLD + c4);
-                        g4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-#if WG_EXP & 2
-                        t4[u] = gr4[u]; m4[u] = gr4[u]; v4[u] = gr4[u];
-                        live[u] = live[u] && (gr4[u].x == 123.456f);
-#else
-                        if (live[u] && !A.grads) {
-                            t4[u] = ldg_plain(th + off[u]);
-                            m4[u] = ldg_plain(am + off[u]);
-                            v4[u] = ldg_plain(av + off[u]);
-                            if (k.sync == 2) g4[u] = ldg_plain(tg + off[u]);
-                        }
-#endif
+                    for (int up = 0; up < 8; ++up) {
+                        const int m = mrow0 + 4 * up;
+                        const bool bias_row = !is_w2 && m == Dp;
+                        if (is_w2 || m < Dp || bias_row)
+                            *reinterpret_cast<float4*>(A.grads + pb + (bias_row ? (int)A.L.b1 + c0 + c4 : wbase + 4 * up * H + c0)) =
+                                *reinterpret_cast<const float4*>(trow + 4 * up * Wg::TLD);
                     }
+                } else {
+                    // two batches of four row groups: every load of a batch is issued before its first use, so twelve
+                    // (sixteen with Polyak) 16-byte loads per thread are in flight while the HBM latency elapses
+#pragma unroll 1
+                    for (int it0 = 0; it0 < 8; it0 += 4) {
+                        int off[4];
+                        float4 gr4[4], t4[4], m4[4], v4[4], g4[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (!live[u]) continue;
-                        if (A.grads) {
-                            *reinterpret_cast<float4*>(A.grads + pb + off[u]) = gr4[u];
-                            continue;
+                        for (int u = 0; u < 4; ++u) {
+                            const int m = mrow0 + 4 * (it0 + u);
+                            off[u] = wbase + 4 * (it0 + u) * H + c0;
+                            if (!is_w2) off[u] = m == Dp ? (int)A.L.b1 + c0 + c4 : (m < Dp ? off[u] : -1);   // db1 from the ones column
+                            gr4[u] = *reinterpret_cast<const float4*>(trow + 4 * (it0 + u) * Wg::TLD);
+                            if (is_w2 || off[u] >= 0) {
+                                t4[u] = ldg_plain(th + off[u]);
+                                m4[u] = ldg_plain(am + off[u]);
+                                v4[u] = ldg_plain(av + off[u]);
+                                if (sync == 2) g4[u] = ldg_plain(tg + off[u]);
+                            }
                         }
-                        adam1(k, gr4[u].x, t4[u].x, m4[u].x, v4[u].x, g4[u].x); adam1(k, gr4[u].y, t4[u].y, m4[u].y, v4[u].y, g4[u].y);
-                        adam1(k, gr4[u].z, t4[u].z, m4[u].z, v4[u].z, g4[u].z); adam1(k, gr4[u].w, t4[u].w, m4[u].w, v4[u].w, g4[u].w);
-                        *reinterpret_cast<float4*>(th + off[u]) = t4[u];
-                        *reinterpret_cast<float4*>(am + off[u]) = m4[u];
-                        *reinterpret_cast<float4*>(av + off[u]) = v4[u];
-                        if (k.sync) *reinterpret_cast<float4*>(tg + off[u]) = g4[u];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (!is_w2 && off[u] < 0) continue;
+                            adam_fast(k, gr4[u].x, t4[u].x, m4[u].x, v4[u].x); adam_fast(k, gr4[u].y, t4[u].y, m4[u].y, v4[u].y);
+                            adam_fast(k, gr4[u].z, t4[u].z, m4[u].z, v4[u].z); adam_fast(k, gr4[u].w, t4[u].w, m4[u].w, v4[u].w);
+                            *reinterpret_cast<float4*>(th + off[u]) = t4[u];
+                            *reinterpret_cast<float4*>(am + off[u]) = m4[u];
+                            *reinterpret_cast<float4*>(av + off[u]) = v4[u];
+                            if (sync == 1) {
+                                *reinterpret_cast<float4*>(tg + off[u]) = t4[u];
+                            } else if (sync == 2) {
+                                const float omt = 1.0f - k.tau;
+                                g4[u] = make_float4(k.tau * t4[u].x + omt * g4[u].x, k.tau * t4[u].y + omt * g4[u].y,
+                                                    k.tau * t4[u].z + omt * g4[u].z, k.tau * t4[u].w + omt * g4[u].w);
+                                *reinterpret_cast<float4*>(tg + off[u]) = g4[u];
+                            }
+                        }
                     }
                 }
                 __syncwarp();                                     // the tile is rewritten by the next column block
@@ -1367,6 +1397,7 @@ int launch_learn_tc(const dmdqn_dims& d, const dmdqn_hparams& hp, const dmdqn_re
     A.step_t = reinterpret_cast<const int32_t*>(ws + w.step_t);
     A.adam_sc = reinterpret_cast<const float4*>(ws + w.adam_sc);
     A.mask2 = reinterpret_cast<uint32_t*>(ws + w.mask2);
+    A.ga = reinterpret_cast<float2*>(ws + w.ga);
     A.w3_copy = reinterpret_cast<float*>(ws + w.w3_copy);
     A.r_hat = reinterpret_cast<const float*>(ws + w.r_hat);
     A.done_b = reinterpret_cast<const float*>(ws + w.done_b);

@@ -352,9 +352,9 @@ class AgentGroup:
             # the tcgen05 path keeps its activation scratch transposed ([feature][batch]) and never
             # materialises dh2: "dh2" is relu'(h2) as 0/1 here (its non-zero pattern is what the tests use)
             out["dh1"] = view(v.dh1, torch.float32, (g, self.hidden, b)).transpose(1, 2)
-            bits = view(v.relu2_bits, torch.int32, (g, self.hidden // 32, b))
-            sh = torch.arange(32, device=bits.device, dtype=torch.int32).view(1, 1, 32, 1)
-            out["dh2"] = ((bits.unsqueeze(2) >> sh) & 1).reshape(g, self.hidden, b).transpose(1, 2).float()
+            bits = view(v.relu2_bits, torch.int32, (g, b, self.hidden // 32))      # [network][batch row][word]
+            sh = torch.arange(32, device=bits.device, dtype=torch.int32).view(1, 1, 1, 32)
+            out["dh2"] = ((bits.unsqueeze(3) >> sh) & 1).reshape(g, b, self.hidden).float()
         else:
             out["dh1"] = view(v.dh1, torch.float32, (g, b, self.hidden))
             out["dh2"] = view(v.dh2, torch.float32, (g, b, self.hidden))

@@ -240,7 +240,7 @@ typedef struct dmdqn_debug_views {
     const int32_t* rows; const float* r_hat; const int32_t* active;
     const int32_t* tc_error;   /* != 0: a tcgen05 kernel's bounded mbarrier wait expired (results invalid) */
     const float* dh1; const float* dh2;   /* [n_nets][B][H] activation gradients of the last step */
-    /* tcgen05 path: dh2 is never materialised; relu'(h2) as bits, uint32 [n_nets][H/32][B]
+    /* tcgen05 path: dh2 is never materialised; relu'(h2) as bits, uint32 [n_nets][B][H/32]
      * (bit j of word w of row i = column 32 w + j), dh2 = bit ? g_i * W3[col][a_i] : 0 */
     const uint32_t* relu2_bits;
 } dmdqn_debug_views;

@@ -56,26 +56,57 @@ def flops_bytes(w):
 
 # ------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons every 200 ms while the timed region runs."""
+    """SM clock, power and throttle reasons sampled WHILE the timed region runs: NVML every 10 ms
+    (nvidia_ml_py), or nvidia-smi every 200 ms when NVML cannot be loaded."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.rows, self._stop_evt, self.how = index, [], threading.Event(), "nvidia-smi"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.how = "nvml"
+        except Exception:
+            self.nv = None
+
+    @staticmethod
+    def _physical_index(local):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v for v in vis.split(",") if v.strip()]
+            if local < len(ids) and ids[local].strip().isdigit():
+                return int(ids[local])
+        return local
+
+    def _nvml_row(self):
+        nv = self.nv
+        bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        flags = (getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8), getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20), getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4))
+        return [float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)), self.max_sm, nv.nvmlDeviceGetPowerUsage(self.h) / 1e3] + \
+               ["Active" if bits & f else "Not Active" for f in flags]
 
     def run(self):
         import subprocess
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 7:
-                    self.rows.append(f)
+                if self.nv is not None:
+                    self.rows.append(self._nvml_row())
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    f = [x.strip() for x in out.strip().split(",")]
+                    if len(f) >= 7:
+                        self.rows.append(f)
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.01 if self.nv is not None else 0.2)
 
     def stop(self):
         self._stop_evt.set()
@@ -83,10 +114,20 @@ class ClockSampler(threading.Thread):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         sm = [float(r[0]) for r in self.rows]
-        reasons = [n for i, n in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), 3)
-                   if any(r[i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(self.rows[0][1]), "samples": len(sm),
+        reasons = [n for i, n in enumerate(self.NAMES, 3) if any(str(r[i]).lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(self.rows[0][1]), "samples": len(sm), "how": self.how,
                 "power_w_max": max(float(r[2]) for r in self.rows), "reasons": reasons}
+
+
+def ncu_traffic(workload, precision, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full`
+    capture of this workload (profiles/ncu_traffic.json names the capture each figure comes from); None when
+    this workload / precision has not been captured."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return t[f"{workload}/{precision}"][kernel]["dram_bytes"]
+    except Exception:
+        return None
 
 
 def peaks():
@@ -194,9 +235,10 @@ def run_ours(args):
     halting = torch.randint(0, 20, (n, 12), dtype=torch.int32, device=grp.device)
     zi = torch.zeros(n, dtype=torch.int32, device=grp.device); zd = torch.zeros(n, dtype=torch.float64, device=grp.device)
     zv = torch.zeros(n, dtype=torch.uint8, device=grp.device)
-    side = int(round(n ** 0.5))
+    side = max(r for r in range(1, int(n ** 0.5) + 1) if n % r == 0)          # this GPU's shard of the grid: side x n/side
     from oracle.featurize import grid_neighbors                               # index table only (not on the timed path)
-    nbr = torch.as_tensor(grid_neighbors(side, max(1, n // side))[:n]).to(grp.device)
+    nbr = torch.as_tensor(grid_neighbors(side, n // side)).to(grp.device)
+    assert nbr.shape[0] == n
     feat_ms = timed(lambda: grp.featurize(halting, zi, zd, zd, 0.0, zv, nbr), 4 * K)
     act_bytes = n * 4 * fb["params"]
     extra = {"act": {"value": n * world / (act_ms / 1e3), "unit": "actions/s", "ms": act_ms, "eps": 0.0,
@@ -265,11 +307,13 @@ def run_ours(args):
         "gpu_launches": 4 * K,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": dom, "achieved": ach_tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": ach_tf / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"],
+                     "frac": ach_tf / pk["bf16_tflops_sustained"], "traffic": ncu_traffic(args.workload, args.precision, dom),
+                     "algorithmic_bytes": n * kf["bytes"], "peak_source": pk["source"],
                      "note": (f"fp32 FFMA kernel: fraction of the fp32 FFMA peak at the sampled clock = {ach_tf / ffma_peak:.3f} of "
                               f"{ffma_peak:.1f} TFLOP/s") if args.precision == "fp32" else
                              ("tcgen05 kind::tf32; achieved counts ALGORITHMIC flops (each product is issued as "
-                              f"{3 if args.precision == 'tf32x3' else 1} MMA(s)); peak is the measured bf16 figure (tf32 dense peak is half of it)")},
+                              f"{3 if args.precision == 'tf32x3' else 1} MMA(s)); peak is the measured bf16 figure (tf32 dense peak is half of it), so the "
+                              f"ceiling of this precision is frac = {1 / (6 if args.precision == 'tf32x3' else 2):.3f}")},
         "kernels": {k_: {"ms": stage_ms[k_], "tflops": n * fb["kernels"][k_]["flops"] / (stage_ms[k_] / 1e3) / 1e12,
                          "gbs": n * fb["kernels"][k_]["bytes"] / (stage_ms[k_] / 1e3) / 1e9} for k_ in stage_names},
         **extra,
@@ -362,8 +406,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32"])

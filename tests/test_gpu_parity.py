@@ -305,7 +305,8 @@ def test_learn_matches_oracle_mse_hard_sync(h, n, batch, cap):
     _learn_case(h, n, batch, cap, steps=7)
 
 
-@pytest.mark.parametrize("n,batch,cap", [(3, 128, 200), (2, 256, 300), (4, 64, 128), (2, 100, 200), (2, 300, 400)])
+@pytest.mark.parametrize("n,batch,cap", [(3, 128, 200), (2, 256, 300), (4, 64, 128), (2, 100, 200), (2, 300, 400), (2, 512, 600),
+                                         (150, 64, 80)])
 def test_learn_tcgen05_3xtf32_meets_the_fp32_bar(n, batch, cap):
     """tcgen05 kind::tf32 with hi/lo error compensation (3 MMAs per product): same 1e-5 tolerance as the
     FFMA path -- this is fp32-class arithmetic on the tensor cores, not a reduced-precision mode."""

@@ -1,78 +1,106 @@
-// K2 -- batched epsilon-greedy action selection: one CTA per agent runs the batch-1 MLP
-// (89 -> H -> H -> 4) as a GEMV chain with argmax and the epsilon mask fused in.
+// K2 -- batched epsilon-greedy action selection: a cluster of four CTAs per agent runs the batch-1
+// MLP (89 -> H -> H -> 4) as a GEMV chain with argmax and the epsilon mask fused in.
 //
 // Replaces DQNAgent.select_action (reference src/agents/dqn_agent.py:263-274) and
 // select_greedy_action (reference src/experimental/agent.py:148-152).
-// HBM bound: every action reads the agent's 4*P weight bytes once (AI 0.5 flop/B); rows of
-// W are streamed with 16-byte loads, 8 in flight per thread, K split over thread groups and
-// combined in a fixed order (deterministic Q-values).  Exploring agents skip the forward
-// pass, as the reference does.
+// HBM bound: every action reads the agent's 4*P weight bytes once (AI 0.5 flop/B).  The layer outputs
+// are split by columns over the four CTAs of a cluster (each streams a [K][H/4] slice of W1 and W2
+// with 16-byte loads, every load of a layer in flight at once), the activation slices are exchanged
+// through distributed shared memory, and the K split over thread groups is combined in a fixed order
+// (deterministic Q-values).  Four CTAs per agent give 1024 CTAs at 256 agents: all resident at once
+// on 148 SMs, so the launch is one latency chain deep instead of a 1.7-wave tail of long CTAs.
+// Exploring agents skip the forward pass, as the reference does.
+#include <cooperative_groups.h>
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace dmdqn {
 
 namespace {
 
 constexpr int kActThreads = 256;
+constexpr int kActCluster = 4;
 
-// out[0..H) = relu?(bias + x[0..K) . W[K][H]) ; x, out, part in shared memory.
-__device__ __forceinline__ void gemv_layer(const float* __restrict__ W, const float* __restrict__ bias,
-                                           const float* x, float* out, float* part, int K, int H, bool relu) {
-    const int c4 = H >> 2;                 // threads covering one row of W with float4
-    const int groups = kActThreads / c4;   // K is split over this many thread groups
+// This CTA's column slice of a layer: out[c0 .. c0 + Hs) = relu(bias + x[0..K) . W[K][H]) written into the
+// `out` buffer of every CTA of the cluster.  x, part in (local) shared memory.  MAXIT = ceil(K / groups).
+template <int MAXIT>
+__device__ __forceinline__ void gemv_slice(cg::cluster_group& cluster, const float* __restrict__ W, const float* __restrict__ bias,
+                                           const float* x, float* out, float* part, int K, int H, int rank) {
+    const int Hs = H / kActCluster, c4 = Hs >> 2;        // threads covering one row slice with float4
+    const int groups = kActThreads / c4;                 // K is split over this many thread groups
     const int col4 = threadIdx.x % c4, grp = threadIdx.x / c4;
+    const float4* Wv = reinterpret_cast<const float4*>(W + rank * Hs) + col4;
+    float4 w[MAXIT];
+#pragma unroll
+    for (int i = 0; i < MAXIT; ++i) {                    // every load first: one HBM latency per layer
+        const int k = grp + i * groups;
+        w[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < K)                                       // volatile: ptxas would otherwise sink the loads to their uses
+            asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w[i].x), "=f"(w[i].y), "=f"(w[i].z), "=f"(w[i].w)
+                         : "l"(Wv + (size_t)k * (H >> 2)));
+    }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4* Wv = reinterpret_cast<const float4*>(W) + col4;
-#pragma unroll 8
-    for (int k = grp; k < K; k += groups) {
-        const float4 w = __ldg(Wv + (size_t)k * c4);
-        const float xv = x[k];
-        acc.x = fmaf(xv, w.x, acc.x);
-        acc.y = fmaf(xv, w.y, acc.y);
-        acc.z = fmaf(xv, w.z, acc.z);
-        acc.w = fmaf(xv, w.w, acc.w);
+#pragma unroll
+    for (int i = 0; i < MAXIT; ++i) {
+        const int k = grp + i * groups;
+        float xv = 0.f;                                  // volatile too: keeps every FMA behind the last global load
+        if (k < K) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xv) : "r"((uint32_t)__cvta_generic_to_shared(x + k)));
+        acc.x = fmaf(xv, w[i].x, acc.x);
+        acc.y = fmaf(xv, w[i].y, acc.y);
+        acc.z = fmaf(xv, w[i].z, acc.z);
+        acc.w = fmaf(xv, w[i].w, acc.w);
     }
     reinterpret_cast<float4*>(part)[grp * c4 + col4] = acc;
     __syncthreads();
-    for (int j = threadIdx.x; j < H; j += kActThreads) {
-        float s = bias[j];
-        for (int g = 0; g < groups; ++g) s += part[g * H + j];
-        out[j] = relu ? fmaxf(s, 0.f) : s;
+    if (threadIdx.x < Hs) {
+        const int j = threadIdx.x;
+        float s = bias[rank * Hs + j];
+        for (int g = 0; g < groups; ++g) s += part[g * Hs + j];
+        s = fmaxf(s, 0.f);
+#pragma unroll
+        for (int r = 0; r < kActCluster; ++r) cluster.map_shared_rank(out, r)[rank * Hs + j] = s;
     }
-    __syncthreads();
+    cluster.sync();
 }
 
-__global__ void __launch_bounds__(kActThreads)
+template <int H_>
+__global__ void __cluster_dims__(kActCluster, 1, 1) __launch_bounds__(kActThreads, 2)
 act_kernel(dmdqn_dims d, Layout L, const float* __restrict__ theta, const float* __restrict__ obs, int stride,
            const double* __restrict__ eps, const uint32_t* __restrict__ w_explore,
            const uint32_t* __restrict__ w_action, int32_t* __restrict__ actions, float* __restrict__ q_out) {
     extern __shared__ __align__(16) float smem[];
-    const int a = blockIdx.x;
-    const int H = d.hidden, Dp = d.obs_stride;
-    // explore iff u < eps with u = w / 2^32 (dqn_agent.py:263), exact in float64
+    cg::cluster_group cluster = cg::this_cluster();
+    const int a = blockIdx.x / kActCluster, rank = (int)cluster.block_rank();
+    constexpr int H = H_;
+    const int Dp = d.obs_stride;
+    // explore iff u < eps with u = w / 2^32 (dqn_agent.py:263), exact in float64; the same for the four CTAs
     const bool explore = (double)w_explore[a] < eps[a] * 4294967296.0;
     if (explore) {
-        if (threadIdx.x == 0) actions[a] = (int32_t)__umulhi(w_action[a], (uint32_t)d.n_actions);
+        if (threadIdx.x == 0 && rank == 0) actions[a] = (int32_t)__umulhi(w_action[a], (uint32_t)d.n_actions);
         return;  // dqn_agent.py:265: no forward pass
     }
     float* xs = smem;            // [Dp]
     float* h1 = xs + Dp;         // [H]
     float* h2 = h1 + H;          // [H]
-    float* part = h2 + H;        // [groups][H] = [256*4]
+    float* part = h2 + H;        // [groups][H/4] = [256*4]; later [4 ranks][4] head partials on rank 0
     const float* P = theta + (size_t)(d.n_nets == 1 ? 0 : a) * L.stride;
     for (int c = threadIdx.x; c < Dp; c += kActThreads)
         xs[c] = c < d.obs_dim ? obs[(size_t)a * stride + c] : 0.f;
     __syncthreads();
-    gemv_layer(P + L.w1, P + L.b1, xs, h1, part, Dp, H, true);
-    gemv_layer(P + L.w2, P + L.b2, h1, h2, part, H, H, true);
+    constexpr int C4 = H / kActCluster / 4, GROUPS = kActThreads / C4;
+    gemv_slice<(96 + GROUPS - 1) / GROUPS>(cluster, P + L.w1, P + L.b1, xs, h1, part, Dp, H, rank);
+    gemv_slice<(H + GROUPS - 1) / GROUPS>(cluster, P + L.w2, P + L.b2, h1, h2, part, H, H, rank);
 
-    // layer 3: q[a] = b3[a] + sum_j h2[j] * W3[j][a]; warp butterfly, then warps in order
+    // layer 3: q[a] = b3[a] + sum_j h2[j] * W3[j][a]: every CTA sums its H/4 rows (warp butterfly, warps in
+    // order), rank 0 adds the four partials in rank order
+    constexpr int Hs = H / kActCluster;
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int j = threadIdx.x; j < H; j += kActThreads) {
+    if (threadIdx.x < Hs) {
+        const int j = rank * Hs + threadIdx.x;
         const float4 w = __ldg(reinterpret_cast<const float4*>(P + L.w3) + j);
         const float hv = h2[j];
-        p.x = fmaf(hv, w.x, p.x); p.y = fmaf(hv, w.y, p.y);
-        p.z = fmaf(hv, w.z, p.z); p.w = fmaf(hv, w.w, p.w);
+        p = make_float4(hv * w.x, hv * w.y, hv * w.z, hv * w.w);
     }
     for (int off = 16; off; off >>= 1) {
         p.x += __shfl_xor_sync(0xffffffffu, p.x, off);
@@ -80,13 +108,21 @@ act_kernel(dmdqn_dims d, Layout L, const float* __restrict__ theta, const float*
         p.z += __shfl_xor_sync(0xffffffffu, p.z, off);
         p.w += __shfl_xor_sync(0xffffffffu, p.w, off);
     }
+    __syncthreads();             // part is reused
     float4* wsum = reinterpret_cast<float4*>(part);
     if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = p;
     __syncthreads();
     if (threadIdx.x == 0) {
+        float4 t = wsum[0];
+        for (int w = 1; w < (Hs + 31) / 32; ++w) { t.x += wsum[w].x; t.y += wsum[w].y; t.z += wsum[w].z; t.w += wsum[w].w; }
+        reinterpret_cast<float4*>(cluster.map_shared_rank(part, 0))[16 + rank] = t;
+    }
+    cluster.sync();
+    if (threadIdx.x == 0 && rank == 0) {
         float q[4] = {P[L.b3 + 0], P[L.b3 + 1], P[L.b3 + 2], P[L.b3 + 3]};
-        for (int w = 0; w < kActThreads / 32; ++w) {
-            q[0] += wsum[w].x; q[1] += wsum[w].y; q[2] += wsum[w].z; q[3] += wsum[w].w;
+        for (int r = 0; r < kActCluster; ++r) {
+            const float4 t = reinterpret_cast<const float4*>(part)[16 + r];
+            q[0] += t.x; q[1] += t.y; q[2] += t.z; q[3] += t.w;
         }
         int best = 0;                                   // ties -> lowest index (torch.argmax)
         for (int k = 1; k < d.n_actions; ++k) if (q[k] > q[best]) best = k;
@@ -104,7 +140,14 @@ int launch_act(const dmdqn_dims& d, const dmdqn_nets& nets, const float* obs, in
                cudaStream_t s) {
     const Layout L = make_layout(d.obs_stride, d.hidden);
     const size_t smem = (size_t)(d.obs_stride + 2 * d.hidden + kActThreads * 4) * sizeof(float);
-    act_kernel<<<d.n_agents, kActThreads, smem, s>>>(d, L, nets.theta, obs, stride, eps, w1, w2, actions, q_out);
+    const dim3 grid(d.n_agents * kActCluster);
+    switch (d.hidden) {
+        case 64: act_kernel<64><<<grid, kActThreads, smem, s>>>(d, L, nets.theta, obs, stride, eps, w1, w2, actions, q_out); break;
+        case 128: act_kernel<128><<<grid, kActThreads, smem, s>>>(d, L, nets.theta, obs, stride, eps, w1, w2, actions, q_out); break;
+        case 256: act_kernel<256><<<grid, kActThreads, smem, s>>>(d, L, nets.theta, obs, stride, eps, w1, w2, actions, q_out); break;
+        case 512: act_kernel<512><<<grid, kActThreads, smem, s>>>(d, L, nets.theta, obs, stride, eps, w1, w2, actions, q_out); break;
+        default: DMDQN_CHECK_ARG(false, "hidden=%d: the act kernel is built for 64, 128, 256, 512", d.hidden);
+    }
     DMDQN_CUDA(cudaGetLastError());
     return DMDQN_OK;
 }

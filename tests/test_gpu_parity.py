@@ -330,6 +330,60 @@ def test_learn_matches_oracle_vanilla_target_torch_adam():
     _learn_case(64, 3, 32, 64, steps=5, double_dqn=False, adam_form="torch")
 
 
+@pytest.mark.parametrize("h,n_agents,batch,cap,precision", [(64, 3, 48, 40, "fp32"), (256, 4, 128, 50, "tf32x3"),
+                                                            (256, 2, 256, 300, "tf32x3")])
+def test_shared_parameter_step_matches_big_batch_oracle(h, n_agents, batch, cap, precision):
+    """Shared-parameter mode (BASELINE cfg5 shape) on one GPU: the batch is drawn over
+    the concatenated rings of all agents, dmdqn_learn_grads leaves the raw gradient block, one
+    (here trivial) all-reduce, dmdqn_adam_apply -- against the single-network oracle on the same batch."""
+    from dmdqn_b200.parallel import SharedParameterStep
+    from oracle import replay as R
+    from oracle.dqn import StackedOracle, adam_scalars
+    rng = np.random.default_rng(h + batch)
+    cfg = {"nn_layers": [h, h], "replay_buffer_size": cap, "batch_size": batch, "learning_rate": 5e-4, "gamma": 0.99,
+           "target_update_frequency": 2, "share_parameters": True, "precision": precision}
+    grp = _group(n_agents, cfg)
+    assert grp.n_nets == 1
+    stk = StackedOracle(1, 89, [h, h], 4, gamma=0.99, learning_rate=5e-4, target_update_frequency=2, seed0=9)
+    for k in (1, 3, 5):
+        stk.online[k] += torch.as_tensor(rng.standard_normal(stk.online[k].shape).astype(np.float32)) * 0.05
+        stk.target[k].copy_(stk.online[k])
+    _load_oracle_weights(grp, stk)
+    ring = R.RingReplay(n_agents, cap, 89)
+    for t in range(cap + 3):
+        s = rng.integers(-1, 20, (n_agents, 89)).astype(np.float32); s2 = rng.integers(-1, 20, (n_agents, 89)).astype(np.float32)
+        a = rng.integers(0, 4, n_agents).astype(np.int32)
+        r = -0.3 * rng.integers(0, 200, n_agents) - 0.7 * rng.integers(0, 5000, n_agents)
+        dn = rng.random(n_agents) < 0.1
+        grp.push(s, a, r, s2, dn); ring.push(s, a, r, s2, dn)
+    step = SharedParameterStep.for_group(grp)
+    for it in range(3):
+        words = rng.integers(0, 2**32, (1, batch), dtype=np.uint64).astype(np.uint32)
+        grp.draw_words = lambda shape, w=words: torch.as_tensor(w.view(np.int32)).to(grp.device)     # the step draws through this
+        loss = step.step().cpu().numpy()
+        assert int(grp.debug_views()["tc_error"][0]) == 0
+        logical = R.fisher_yates_indices(words[0], cap * n_agents)                                    # population = all rings, agent-major
+        agent, lj = logical // cap, logical % cap
+        rows = [ring.gather(int(ag), np.array([j]), normalize_rewards=False) for ag, j in zip(agent, lj)]
+        S, A_, Rw, S2, D = (np.concatenate([b[k] for b in rows])[None] for k in range(5))
+        slot_rew = np.array([ring.rew[int(ag), ring.logical_to_slot(int(ag), np.array([j]))[0]] for ag, j in zip(agent, lj)])
+        Rw = R.zscore_canonical(slot_rew).astype(np.float32)[None]
+        assert np.array_equal(grp.debug_views()["r_hat"].cpu().numpy(), Rw)
+        th0 = [p[0].clone() for p in stk.online]; m0 = [p[0].clone() for p in stk.adam_m]; v0 = [p[0].clone() for p in stk.adam_v]
+        out = stk.learn_on_batch(S, A_, Rw, S2, D)
+        alpha, eps = adam_scalars(int(stk.learn_step[0]), 5e-4, "keras")
+        close(loss, out["loss"], rtol=RTOL, what=f"shared step {it} loss")
+        got = grp.get_weights(0, "online"); gt = grp.get_weights(0, "target"); gm = grp.get_weights(0, "m")
+        for k in range(6):
+            gk = torch.as_tensor(out["grads"][k][0])
+            close(gm[k].numpy(), (m0[k] + (gk - m0[k]) * np.float32(0.1)).numpy(), rtol=RTOL, what=f"shared step {it} adam_m[{k}]")
+            adam_close(got[k].numpy(), th0[k], m0[k], v0[k], gk, alpha, eps, rtol=RTOL, what=f"shared step {it} theta[{k}]")
+            if int(stk.learn_step[0]) % 2 == 0:     # hard sync copies the just-updated weights
+                assert torch.equal(gt[k], got[k])
+        _load_oracle_weights(grp, stk)
+        grp.set_weights(0, [p[0] for p in stk.adam_m], "m"); grp.set_weights(0, [p[0] for p in stk.adam_v], "v")
+
+
 def test_learn_skips_short_buffers_and_masked_agents():
     n, batch = 4, 16
     grp = _group(n, {"nn_layers": [64, 64], "replay_buffer_size": 64, "batch_size": batch})

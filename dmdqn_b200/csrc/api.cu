@@ -91,6 +91,17 @@ int dmdqn_featurize(int32_t n, const int32_t* halting, const int32_t* phase, con
                             obs_out_stride, reward_out, global_out, scratch, (cudaStream_t)stream);
 }
 
+int dmdqn_featurize_alt(int32_t n, const int32_t* halting, const int32_t* phase, const double* next_switch,
+                        const uint8_t* signal_valid, double sim_time, const int32_t* nbr_idx, const double* prev_own,
+                        double* own_out, float* obs_out, int32_t obs_out_stride, double* reward_out, void* stream) {
+    DMDQN_CHECK_ARG(n >= 1, "n=%d must be >= 1", n);
+    DMDQN_CHECK_ARG(halting && phase && next_switch && signal_valid && nbr_idx, "featurize_alt: NULL input");
+    DMDQN_CHECK_ARG(obs_out != nullptr, "featurize_alt: obs_out is NULL");
+    DMDQN_CHECK_ARG(obs_out_stride >= DMDQN_OBS_ALT_DIM, "obs_out_stride=%d must be >= 74", obs_out_stride);
+    return launch_featurize_alt(n, halting, phase, next_switch, signal_valid, sim_time, nbr_idx, prev_own, own_out,
+                                obs_out, obs_out_stride, reward_out, (cudaStream_t)stream);
+}
+
 int dmdqn_act(const dmdqn_dims* dims, const dmdqn_nets* nets, const float* obs, int32_t obs_in_stride,
               const double* eps, const uint32_t* w_explore, const uint32_t* w_action, int32_t* actions_out,
               float* q_out, void* stream) {

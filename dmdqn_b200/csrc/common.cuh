@@ -117,6 +117,9 @@ int launch_featurize(int32_t n, const int32_t* halting, const int32_t* phase, co
                      const int32_t* nbr_idx, const int32_t* phase_lut, const double* snapshot,
                      double lw, double gw, double* own_out, float* obs_out, int32_t obs_out_stride,
                      double* reward_out, double* global_out, int64_t* scratch, cudaStream_t s);
+int launch_featurize_alt(int32_t n, const int32_t* halting, const int32_t* phase, const double* next_switch,
+                         const uint8_t* signal_valid, double sim_time, const int32_t* nbr_idx, const double* prev_own,
+                         double* own_out, float* obs_out, int32_t obs_out_stride, double* reward_out, cudaStream_t s);
 int launch_act(const dmdqn_dims& d, const dmdqn_nets& nets, const float* obs, int32_t stride,
                const double* eps, const uint32_t* w1, const uint32_t* w2, int32_t* actions, float* q_out,
                cudaStream_t s);

@@ -100,7 +100,68 @@ featurize_kernel(int n, FeatIn in, const int32_t* __restrict__ nbr_idx, const do
     }
 }
 
+// ---- alt contract: SumoTrafficEnvironment's 74-dim observation and queue-reduction reward
+// (reference src/agents/sumo_env.py:532-580 local block, :582-631 assembly, :633-645 presence, :652-679 reward).
+// local(14) = 12 queues in N,E,S,W order x 3 lanes (code -2 = PAD lane -> 0.0 (:545-549), -1 = failed read keeps
+// the -1.0 padding (:555-557)) | phase index | max(0, nextSwitch - now); a junction without a readable signal keeps
+// -1.0 in both signal slots (:560-575).
+__device__ __forceinline__ double own_alt_elem(const int32_t* __restrict__ halting, const int32_t* __restrict__ phase,
+                                               const double* __restrict__ next_switch, const uint8_t* __restrict__ signal_valid,
+                                               double sim_time, int a, int e) {
+    if (e < 12) {
+        const int h = halting[a * 12 + e];
+        return h == -2 ? 0.0 : (double)h;
+    }
+    if (!signal_valid[a]) return -1.0;
+    if (e == 12) return (double)phase[a];
+    return fmax(0.0, __dsub_rn(next_switch[a], sim_time));
+}
+
+__global__ void __launch_bounds__(32 * kWarpsPerCta)
+featurize_alt_kernel(int n, const int32_t* __restrict__ halting, const int32_t* __restrict__ phase,
+                     const double* __restrict__ next_switch, const uint8_t* __restrict__ signal_valid, double sim_time,
+                     const int32_t* __restrict__ nbr_idx, const double* __restrict__ prev_own,
+                     double* __restrict__ own_out, float* __restrict__ obs_out, int obs_stride, double* __restrict__ reward_out) {
+    const int lane = threadIdx.x & 31;
+    const int a = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    if (a >= n) return;
+    if (lane < DMDQN_OWN_ALT_DIM && own_out)
+        own_out[a * DMDQN_OWN_ALT_DIM + lane] = own_alt_elem(halting, phase, next_switch, signal_valid, sim_time, a, lane);
+    for (int c = lane; c < obs_stride; c += 32) {
+        double v = 0.0;  // pad columns
+        if (c < DMDQN_OWN_ALT_DIM) {
+            v = own_alt_elem(halting, phase, next_switch, signal_valid, sim_time, a, c);
+        } else if (c < DMDQN_OWN_ALT_DIM + 4) {
+            v = nbr_idx[a * 4 + (c - DMDQN_OWN_ALT_DIM)] >= 0 ? 1.0 : 0.0;   // presence N,E,S,W (:633-645)
+        } else if (c < DMDQN_OBS_ALT_DIM) {
+            const int k = (c - DMDQN_OWN_ALT_DIM - 4) / DMDQN_OWN_ALT_DIM, e = (c - DMDQN_OWN_ALT_DIM - 4) % DMDQN_OWN_ALT_DIM;
+            const int nb = nbr_idx[a * 4 + k];
+            v = nb < 0 ? -1.0 : own_alt_elem(halting, phase, next_switch, signal_valid, sim_time, nb, e);   // (:606-617)
+        }
+        obs_out[(size_t)a * obs_stride + c] = (float)v;
+    }
+    if (reward_out) {   // sum max(0, prev q) - sum max(0, curr q) (:672-677); 0 on the first step (:655-656)
+        double d = 0.0;
+        if (prev_own && lane < 12) {
+            const double cur = own_alt_elem(halting, phase, next_switch, signal_valid, sim_time, a, lane);
+            d = fmax(0.0, prev_own[a * DMDQN_OWN_ALT_DIM + lane]) - fmax(0.0, cur);   // small integers: exact in any order
+        }
+        for (int off = 16; off; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+        if (lane == 0) reward_out[a] = d;
+    }
+}
+
 }  // namespace
+
+int launch_featurize_alt(int32_t n, const int32_t* halting, const int32_t* phase, const double* next_switch,
+                         const uint8_t* signal_valid, double sim_time, const int32_t* nbr_idx, const double* prev_own,
+                         double* own_out, float* obs_out, int32_t obs_out_stride, double* reward_out, cudaStream_t s) {
+    const int grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
+    featurize_alt_kernel<<<grid, 32 * kWarpsPerCta, 0, s>>>(n, halting, phase, next_switch, signal_valid, sim_time, nbr_idx,
+                                                           prev_own, own_out, obs_out, obs_out_stride, reward_out);
+    DMDQN_CUDA(cudaGetLastError());
+    return DMDQN_OK;
+}
 
 int launch_featurize(int32_t n, const int32_t* halting, const int32_t* phase, const double* next_switch,
                      const double* phase_dur, double sim_time, const uint8_t* signal_valid,

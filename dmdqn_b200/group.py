@@ -220,6 +220,25 @@ class AgentGroup:
                                          _ptr(self._feat_scratch), self._stream))
         return obs, own, reward, glob
 
+    def featurize_alt(self, halting_nesw, phase, next_switch, sim_time, nbr_idx_nesw, signal_valid=None, prev_own=None,
+                      obs_stride: int = 76):
+        """The SumoTrafficEnvironment contract (sumo_env.py:532-679): returns (obs[N,obs_stride] f32 whose first 74
+        columns are ``_get_observations``' vector, own[N,14] f64 to pass as ``prev_own`` next step, reward[N] f64 =
+        ``_calculate_rewards`` (0 on the first step)), all on the device.  Queue codes: -2 = PAD lane, -1 = failed read."""
+        n = self.n_agents
+        halting = self._dev(halting_nesw, torch.int32); phase = self._dev(phase, torch.int32)
+        next_switch = self._dev(next_switch, torch.float64); nbr_idx = self._dev(nbr_idx_nesw, torch.int32)
+        signal_valid = torch.ones((n,), dtype=torch.uint8, device=self.device) if signal_valid is None \
+            else self._dev(signal_valid, torch.uint8)
+        prev = None if prev_own is None else self._dev(prev_own, torch.float64)
+        obs = torch.empty((n, obs_stride), dtype=torch.float32, device=self.device)
+        own = torch.empty((n, 14), dtype=torch.float64, device=self.device)
+        reward = torch.empty((n,), dtype=torch.float64, device=self.device)
+        N.check(self.lib.dmdqn_featurize_alt(n, _ptr(halting), _ptr(phase), _ptr(next_switch), _ptr(signal_valid),
+                                             float(sim_time), _ptr(nbr_idx), _ptr(prev), _ptr(own), _ptr(obs), obs.shape[1],
+                                             _ptr(reward), self._stream))
+        return obs, own, reward
+
     # ------------------------------------------------------------------ K2 --------------
     def act(self, obs, eps=None, w_explore=None, w_action=None, return_q: bool = False):
         """Batched epsilon-greedy (dqn_agent.py:263-274).  ``eps`` None -> greedy for all.

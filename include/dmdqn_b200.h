@@ -156,6 +156,24 @@ int dmdqn_featurize(int32_t n, const int32_t* halting, const int32_t* phase,
                     double* own_out, float* obs_out, int32_t obs_out_stride,
                     double* reward_out, double* global_out, int64_t* scratch, void* stream);
 
+/* K0, second layout -- replaces SumoTrafficEnvironment._get_local_observation / _get_observations /
+ * _get_neighbor_presence_vector / _calculate_rewards (reference src/agents/sumo_env.py:532-580,582-631,633-645,
+ * 652-679): the 74-dim observation local(14) | presence(4: N,E,S,W) | 4 x neighbour local(14), pad -1.0, and the
+ * queue-reduction reward.
+ *   halting      device int32 [n][12]   queues in N,E,S,W order x 3 lanes; -2 = PAD lane (-> 0.0), -1 = failed read (-> -1.0)
+ *   phase        device int32 [n], next_switch device double[n], sim_time
+ *   signal_valid device uint8 [n]       0 -> both signal slots keep the -1.0 padding value
+ *   nbr_idx      device int32 [n][4]    neighbour rows in N,E,S,W order, -1 = none / not controlled
+ *   prev_own     device double[n][14] or NULL (first step): the previous call's own_out
+ *   own_out      device double[n][14] or NULL
+ *   obs_out      device float [n][obs_out_stride]  first 74 columns written, rest zeroed
+ *   reward_out   device double[n] or NULL: sum max(0, prev queues) - sum max(0, current queues); 0 when prev_own is NULL */
+#define DMDQN_OWN_ALT_DIM 14
+#define DMDQN_OBS_ALT_DIM 74
+int dmdqn_featurize_alt(int32_t n, const int32_t* halting, const int32_t* phase, const double* next_switch,
+                        const uint8_t* signal_valid, double sim_time, const int32_t* nbr_idx, const double* prev_own,
+                        double* own_out, float* obs_out, int32_t obs_out_stride, double* reward_out, void* stream);
+
 /* K2 -- batched epsilon-greedy action selection, one observation per agent.
  * Replaces DQNAgent.select_action (src/agents/dqn_agent.py:263-274; the epsilon schedule
  * :258-261 stays on the host) and select_greedy_action (experimental/agent.py:148-152).

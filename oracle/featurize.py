@@ -108,16 +108,18 @@ OWN_ALT = 14
 OBS_ALT = 74
 
 
-def own_state_alt(halting_nesw, phase, next_switch, sim_time):
+def own_state_alt(halting_nesw, phase, next_switch, sim_time, signal_valid=None):
     """local(14) = 12 queues in N,E,S,W order || phase index || max(0, nextSwitch - now)
     (sumo_env.py:532-580).  Queue codes: -2 = PAD lane -> 0.0 (:545-549); -1 = failed
-    read -> keeps the -1.0 padding value (:555-557)."""
+    read -> keeps the -1.0 padding value (:555-557).  A junction without a readable signal
+    (``signal_valid`` 0) keeps -1.0 in both signal slots (:560-575)."""
     h = np.asarray(halting_nesw, np.float64)
     n = h.shape[0]
+    valid = np.ones(n, bool) if signal_valid is None else np.asarray(signal_valid).astype(bool)
     own = np.zeros((n, OWN_ALT), np.float64)
     own[:, :12] = np.where(h == -2, 0.0, h)
-    own[:, 12] = np.asarray(phase, np.float64)
-    own[:, 13] = np.maximum(0.0, np.asarray(next_switch, np.float64) - np.float64(sim_time))
+    own[:, 12] = np.where(valid, np.asarray(phase, np.float64), -1.0)
+    own[:, 13] = np.where(valid, np.maximum(0.0, np.asarray(next_switch, np.float64) - np.float64(sim_time)), -1.0)
     return own
 
 

@@ -24,6 +24,8 @@ What is executed for real, and which fixture it lands in:
                      (src/agents/dqn_agent.py:27-89) under ``random.seed``
   ref_epsilon.npz    the epsilon schedule and explore branch of DQNAgent.select_action
                      (src/agents/dqn_agent.py:246-265)
+  ref_env_alt.npz    SumoTrafficEnvironment._get_local_observation / _get_observations /
+                     _get_neighbor_presence_vector / _calculate_rewards (src/agents/sumo_env.py:532-679)
 The MLP / learn arithmetic (TensorFlow ops) is NOT executed: MagicMock swallows it.
 """
 from __future__ import annotations
@@ -258,6 +260,81 @@ def golden_epsilon(dqn_agent):
     print("ref_epsilon.npz", len(steps), "steps; eps range", min(eps), max(eps))
 
 
+def golden_env_alt(FakeTraci):
+    """ref_env_alt.npz: SumoTrafficEnvironment._get_local_observation / _get_observations /
+    _get_neighbor_presence_vector / _calculate_rewards (src/agents/sumo_env.py:532-679) run unmodified on an
+    instance whose network-derived attributes (lane order, neighbour map: the sumolib part of __init__) are set
+    by hand for a 3x4 grid with one PAD lane block, one unreadable lane and one junction without a signal."""
+    import tempfile
+    home = tempfile.mkdtemp()
+    os.makedirs(os.path.join(home, "tools"), exist_ok=True)
+    os.environ["SUMO_HOME"] = home                                    # the module exits at import without it
+    sys.modules["tensorflow.keras.models"] = MagicMock(name="tensorflow.keras.models")   # imported, unused on this path
+    import src.agents.sumo_env as sumo_env                            # noqa: E402  (the reference, unmodified)
+    from dmdqn_b200.sim.fake_traci import DIRS
+    rows, cols = 3, 4
+    fake = FakeTraci(rows=rows, cols=cols, seed=5, arrival_rate=0.3)
+    sumo_env.traci = fake
+    fake.start(["sumo"])
+    ids = fake.junction_ids
+    n = len(ids)
+    env = object.__new__(sumo_env.SumoTrafficEnvironment)
+    env.max_lanes_per_direction, env.padding_value = 3, -1.0
+    env.neighbor_info_size, env.state_vector_size = 14, 74
+    env.controlled_intersection_ids = list(ids)
+    no_signal = ids[5]
+    env.traffic_light_ids = {j: j for j in ids if j != no_signal}
+    pos = {f"J_{r}_{c}": (r, c) for r in range(rows) for c in range(cols)}
+    step = {"N": (-1, 0), "E": (0, 1), "S": (1, 0), "W": (0, -1)}
+    env.neighbor_map, nbr_idx = {}, np.full((n, 4), -1, np.int32)
+    for a, j in enumerate(ids):
+        r, c = pos[j]
+        env.neighbor_map[j] = {}
+        for k, d in enumerate("NESW"):
+            rr, cc = r + step[d][0], c + step[d][1]
+            if 0 <= rr < rows and 0 <= cc < cols:
+                env.neighbor_map[j][d] = f"J_{rr}_{cc}"
+                nbr_idx[a, k] = ids.index(f"J_{rr}_{cc}")
+    env.observed_lanes, lane_tab = {}, []
+    for a, j in enumerate(ids):
+        r, c = pos[j]
+        lanes = []
+        for d in "nesw":
+            lanes += list(fake._lanes[(r, c, d)])
+        if a == 2:
+            lanes[3:6] = ["PAD_E_0", "PAD_E_1", "PAD_E_2"]                # a missing approach (:545-549)
+        if a == 7:
+            lanes[10] = "no_such_lane"                                   # TraCIException -> keeps -1.0 (:555-557)
+        env.observed_lanes[j] = lanes
+        lane_tab.append(lanes)
+    T = 6
+    halting = np.zeros((T, n, 12), np.int32); phase = np.zeros((T, n), np.int32); nsw = np.zeros((T, n), np.float64)
+    times = np.zeros(T); obs_all = np.zeros((T, n, 74), np.float32); rew_all = np.zeros((T, n), np.float64)
+    prev = None
+    rng = np.random.default_rng(1)
+    for t in range(T):
+        for _ in range(7):
+            fake.simulationStep()
+        for j in ids:
+            if rng.random() < 0.5:
+                fake.trafficlight.setPhase(j, int(rng.integers(0, 12)))
+        env.current_time = fake.time
+        times[t] = fake.time
+        for a, j in enumerate(ids):
+            for e, lid in enumerate(lane_tab[a]):
+                halting[t, a, e] = -2 if lid.startswith("PAD_") else (fake.queue[lid] if lid in fake.queue else -1)
+            phase[t, a] = fake.phase[j]; nsw[t, a] = fake.trafficlight.getNextSwitch(j)
+        obs = env._get_observations()
+        rew = env._calculate_rewards(prev, obs, None)
+        for a, j in enumerate(ids):
+            obs_all[t, a] = obs[j]; rew_all[t, a] = float(rew[j])
+        prev = obs
+    valid = np.array([j != no_signal for j in ids], np.uint8)
+    np.savez_compressed(os.path.join(OUT, "ref_env_alt.npz"), halting=halting, phase=phase, next_switch=nsw, sim_time=times,
+                        signal_valid=valid, nbr_idx=nbr_idx, obs=obs_all, reward=rew_all)
+    print("ref_env_alt.npz", obs_all.shape, "rewards", rew_all.min(), rew_all.max())
+
+
 def main():
     if not os.path.isdir(REF):
         raise SystemExit("/root/reference is not present: goldens can only be made in the build container")
@@ -275,6 +352,7 @@ def main():
     golden_episode(train, order_lanes, FakeTraci, sumolib, live=True, tag="live")
     golden_replay(dqn_agent)
     golden_epsilon(dqn_agent)
+    golden_env_alt(FakeTraci)
 
 
 if __name__ == "__main__":

@@ -91,6 +91,40 @@ def _fill(grp, ring, n_push, rng, d=89):
         ring.push(s, a, r, s2, dn)
 
 
+def test_featurize_alt_matches_reference_fixture_and_oracle():
+    """Second observation layout (SumoTrafficEnvironment, sumo_env.py:532-679): bit-exact against the fixture made by
+    running the reference's own methods, then against the oracle on a 64 x 64 grid with PAD / failed lanes."""
+    from oracle import featurize as F
+    z = np.load(os.path.join(G, "ref_env_alt.npz"))
+    n = z["obs"].shape[1]
+    grp = _group(n, {"nn_layers": [64, 64], "replay_buffer_size": 8, "batch_size": 4})
+    prev = None
+    for t in range(z["obs"].shape[0]):
+        obs, own, rew = grp.featurize_alt(z["halting"][t], z["phase"][t], z["next_switch"][t], float(z["sim_time"][t]),
+                                          z["nbr_idx"], z["signal_valid"], prev)
+        assert np.array_equal(obs.cpu().numpy()[:, :74], z["obs"][t]) and np.all(obs.cpu().numpy()[:, 74:] == 0)
+        assert np.array_equal(rew.cpu().numpy(), z["reward"][t])
+        prev = own
+    rng = np.random.default_rng(0)
+    rows = cols = 64
+    n = rows * cols
+    big = _group(n, {"nn_layers": [64, 64], "replay_buffer_size": 8, "batch_size": 4})
+    idx = np.arange(n).reshape(rows, cols)
+    nbr = np.full((n, 4), -1, np.int32)                       # N, E, S, W
+    nbr[idx[1:, :].ravel(), 0] = idx[:-1, :].ravel(); nbr[idx[:, :-1].ravel(), 1] = idx[:, 1:].ravel()
+    nbr[idx[:-1, :].ravel(), 2] = idx[1:, :].ravel(); nbr[idx[:, 1:].ravel(), 3] = idx[:, :-1].ravel()
+    prev_dev, prev_ref = None, None
+    for t in range(3):
+        halting = rng.integers(-2, 25, (n, 12)).astype(np.int32)
+        phase = rng.integers(0, 12, n).astype(np.int32); nsw = rng.random(n) * 60 + t * 10 - 5; valid = (rng.random(n) < 0.9).astype(np.uint8)
+        obs, own, rew = big.featurize_alt(halting, phase, nsw, 10.0 * t, nbr, valid, prev_dev)
+        own_ref = F.own_state_alt(halting, phase, nsw, 10.0 * t, valid)
+        assert np.array_equal(own.cpu().numpy(), own_ref)
+        assert np.array_equal(obs.cpu().numpy()[:, :74], F.build_obs_alt(own_ref, nbr))
+        assert np.array_equal(rew.cpu().numpy(), np.zeros(n) if prev_ref is None else F.rewards_alt(prev_ref, own_ref))
+        prev_dev, prev_ref = own, own_ref
+
+
 @pytest.mark.parametrize("cap,n_push,batch", [(50, 20, 16), (50, 50, 50), (37, 120, 32), (300, 1000, 256)])
 def test_push_sample_bit_exact_fisher_yates(cap, n_push, batch):
     from oracle import replay as R

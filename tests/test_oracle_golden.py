@@ -109,3 +109,19 @@ def test_epsilon_schedule_matches_reference():
         if explored:
             np.random.randint(0, 4)
     assert z["eps"].min() < 0.05 and z["eps"].max() == 1.0
+
+
+def test_alt_env_contract_matches_reference_fixture():
+    """SumoTrafficEnvironment's 74-dim observation and queue-reduction reward (sumo_env.py:532-679), incl. a PAD
+    approach, an unreadable lane and a junction without a signal."""
+    from oracle import featurize as F
+    z = np.load(os.path.join(G, "ref_env_alt.npz"))
+    prev = None
+    for t in range(z["obs"].shape[0]):
+        own = F.own_state_alt(z["halting"][t], z["phase"][t], z["next_switch"][t], z["sim_time"][t], z["signal_valid"])
+        obs = F.build_obs_alt(own, z["nbr_idx"])
+        assert obs.dtype == np.float32 and np.array_equal(obs, z["obs"][t])
+        rew = np.zeros(own.shape[0]) if prev is None else F.rewards_alt(prev, own)
+        assert np.array_equal(rew, z["reward"][t])
+        prev = own
+    assert (z["obs"][:, 2, 3:6] == 0).all() and (z["obs"][:, 7, 10] == -1).all() and (z["obs"][:, 5, 12:14] == -1).all()

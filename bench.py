@@ -270,26 +270,20 @@ def run_ours(args):
              "featurize": {"ms": feat_ms, "agents_per_s": n * world / (feat_ms / 1e3), "bytes_per_agent": 64 + 96 * 4 + 17 * 8 + 8}}
 
     # ---- end to end: host transitions + draws in, losses out, every step ------------------
-    pin = lambda t: t.pin_memory()
-    h_obs, h_next = pin(torch.randint(0, 20, (n, D)).float()), pin(torch.randint(0, 20, (n, D)).float())
-    h_act, h_rew = pin(torch.randint(0, A, (n,), dtype=torch.int32)), pin(-torch.rand(n, dtype=torch.float64) * 100)
-    h_done = pin(torch.zeros(n, dtype=torch.uint8))
-    h_draws = pin(torch.randint(0, 2**31, (n, b), dtype=torch.int32))
-    h_metrics = pin(torch.empty((n, N.METRICS_STRIDE), dtype=torch.float32))
-    d_obs, d_next = torch.empty((n, D), device=grp.device), torch.empty((n, D), device=grp.device)
-    d_act = torch.empty(n, dtype=torch.int32, device=grp.device); d_rew = torch.empty(n, dtype=torch.float64, device=grp.device)
-    d_done = torch.empty(n, dtype=torch.uint8, device=grp.device); d_draws = torch.empty((n, b), dtype=torch.int32, device=grp.device)
-    h2d = sum(t.numel() * t.element_size() for t in (h_obs, h_next, h_act, h_rew, h_done, h_draws))
-    d2h = h_metrics.numel() * h_metrics.element_size()
+    # dmdqn_step_host (include/dmdqn_b200.h): the step's inputs sit in ONE pinned host block (struct of arrays);
+    # the call queues one H2D copy, push, learn and the copy of the metrics back; the caller synchronises and reads.
+    sb = grp.make_step_block()
+    hv = sb["host"]
+    hv["obs"].copy_(torch.randint(0, 20, (n, D)).float()); hv["next_obs"].copy_(torch.randint(0, 20, (n, D)).float())
+    hv["act"].copy_(torch.randint(0, A, (n,), dtype=torch.int32)); hv["rew"].copy_(-torch.rand(n, dtype=torch.float64) * 100)
+    hv["done"].zero_(); hv["draws"].copy_(torch.randint(0, 2**31, (n, b), dtype=torch.int32))
+    h2d = sb["bytes"]
+    d2h = sb["metrics_host"].numel() * sb["metrics_host"].element_size()
 
     def e2e_step():
-        for dst, src in ((d_obs, h_obs), (d_next, h_next), (d_act, h_act), (d_rew, h_rew), (d_done, h_done), (d_draws, h_draws)):
-            dst.copy_(src, non_blocking=True)
-        grp.push(d_obs, d_act, d_rew, d_next, d_done)          # remember (train.py:275)
-        m = grp.learn(d_draws)                                 # replay   (train.py:282)
-        h_metrics.copy_(m, non_blocking=True)
+        m = grp.step_host(sb)                                  # remember + replay (train.py:274-292), host buffers
         stream.synchronize()                                   # the caller reads the losses
-        return float(h_metrics[0, 0])
+        return float(m[0, 0])
     for _ in range(W):
         e2e_step()
     barrier()
@@ -326,7 +320,7 @@ def run_ours(args):
                    "sample_mode": "fisher_yates (device draws)"},
         "e2e": {"value": total_agents * K / (ms_e2e / 1e3), "unit": "agent-updates/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K,
-                "what": "pinned host transition+draws -> push -> learn -> losses to host, synchronised every step"},
+                "what": "dmdqn_step_host: one pinned host block (transition of every agent + draws) -> one H2D copy -> push -> learn -> losses to pinned host memory, stream synchronised and the loss read every step"},
         "gpu_launches": 4 * K,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": dom, "achieved": ach_tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",

@@ -43,6 +43,11 @@ class DebugViews(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("y", "q_all", "q_next", "tq_all", "rows", "r_hat", "active", "tc_error", "dh1", "dh2", "relu2_bits")]
 
 
+class StepBlock(C.Structure):
+    _fields_ = [(n, C.c_size_t) for n in ("bytes", "obs_off", "next_obs_off", "act_off", "rew_off", "done_off", "draws_off")] + \
+               [("in_stride", C.c_int32)]
+
+
 # name -> (restype, argtypes); mirrors include/dmdqn_b200.h one to one
 _P = C.c_void_p
 SIGNATURES = {
@@ -62,6 +67,8 @@ SIGNATURES = {
                               _P, _P, C.c_size_t, _P]),
     "dmdqn_learn_stages": (C.c_int, [C.POINTER(Dims), C.POINTER(HParams), C.POINTER(Replay), C.POINTER(Nets), _P, _P,
                                      _P, _P, C.c_size_t, C.c_int32, _P]),
+    "dmdqn_step_host": (C.c_int, [C.POINTER(Dims), C.POINTER(HParams), C.POINTER(Replay), C.POINTER(Nets), C.POINTER(StepBlock),
+                                 _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "dmdqn_learn_grads": (C.c_int, [C.POINTER(Dims), C.POINTER(HParams), C.POINTER(Replay), C.POINTER(Nets), _P, _P,
                                     C.c_int32, _P, _P, _P, C.c_size_t, _P]),
     "dmdqn_adam_apply": (C.c_int, [C.POINTER(Dims), C.POINTER(HParams), C.POINTER(Nets), _P, _P, C.c_size_t, _P]),

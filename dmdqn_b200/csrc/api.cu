@@ -186,6 +186,28 @@ int dmdqn_learn(const dmdqn_dims* dims, const dmdqn_hparams* hp, const dmdqn_rep
                               DMDQN_STAGE_SAMPLE | DMDQN_STAGE_TARGET | DMDQN_STAGE_ONLINE | DMDQN_STAGE_WGRAD, stream);
 }
 
+int dmdqn_step_host(const dmdqn_dims* dims, const dmdqn_hparams* hp, const dmdqn_replay* replay,
+                    const dmdqn_nets* nets, const dmdqn_step_block* blk, const void* host_block, void* device_block,
+                    float* metrics_dev, float* metrics_host, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = validate_dims(dims);
+    if (rc) return rc;
+    DMDQN_CHECK_ARG(blk && host_block && device_block && metrics_dev && metrics_host, "step_host: NULL argument");
+    const size_t offs[6] = {blk->obs_off, blk->next_obs_off, blk->act_off, blk->rew_off, blk->done_off, blk->draws_off};
+    for (size_t o : offs) DMDQN_CHECK_ARG(o % 16 == 0 && o < blk->bytes, "step_host: offset %zu is not a multiple of 16 inside the block", o);
+    cudaStream_t s = (cudaStream_t)stream;
+    char* d = static_cast<char*>(device_block);
+    DMDQN_CUDA(cudaMemcpyAsync(d, host_block, blk->bytes, cudaMemcpyHostToDevice, s));
+    rc = dmdqn_push(dims, replay, reinterpret_cast<const float*>(d + blk->obs_off), reinterpret_cast<const int32_t*>(d + blk->act_off),
+                    reinterpret_cast<const double*>(d + blk->rew_off), reinterpret_cast<const float*>(d + blk->next_obs_off),
+                    reinterpret_cast<const uint8_t*>(d + blk->done_off), blk->in_stride, nullptr, stream);
+    if (rc) return rc;
+    rc = dmdqn_learn(dims, hp, replay, nets, d + blk->draws_off, nullptr, metrics_dev, workspace, workspace_bytes, stream);
+    if (rc) return rc;
+    DMDQN_CUDA(cudaMemcpyAsync(metrics_host, metrics_dev, (size_t)dims->n_nets * DMDQN_METRICS_STRIDE * sizeof(float),
+                               cudaMemcpyDeviceToHost, s));
+    return DMDQN_OK;
+}
+
 int dmdqn_learn_grads(const dmdqn_dims* dims, const dmdqn_hparams* hp, const dmdqn_replay* replay,
                       const dmdqn_nets* nets, const void* draws, const uint8_t* learn_mask, int32_t global_batch,
                       float* grads_out, float* metrics_out, void* workspace, size_t workspace_bytes, void* stream) {

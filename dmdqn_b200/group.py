@@ -352,6 +352,41 @@ class AgentGroup:
         self.learn_step_host += self.active_host(mask).astype(np.int64)
         return self.metrics
 
+    # ------------------------------------------------------------------ host-buffer step ----
+    def make_step_block(self):
+        """Pinned host block + device mirror for ``step_host``: typed views ``host[name]`` / ``dev[name]`` for
+        obs, next_obs [N,obs_dim] f32, act [N] i32, rew [N] f64, done [N] u8, draws [n_nets,B] i32, laid out as one
+        struct of arrays so a step is one H2D copy (include/dmdqn_b200.h dmdqn_step_block)."""
+        n, d, g, b = self.n_agents, self.state_size, self.n_nets, self.batch_size
+        fields = [("obs", torch.float32, (n, d)), ("next_obs", torch.float32, (n, d)), ("rew", torch.float64, (n,)),
+                  ("act", torch.int32, (n,)), ("draws", torch.int32, (g, b)), ("done", torch.uint8, (n,))]
+        offs, off = {}, 0
+        for name, dt, shape in fields:
+            off = (off + 15) // 16 * 16
+            nbytes = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+            offs[name] = (off, nbytes, dt, shape); off += nbytes
+        off = (off + 15) // 16 * 16
+        host = torch.zeros(off, dtype=torch.uint8).pin_memory()
+        dev = torch.zeros(off, dtype=torch.uint8, device=self.device)
+        view = lambda blk, k: blk[offs[k][0]:offs[k][0] + offs[k][1]].view(offs[k][2]).view(offs[k][3])
+        blk = N.StepBlock(off, offs["obs"][0], offs["next_obs"][0], offs["act"][0], offs["rew"][0], offs["done"][0],
+                          offs["draws"][0], d)
+        return {"desc": blk, "host_block": host, "dev_block": dev, "bytes": off,
+                "host": {k: view(host, k) for k in offs}, "dev": {k: view(dev, k) for k in offs},
+                "metrics_host": torch.zeros((g, N.METRICS_STRIDE), dtype=torch.float32).pin_memory()}
+
+    def step_host(self, sb) -> torch.Tensor:
+        """remember + replay for every agent from the HOST block ``sb`` (``make_step_block``): one H2D copy, push, learn,
+        metrics back to ``sb["metrics_host"]`` -- all queued on the current stream by ONE library call
+        (train.py:274-292).  Synchronise the stream before reading the returned pinned tensor."""
+        N.check(self.lib.dmdqn_step_host(C.byref(self.dims), C.byref(self._hp_for(None)), C.byref(self.replay), C.byref(self.nets),
+                                         C.byref(sb["desc"]), sb["host_block"].data_ptr(), sb["dev_block"].data_ptr(),
+                                         _ptr(self.metrics), sb["metrics_host"].data_ptr(), _ptr(self.workspace),
+                                         self.workspace.numel(), self._stream))
+        self.n_written_host += 1
+        self.learn_step_host += self.active_host().astype(np.int64)
+        return sb["metrics_host"]
+
     def debug_views(self) -> dict:
         """Intermediate results of the last learn() as device tensors (parity tests)."""
         v = N.DebugViews()

@@ -238,6 +238,25 @@ int dmdqn_learn_stages(const dmdqn_dims* dims, const dmdqn_hparams* hp, const dm
                        float* metrics_out, void* workspace, size_t workspace_bytes, int32_t stages,
                        void* stream);
 
+/* remember + replay of every agent with HOST buffers -- what the reference's train loop does per step
+ * (src/scripts/train.py:274-292: agent.remember(...) then agent.replay() for every agent), as one call:
+ * the step's inputs sit in ONE pinned host block (struct of arrays at the byte offsets below, each a
+ * multiple of 16), which is copied to its device mirror with a single cudaMemcpyAsync; then dmdqn_push,
+ * dmdqn_learn and a copy of the metrics back to host memory are queued on `stream`.  Nothing is synchronised:
+ * the caller waits on the stream before reading `metrics_host` (the losses replay() returns). */
+typedef struct dmdqn_step_block {
+    size_t bytes;                 /* size of the host / device block */
+    size_t obs_off, next_obs_off; /* float [n_agents][in_stride] */
+    size_t act_off;               /* int32 [n_agents] */
+    size_t rew_off;               /* double[n_agents] */
+    size_t done_off;              /* uint8 [n_agents] */
+    size_t draws_off;             /* [n_nets][batch] words / indices per hp->sample_mode */
+    int32_t in_stride;
+} dmdqn_step_block;
+int dmdqn_step_host(const dmdqn_dims* dims, const dmdqn_hparams* hp, const dmdqn_replay* replay,
+                    const dmdqn_nets* nets, const dmdqn_step_block* blk, const void* host_block, void* device_block,
+                    float* metrics_dev, float* metrics_host, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Shared-parameter mode across ranks (n_nets == 1; not in the reference, BASELINE.json cfg5):
  * the same step but K4b stores dL/dtheta into grads_out[n_nets][layout.stride] instead of
  * applying Adam, with the loss mean taken over global_batch (= batch * ranks), so that the

@@ -554,3 +554,25 @@ def test_evaluation_rollout_modes_and_model_round_trip(tmp_path):
     assert not agents2[env.ids[0]].load_model(str(tmp_path / "missing.pt"))
     assert run_evaluation_episode(env, config, 7, "dqn", agents2, eval_epsilon=0.0) == r_b
     env.close()
+
+
+def test_step_host_equals_push_then_learn():
+    """dmdqn_step_host (host block -> one H2D copy -> push -> learn -> metrics to host) leaves exactly the state and
+    the losses of the separate push + learn calls on the same inputs."""
+    cfg = {"nn_layers": [256, 256], "replay_buffer_size": 96, "batch_size": 64, "learning_rate": 5e-4, "precision": "tf32x3"}
+    a, b_ = _group(5, cfg, seed=4), _group(5, cfg, seed=4)
+    rng = np.random.default_rng(2)
+    sb = a.make_step_block()
+    for t in range(80):
+        s = rng.integers(-1, 20, (5, 89)).astype(np.float32); s2 = rng.integers(-1, 20, (5, 89)).astype(np.float32)
+        act = rng.integers(0, 4, 5).astype(np.int32); r = -rng.random(5) * 50; dn = (rng.random(5) < 0.1).astype(np.uint8)
+        words = rng.integers(0, 2**32, (5, 64), dtype=np.uint64).astype(np.uint32)
+        for k, v in (("obs", s), ("next_obs", s2), ("act", act), ("rew", r), ("done", dn), ("draws", words.view(np.int32))):
+            sb["host"][k].copy_(torch.as_tensor(v))
+        m = a.step_host(sb)
+        torch.cuda.synchronize()
+        b_.push(s, act, r, s2, dn)
+        ref = b_.learn(words).cpu()
+        assert torch.equal(m, ref), t
+    assert m[:, 7].all() and torch.equal(a.theta, b_.theta) and torch.equal(a.adam_v, b_.adam_v) and torch.equal(a.obs, b_.obs)
+    assert np.array_equal(a.learn_step_host, b_.learn_step_host) and np.array_equal(a.n_written_host, b_.n_written_host)

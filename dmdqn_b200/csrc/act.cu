@@ -22,24 +22,32 @@ namespace {
 constexpr int kActThreads = 256;
 constexpr int kActCluster = 4;
 
-// This CTA's column slice of a layer: out[c0 .. c0 + Hs) = relu(bias + x[0..K) . W[K][H]) written into the
-// `out` buffer of every CTA of the cluster.  x, part in (local) shared memory.  MAXIT = ceil(K / groups).
+// This CTA's column slice of a layer, in two steps so that the weight loads of BOTH hidden layers are in flight
+// before the first FMA (they do not depend on the activations): load_slice issues every 16-byte load of the
+// [K][H/4] slice, gemv_slice consumes them: out[c0 .. c0 + Hs) = relu(bias + x[0..K) . W) written into the `out`
+// buffer of every CTA of the cluster.  x, part in (local) shared memory.  MAXIT = ceil(K / groups).
 template <int MAXIT>
-__device__ __forceinline__ void gemv_slice(cg::cluster_group& cluster, const float* __restrict__ W, const float* __restrict__ bias,
-                                           const float* x, float* out, float* part, int K, int H, int rank) {
+__device__ __forceinline__ void load_slice(float4 (&w)[MAXIT], const float* __restrict__ W, int K, int H, int rank) {
     const int Hs = H / kActCluster, c4 = Hs >> 2;        // threads covering one row slice with float4
     const int groups = kActThreads / c4;                 // K is split over this many thread groups
     const int col4 = threadIdx.x % c4, grp = threadIdx.x / c4;
     const float4* Wv = reinterpret_cast<const float4*>(W + rank * Hs) + col4;
-    float4 w[MAXIT];
 #pragma unroll
-    for (int i = 0; i < MAXIT; ++i) {                    // every load first: one HBM latency per layer
+    for (int i = 0; i < MAXIT; ++i) {
         const int k = grp + i * groups;
         w[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (k < K)                                       // volatile: ptxas would otherwise sink the loads to their uses
             asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w[i].x), "=f"(w[i].y), "=f"(w[i].z), "=f"(w[i].w)
                          : "l"(Wv + (size_t)k * (H >> 2)));
     }
+}
+
+template <int MAXIT>
+__device__ __forceinline__ void gemv_slice(cg::cluster_group& cluster, const float4 (&w)[MAXIT], const float* __restrict__ bias,
+                                           const float* x, float* out, float* part, int K, int H, int rank) {
+    const int Hs = H / kActCluster, c4 = Hs >> 2;
+    const int groups = kActThreads / c4;
+    const int col4 = threadIdx.x % c4, grp = threadIdx.x / c4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < MAXIT; ++i) {
@@ -50,6 +58,34 @@ __device__ __forceinline__ void gemv_slice(cg::cluster_group& cluster, const flo
         acc.y = fmaf(xv, w[i].y, acc.y);
         acc.z = fmaf(xv, w[i].z, acc.z);
         acc.w = fmaf(xv, w[i].w, acc.w);
+    }
+    reinterpret_cast<float4*>(part)[grp * c4 + col4] = acc;
+    __syncthreads();
+    if (threadIdx.x < Hs) {
+        const int j = threadIdx.x;
+        float s = bias[rank * Hs + j];
+        for (int g = 0; g < groups; ++g) s += part[g * Hs + j];
+        s = fmaxf(s, 0.f);
+#pragma unroll
+        for (int r = 0; r < kActCluster; ++r) cluster.map_shared_rank(out, r)[rank * Hs + j] = s;
+    }
+    cluster.sync();
+}
+
+// Same layer slice with the weight rows streamed 8 at a time (wide layers)
+__device__ __forceinline__ void gemv_slice_loop(cg::cluster_group& cluster, const float* __restrict__ W, const float* __restrict__ bias,
+                                                const float* x, float* out, float* part, int K, int H, int rank) {
+    const int Hs = H / kActCluster, c4 = Hs >> 2;
+    const int groups = kActThreads / c4;
+    const int col4 = threadIdx.x % c4, grp = threadIdx.x / c4;
+    const float4* Wv = reinterpret_cast<const float4*>(W + rank * Hs) + col4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int k = grp; k < K; k += groups) {
+        const float4 w = __ldg(Wv + (size_t)k * (H >> 2));
+        const float xv = x[k];
+        acc.x = fmaf(xv, w.x, acc.x); acc.y = fmaf(xv, w.y, acc.y);
+        acc.z = fmaf(xv, w.z, acc.z); acc.w = fmaf(xv, w.w, acc.w);
     }
     reinterpret_cast<float4*>(part)[grp * c4 + col4] = acc;
     __syncthreads();
@@ -85,12 +121,25 @@ act_kernel(dmdqn_dims d, Layout L, const float* __restrict__ theta, const float*
     float* h2 = h1 + H;          // [H]
     float* part = h2 + H;        // [groups][H/4] = [256*4]; later [4 ranks][4] head partials on rank 0
     const float* P = theta + (size_t)(d.n_nets == 1 ? 0 : a) * L.stride;
-    for (int c = threadIdx.x; c < Dp; c += kActThreads)
-        xs[c] = c < d.obs_dim ? obs[(size_t)a * stride + c] : 0.f;
-    __syncthreads();
     constexpr int C4 = H / kActCluster / 4, GROUPS = kActThreads / C4;
-    gemv_slice<(96 + GROUPS - 1) / GROUPS>(cluster, P + L.w1, P + L.b1, xs, h1, part, Dp, H, rank);
-    gemv_slice<(H + GROUPS - 1) / GROUPS>(cluster, P + L.w2, P + L.b2, h1, h2, part, H, H, rank);
+    if constexpr (H <= 256) {
+        float4 w1[(96 + GROUPS - 1) / GROUPS], w2[(H + GROUPS - 1) / GROUPS];
+        load_slice(w1, P + L.w1, Dp, H, rank);           // 4P bytes per action: all of this CTA's share is requested here
+        load_slice(w2, P + L.w2, H, H, rank);
+        for (int c = threadIdx.x; c < Dp; c += kActThreads)
+            xs[c] = c < d.obs_dim ? obs[(size_t)a * stride + c] : 0.f;
+        __syncthreads();
+        gemv_slice(cluster, w1, P + L.b1, xs, h1, part, Dp, H, rank);
+        gemv_slice(cluster, w2, P + L.b2, h1, h2, part, H, H, rank);
+    } else {                                             // H = 512: a layer's slice does not fit the register file at once
+        for (int c = threadIdx.x; c < Dp; c += kActThreads)
+            xs[c] = c < d.obs_dim ? obs[(size_t)a * stride + c] : 0.f;
+        __syncthreads();
+        float4 w1[(96 + GROUPS - 1) / GROUPS];
+        load_slice(w1, P + L.w1, Dp, H, rank);
+        gemv_slice(cluster, w1, P + L.b1, xs, h1, part, Dp, H, rank);
+        gemv_slice_loop(cluster, P + L.w2, P + L.b2, h1, h2, part, H, H, rank);
+    }
 
     // layer 3: q[a] = b3[a] + sum_j h2[j] * W3[j][a]: every CTA sums its H/4 rows (warp butterfly, warps in
     // order), rank 0 adds the four partials in rank order

@@ -36,6 +36,12 @@ WORKLOADS = {
 D, A = 89, 4
 
 
+def workload_name(key):
+    w = WORKLOADS[key]
+    return (f"{key}: {w['agents']} agents/GPU ({w['grid']}), batch {w['batch']}, hidden [{w['hidden']},{w['hidden']}], obs 89, "
+            f"actions 4, replay capacity {w['capacity']}, independent networks")
+
+
 def agent_cfg(w, precision="fp32"):
     return {"learning_rate": 5e-4, "gamma": 0.99, "replay_buffer_size": w["capacity"], "batch_size": w["batch"],
             "target_update_frequency": 1000, "nn_layers": [w["hidden"], w["hidden"]],    # config/agent_config.yaml
@@ -312,9 +318,7 @@ def run_ours(args):
         "metric": "agent-updates/sec", "value": value, "unit": "agent-updates/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic replay (observation-shaped integers, full rings), random-init weights",
-        "config": {"workload": f"{args.workload}: {w['agents']} agents/GPU ({w['grid']}), batch {w['batch']}, hidden "
-                               f"[{w['hidden']},{w['hidden']}], obs 89, actions 4, replay capacity {w['capacity']}, "
-                               f"independent networks, precision {args.precision}",
+        "config": {"workload": workload_name(args.workload), "precision": args.precision,
                    "agents_total": total_agents, "sharding": "agent ranges, no collectives" if world > 1 else "single GPU",
                    "l2_policy": "working set (replay ring 5.9 GB, theta/m/v 368 MB, scratch 200 MB at cfg3) exceeds the 126 MB L2",
                    "sample_mode": "fisher_yates (device draws)"},
@@ -413,8 +417,7 @@ def run_reference(args):
         "impl": "reference", "metric": "agent-updates/sec", "value": v, "unit": "agent-updates/s",
         "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": K, "warmup": W, "ms_per_step": el / K * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic replay",
-        "config": {"workload": f"{args.workload}: {w['agents']} agents ({w['grid']}), batch {w['batch']}, hidden "
-                               f"[{w['hidden']},{w['hidden']}], obs 89, actions 4, replay capacity {w['capacity']}"},
+        "config": {"workload": workload_name(args.workload), "precision": "fp32 (CPU torch oracle)"},
         "cpu_baseline": {"value": v, "unit": "agent-updates/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "agent-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}), flush=True)

@@ -31,7 +31,7 @@ DEFAULTS = {  # DQNAgent defaults, dqn_agent.py:112-127
     "target_update_frequency": 1000, "nn_layers": [64, 64],
     # new keys (SURVEY.md section 5 "Config / flags"); defaults = reference behaviour
     "tau": None, "loss": "mse", "normalize_rewards": True, "double_dqn": True, "adam_form": "keras",
-    "share_parameters": False, "precision": "fp32", "sample_mode": "fisher_yates",
+    "share_parameters": False, "precision": "auto", "sample_mode": "fisher_yates",
 }
 
 
@@ -82,6 +82,9 @@ class AgentGroup:
                            self.action_size, self.batch_size, self.capacity)
         self.layout = N.Layout()
         N.check(self.lib.dmdqn_param_layout(C.byref(self.dims), C.byref(self.layout)))
+        if cfg["precision"] == "auto":   # fp32-class either way (same 1e-5 bar): tcgen05 3xTF32 where that path is built, FFMA elsewhere
+            cfg["precision"] = "tf32x3" if (self.hidden == 256 and self.obs_stride in (32, 64, 96) and self.batch_size % 4 == 0
+                                            and self.batch_size <= 4096) else "fp32"
         self.hp = N.HParams(
             float(cfg["gamma"]), float(cfg["learning_rate"]), 0.9, 0.999,
             1e-7 if cfg["adam_form"] == "keras" else 1e-8,

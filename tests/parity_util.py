@@ -39,7 +39,8 @@ def adam_close(got, theta0, m0, v0, grad, alpha, eps, rtol=RTOL, what=""):
     loose = np.abs(got - ref) > tol
     assert not bad.any(), f"{what}: {bad.sum()} / {bad.size} outside the Adam interval, worst {np.abs(got - ref).max():.3e}"
     # the ill-conditioned elements must stay a vanishing minority
-    assert loose.mean() < 1e-3, f"{what}: {loose.sum()} / {loose.size} elements needed the gradient-interval allowance"
+    # (a floor of 3 elements: on a 256-element bias vector one ill-conditioned element is already 0.4 %)
+    assert loose.sum() <= max(3, 1e-3 * loose.size), f"{what}: {loose.sum()} / {loose.size} elements needed the gradient-interval allowance"
     return int(loose.sum())
 
 

@@ -14,10 +14,11 @@
 //   * activations: hi part in shared memory as the next layer's A operand (K-major, 128-byte
 //     swizzle), lo part in TMEM columns 256..511 (A-from-TMEM MMA) -- 128 KB each, so the full
 //     512 TMEM columns are used: 256 accumulator + 256 operand;
-//   * weights: 8 x 256 (x.W) or 256 x 16 (d.W^T) chunks streamed from L2 with cp.async straight into
-//     the UMMA canonical layout (MN-major "128B_BASE32B" / K-major 64-byte swizzle), split hi/lo in
-//     place by the thread that copied them; a full/empty mbarrier ring (4 / 2 stages) couples the 8
-//     producer warps to the single MMA-issuing lane (warp 8), tcgen05.commit frees a stage;
+//   * weights: 8 x 256 (x.W) or 256 x 16 (d.W^T) chunks streamed from L2 through registers (loads two own
+//     chunks ahead) into the UMMA canonical layout (MN-major "128B_BASE32B" / K-major 64-byte swizzle),
+//     split hi/lo by the thread that loaded them; a full/empty mbarrier ring (4 / 2 stages, one producer
+//     group per stage) couples the 8 producer warps to the single MMA-issuing lane (warp 8),
+//     tcgen05.commit frees a stage;
 //   * epilogues read the accumulator with tcgen05.ld (thread = batch row), so bias/ReLU, the
 //     4-wide head (layer 3), TD target, loss gradient and dh2 are computed per row in registers.
 #include "common.cuh"
@@ -932,15 +933,15 @@ __device__ __forceinline__ void wg_item(int q, int G, int& g, int& t) {
 }
 
 // dW tile: D[128 x 256] = A^T-operand * D-operand over K = batch, Adam in the epilogue.
-//   t = 0,1: dW2 rows t*128.. : A = h1^T scratch [m][k] (K-major SW64), B = dh2^T rebuilt [n][k] (K-major SW64)
+//   t = 0,1: dW2 rows t*128.. : A = h1^T scratch [m][k] (K-major SW64), B = dh2 rebuilt [k][n] (MN-major)
 //   t = 2  : dW1 rows 0..95   : A = s gathered from the ring [k][m] (MN-major),  B = dh1^T scratch (K-major SW64);
 //            A column m = obs_stride is set to 1, so row obs_stride of the tile is db1 = sum_k dh1[k][:] for free;
 //            the epilogue of this item also folds the per-row-tile partials of db2 / dW3 / db3 (from K4a) and
 //            emits the metrics.
 // Persistent and warp-specialised: a CTA walks its items q = blockIdx.x, + gridDim.x, ...;
 //   warps 0-7  stage operand chunks (global -> registers -> hi | lo -> shared memory, 3 stages) and run ahead
-//              into the next item while
-//   warp 16    (one lane) issues the tcgen05.mma of a chunk as soon as it is staged, alternating between two
+//              into the next item;
+//   lane 0 of warp 0 also issues the tcgen05.mma of the chunk staged one step earlier, alternating between two
 //              TMEM accumulators (columns 0..255 / 256..511), and
 //   warps 8-15 read a finished accumulator and do the Adam read-modify-write of theta / m / v / theta_tgt.
 // The epilogue is pure HBM traffic (24 bytes per parameter) and the GEMM needs almost none, so running them

@@ -286,13 +286,9 @@ def run_ours(args):
     h2d = sb["bytes"]
     d2h = sb["metrics_host"].numel() * sb["metrics_host"].element_size()
 
-    done_ev = torch.cuda.Event()
-
     def e2e_step():
         m = grp.step_host(sb)                                  # remember + replay (train.py:274-292), host buffers
-        done_ev.record(stream)
-        while not done_ev.query():                             # the caller waits for the losses: poll the event instead of
-            pass                                               # a blocking stream sync (saves the wake-up latency)
+        stream.synchronize()                                   # the caller reads the losses
         return float(m[0, 0])
     for _ in range(W):
         e2e_step()

@@ -27,6 +27,14 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints "NCCL version ..." on stdout at
+# init), so the real stdout is kept on a private descriptor for the result and fd 1 is pointed at stderr.
+_JSON_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    os.write(_JSON_FD, (json.dumps(obj) + "\n").encode())
 
 WORKLOADS = {
     "cfg2": dict(agents=16, batch=64, hidden=256, capacity=30000, grid="4x4"),
@@ -345,7 +353,7 @@ def run_ours(args):
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(w, budget_s=args.cpu_budget)
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -413,14 +421,14 @@ def run_reference(args):
     v = sample_agents * K / el
     sample = (f"each step = one learn sweep over {sample_agents} of {w['agents']} agents (full {w['capacity']}-deep deque buffers); "
               "sequential per-agent loop")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "agent-updates/sec", "value": v, "unit": "agent-updates/s",
         "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": K, "warmup": W, "ms_per_step": el / K * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic replay",
         "config": {"workload": workload_name(args.workload), "precision": "fp32 (CPU torch oracle)"},
         "cpu_baseline": {"value": v, "unit": "agent-updates/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "agent-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}), flush=True)
+        "gpu_launches": 0})
 
 
 def main():

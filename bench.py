@@ -272,8 +272,8 @@ def run_ours(args):
     zi = torch.zeros(n, dtype=torch.int32, device=grp.device); zd = torch.zeros(n, dtype=torch.float64, device=grp.device)
     zv = torch.zeros(n, dtype=torch.uint8, device=grp.device)
     side = max(r for r in range(1, int(n ** 0.5) + 1) if n % r == 0)          # this GPU's shard of the grid: side x n/side
-    from oracle.featurize import grid_neighbors                               # index table only (not on the timed path)
-    nbr = torch.as_tensor(grid_neighbors(side, n // side)).to(grp.device)
+    from dmdqn_b200.parallel import grid_neighbor_table
+    nbr = torch.as_tensor(grid_neighbor_table(side, n // side)).to(grp.device)
     assert nbr.shape[0] == n
     feat_ms = timed(lambda: grp.featurize(halting, zi, zd, zd, 0.0, zv, nbr), 4 * K)
     act_bytes = n * 4 * fb["params"]

@@ -28,6 +28,20 @@ def shard_range(n_total: int, world: int, rank: int) -> tuple[int, int]:
     return start, start + base + (1 if rank < extra else 0)
 
 
+def grid_neighbor_table(rows: int, cols: int):
+    """Neighbour rows ``[rows*cols, 4]`` (int32, n,s,e,w; -1 = none) of a row-major ``J_r_c`` grid -- the table
+    ``dmdqn_featurize`` takes instead of junction-id strings (order_lanes.py:399-404: n=(r-1,c), s=(r+1,c),
+    e=(r,c+1), w=(r,c-1))."""
+    import numpy as np
+    r, c = np.divmod(np.arange(rows * cols), cols)
+    out = np.full((rows * cols, 4), -1, np.int32)
+    for k, (dr, dc) in enumerate(((-1, 0), (1, 0), (0, 1), (0, -1))):
+        rr, cc = r + dr, c + dc
+        ok = (rr >= 0) & (rr < rows) & (cc >= 0) & (cc < cols)
+        out[ok, k] = (rr * cols + cc)[ok]
+    return out
+
+
 def shard_seed(seed: int, agent_global_index: int) -> int:
     """Per-agent init seed that does not depend on how agents are sharded."""
     return int(seed) + int(agent_global_index)

@@ -25,6 +25,13 @@ def test_shard_range_partitions_agents():
     assert shard_seed(7, 1536) == 1543
 
 
+def test_grid_neighbor_table_matches_oracle():
+    from dmdqn_b200.parallel import grid_neighbor_table
+    from oracle.featurize import grid_neighbors
+    for r, c in ((1, 1), (3, 3), (4, 7), (16, 32)):
+        assert np.array_equal(grid_neighbor_table(r, c), grid_neighbors(r, c))
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))

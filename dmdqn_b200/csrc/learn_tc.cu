@@ -478,13 +478,16 @@ __device__ __forceinline__ void epi_hidden(uint32_t sbase, uint32_t tmem, const 
     for (int cc = 0; cc < 4; ++cc) {
         const int c0 = e.half * 128 + cc * 32;
         float v[32], lo[32];
+        float4 bq[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)       // every bias load of the block before the first (volatile) store below
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bq[j].x), "=f"(bq[j].y), "=f"(bq[j].z), "=f"(bq[j].w)
+                         : "r"(sbase + bias_off + (uint32_t)(c0 + 4 * j) * 4));
         tmem_ld32(tmem + e.lane_addr + (uint32_t)c0, v);
         uint32_t m = 0;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-            float4 b;
-            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
-                         : "r"(sbase + bias_off + (uint32_t)(c0 + j) * 4));
+            const float4 b = bq[j >> 2];
             float4 x = make_float4(fmaxf(v[j] + b.x, 0.f), fmaxf(v[j + 1] + b.y, 0.f), fmaxf(v[j + 2] + b.z, 0.f),
                                    fmaxf(v[j + 3] + b.w, 0.f));
             m |= (x.x > 0.f ? 1u : 0u) << j | (x.y > 0.f ? 1u : 0u) << (j + 1) | (x.z > 0.f ? 1u : 0u) << (j + 2) |
@@ -822,16 +825,15 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A) {
 #pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {
         const int c0 = e.half * 128 + cc * 32;
-        float lo[32];
+        float lo[32], wv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j)      // all 32 loads first: the volatile stores below would otherwise serialise load -> store chains
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(wv[j]) : "r"(sbase + Fwd::W3S + (uint32_t)(c0 + j) * 16 + (uint32_t)ai * 4));
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
             float x[4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                float w;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w) : "r"(sbase + Fwd::W3S + (uint32_t)(c0 + j + t) * 16 + (uint32_t)ai * 4));
-                x[t] = ((mask2[cc] >> (j + t)) & 1u) ? gi * w : 0.f;
-            }
+            for (int t = 0; t < 4; ++t) x[t] = ((mask2[cc] >> (j + t)) & 1u) ? gi * wv[j + t] : 0.f;
             const float4 x4 = make_float4(x[0], x[1], x[2], x[3]);
             float4 hi, l4;
             split4<PASSES>(x4, hi, l4);

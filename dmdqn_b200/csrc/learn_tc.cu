@@ -752,12 +752,10 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A) {
             for (int k = 0; k < 4; ++k) A.q_all[(sb + gr) * 4 + k] = q[k];
         }
     }
-    float* rowf = sf + Fwd::ROWF / 4;                     // [0]: loss term, [1..4]: q per row, [5]: action, [6]: g, [7]: warp partials
+    float* rowf = sf + Fwd::ROWF / 4;                     // [1..4]: per row float4 g * onehot(action), [7]: warp partials
     if (e.half == 0) {
-        rowf[e.row] = term;
-        for (int k = 0; k < 4; ++k) rowf[(1 + k) * BM + e.row] = valid ? q[k] : 0.f;
-        reinterpret_cast<int*>(rowf)[5 * BM + e.row] = valid ? ai : -1;
-        rowf[6 * BM + e.row] = gi;
+        // dL/dq of this row as a 4-vector (one non-zero): the column loop below then needs no selects
+        reinterpret_cast<float4*>(rowf + BM)[e.row] = make_float4(ai == 0 ? gi : 0.f, ai == 1 ? gi : 0.f, ai == 2 ? gi : 0.f, ai == 3 ? gi : 0.f);
         // per-tile loss / metric / db3 partials: butterfly over the 32 rows of this warp (fixed order), then
         // the four warp partials are added in warp order by thread 0
         float red[11];
@@ -794,16 +792,23 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A) {
         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w3.x), "=f"(w3.y), "=f"(w3.z), "=f"(w3.w)
                      : "r"(sbase + Fwd::W3S + (uint32_t)j * 16));
         float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, s2 = 0.f;
-#pragma unroll 4
-        for (int i = 0; i < BM; ++i) {
-            float h;
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(h) : "r"(sbase + Fwd::R + off_k128(BM, i, j)));
-            const float gv = rowf[6 * BM + i];
-            const int a = reinterpret_cast<int*>(rowf)[5 * BM + i];
-            const float tv = h * gv;
-            d0 += a == 0 ? tv : 0.f; d1 += a == 1 ? tv : 0.f; d2 += a == 2 ? tv : 0.f; d3 += a == 3 ? tv : 0.f;
-            const float w = a == 0 ? w3.x : a == 1 ? w3.y : a == 2 ? w3.z : w3.w;
-            s2 += h > 0.f ? gv * w : 0.f;
+        // h2 column j of the tile: K-major SW128, the 16-byte piece index is xor-ed with row % 8
+        const uint32_t hcol = sbase + Fwd::R + (uint32_t)(j >> 5) * ATOM + (uint32_t)((j & 3) << 2);
+        const uint32_t jq = (uint32_t)((j & 31) >> 2);
+        const uint32_t gsel = sbase + Fwd::ROWF + BM * 4;
+#pragma unroll 1
+        for (int i0 = 0; i0 < BM; i0 += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u;
+                float h;
+                float4 gs;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(h) : "r"(hcol + (uint32_t)i * 128u + ((jq ^ (uint32_t)u) << 4)));
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(gs.x), "=f"(gs.y), "=f"(gs.z), "=f"(gs.w) : "r"(gsel + (uint32_t)i * 16u));
+                d0 = fmaf(h, gs.x, d0); d1 = fmaf(h, gs.y, d1); d2 = fmaf(h, gs.z, d2); d3 = fmaf(h, gs.w, d3);
+                const float gw = fmaf(gs.w, w3.w, fmaf(gs.z, w3.z, fmaf(gs.y, w3.y, gs.x * w3.x)));   // = g * W3[j][a]: the other terms are exact zeros
+                s2 += h > 0.f ? gw : 0.f;
+            }
         }
         const size_t pt = (size_t)g * A.tiles + rt;
         reinterpret_cast<float4*>(A.part_w3 + pt * H * 4)[j] = make_float4(d0, d1, d2, d3);

@@ -7,8 +7,10 @@
 // are split by columns over the four CTAs of a cluster (each streams a [K][H/4] slice of W1 and W2
 // with 16-byte loads, every load of a layer in flight at once), the activation slices are exchanged
 // through distributed shared memory, and the K split over thread groups is combined in a fixed order
-// (deterministic Q-values).  Four CTAs per agent give 1024 CTAs at 256 agents: all resident at once
-// on 148 SMs, so the launch is one latency chain deep instead of a 1.7-wave tail of long CTAs.
+// (deterministic Q-values).  Four CTAs per agent give 1024 CTAs at 256 agents; the launch bound asks for four
+// resident CTAs per SM (64 registers: measured best -- 2 / 3 / 4 / 5 / 6 per SM give 24 / 21 / 20 / 27 / 33 us at 256
+// agents): an agent is a chain of two HBM latencies, three cluster barriers and serial reductions, so the number of
+// agents in flight matters more than the number of loads each thread keeps in flight.
 // Exploring agents skip the forward pass, as the reference does.
 #include <cooperative_groups.h>
 #include "common.cuh"
@@ -101,7 +103,7 @@ __device__ __forceinline__ void gemv_slice_loop(cg::cluster_group& cluster, cons
 }
 
 template <int H_>
-__global__ void __cluster_dims__(kActCluster, 1, 1) __launch_bounds__(kActThreads, 2)
+__global__ void __cluster_dims__(kActCluster, 1, 1) __launch_bounds__(kActThreads, 4)
 act_kernel(dmdqn_dims d, Layout L, const float* __restrict__ theta, const float* __restrict__ obs, int stride,
            const double* __restrict__ eps, const uint32_t* __restrict__ w_explore,
            const uint32_t* __restrict__ w_action, int32_t* __restrict__ actions, float* __restrict__ q_out) {

@@ -40,6 +40,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         cmd.insert(1, "-DTC_EXP=" + os.environ.get("DMDQN_TC_EXP", "0"))
     if os.environ.get("DMDQN_TC_EXP_ONLY"):        # experiment switch without the stamps (results are wrong by design)
         cmd.insert(1, "-DWG_EXP=" + os.environ["DMDQN_TC_EXP_ONLY"])
+    if os.environ.get("DMDQN_NVCC_DEFINES"):       # e.g. "DMDQN_NO_ROW_PREFETCH": A/B switches for tools/exp_timing.sh
+        for dname in os.environ["DMDQN_NVCC_DEFINES"].split(","):
+            cmd.insert(1, "-D" + dname)
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -12,12 +12,17 @@ seeded reference run and a seeded facade run pick the same actions and transitio
 """
 from __future__ import annotations
 
+import logging
 import random
 
 import numpy as np
 import torch
 
+from . import epsilon as epsilon_schedules
 from .group import AgentGroup
+
+
+logger = logging.getLogger("dmdqn_logger")        # the reference's logger name (log_config.py)
 
 
 class ReplayBuffer:
@@ -69,10 +74,9 @@ class _Network:
 
     def __call__(self, states) -> torch.Tensor:
         """Q-values ``[n, A]`` for ``states [n, D]`` (one act-kernel launch per row)."""
-        if self._which != "online":
-            raise NotImplementedError("forward through the target network is internal to learn()")
         x = torch.as_tensor(states, dtype=torch.float32).reshape(-1, self._g.state_size)
-        return torch.stack([self._g.act(row[None], return_q=True)[1][0, : self._g.action_size] for row in x])
+        target = self._which == "target"
+        return torch.stack([self._g.act(row[None], return_q=True, target=target)[1][0, : self._g.action_size] for row in x])
 
 
 class DQNAgent:
@@ -88,7 +92,12 @@ class DQNAgent:
         self.epsilon_min = config.get("epsilon_min", 0.01)
         self.epsilon_decay_steps = config.get("epsilon_decay_steps", 100000)
         self.epsilon_decay_rate = ((self.epsilon - self.epsilon_min) / self.epsilon_decay_steps
-                                   if self.epsilon_decay_steps > 0 else 0)
+                                   if self.epsilon_decay_steps > 0 else 0)      # experimental/agent.py:82-84
+        # 'reference' = the hard-coded exponential schedule of src/agents (:258-261, yaml epsilon_* keys ignored);
+        # 'linear' = the variant's decay after every action (experimental/agent.py:140-144)
+        self.epsilon_schedule = config.get("epsilon_schedule", "reference")
+        if self.epsilon_schedule not in epsilon_schedules.KINDS:
+            raise ValueError(f"epsilon_schedule={self.epsilon_schedule!r}: expected 'reference' or 'linear'")
         self.buffer_size = config.get("replay_buffer_size", 10000)
         self.batch_size = config.get("batch_size", 128)
         self.target_update_frequency = config.get("target_update_frequency", 1000)
@@ -105,14 +114,26 @@ class DQNAgent:
         self.last_metrics = None
 
     # -- act -----------------------------------------------------------------------------
+    def update_epsilon_before_action(self) -> float:
+        """The src/agents schedule, evaluated before the explore draw (:258-261); a no-op for 'linear'."""
+        self.epsilon = epsilon_schedules.before_action(self.epsilon_schedule, self.epsilon, self.epsilon_min,
+                                                       self.global_step_count)
+        return self.epsilon
+
+    def update_epsilon_after_action(self) -> float:
+        """The variant's linear decay, applied after the action was chosen (experimental/agent.py:140-144)."""
+        self.epsilon = epsilon_schedules.after_action(self.epsilon_schedule, self.epsilon, self.epsilon_min,
+                                                      self.epsilon_decay_rate)
+        return self.epsilon
+
     def select_action(self, state_tensor) -> int:
-        if self.global_step_count < 8000:                                   # :258-261
-            self.epsilon = 1.0
-        elif self.epsilon > self.epsilon_min:
-            self.epsilon = max(0.01, 1.0 * np.exp(-(self.global_step_count - 8000) / 16000))
+        self.update_epsilon_before_action()
         if np.random.rand() < self.epsilon:                                 # :263-265
-            return np.random.randint(0, self.action_size)
-        return self.select_greedy_action(state_tensor)
+            action = np.random.randint(0, self.action_size)
+        else:
+            action = self.select_greedy_action(state_tensor)
+        self.update_epsilon_after_action()
+        return action
 
     def select_greedy_action(self, state_tensor) -> int:
         return int(self._g.act(torch.as_tensor(state_tensor, dtype=torch.float32).reshape(1, -1)).item())
@@ -151,15 +172,16 @@ class DQNAgent:
     def save_model(self, filepath) -> None:                                 # :401-409 (online weights only)
         try:
             torch.save({"weights": self._g.get_weights(0), "nn_layers": self.nn_layers}, filepath)
-        except Exception:
-            pass
+        except Exception as exc:                                            # the reference logs and carries on (:408-409)
+            logger.error("Agent %s: error saving model to %s: %s", self.agent_id, filepath, exc)
 
     def load_model(self, filepath) -> bool:                                 # :411-422
         try:
             blob = torch.load(filepath, weights_only=True)
             self._g.set_weights(0, blob["weights"], sync_target=True)
             return True
-        except Exception:
+        except Exception as exc:
+            logger.error("Agent %s: error loading model from %s: %s", self.agent_id, filepath, exc)
             return False
 
     def get_epsilon(self) -> float:                                         # :424-426

@@ -124,22 +124,39 @@ act_kernel(dmdqn_dims d, Layout L, const float* __restrict__ theta, const float*
     float* part = h2 + H;        // [groups][H/4] = [256*4]; later [4 ranks][4] head partials on rank 0
     const float* P = theta + (size_t)(d.n_nets == 1 ? 0 : a) * L.stride;
     constexpr int C4 = H / kActCluster / 4, GROUPS = kActThreads / C4;
+    // The register-resident W1 slice is sized for the yaml observation (89 -> stride 96); wider observations
+    // (stride 112 / 128, accepted by validate_dims and by the learn kernels) stream layer 1 row by row instead.
+    constexpr int kRegRows = 96;
     if constexpr (H <= 256) {
-        float4 w1[(96 + GROUPS - 1) / GROUPS], w2[(H + GROUPS - 1) / GROUPS];
-        load_slice(w1, P + L.w1, Dp, H, rank);           // 4P bytes per action: all of this CTA's share is requested here
-        load_slice(w2, P + L.w2, H, H, rank);
-        for (int c = threadIdx.x; c < Dp; c += kActThreads)
-            xs[c] = c < d.obs_dim ? obs[(size_t)a * stride + c] : 0.f;
-        __syncthreads();
-        gemv_slice(cluster, w1, P + L.b1, xs, h1, part, Dp, H, rank);
-        gemv_slice(cluster, w2, P + L.b2, h1, h2, part, H, H, rank);
+        if (Dp <= kRegRows) {
+            float4 w1[(kRegRows + GROUPS - 1) / GROUPS], w2[(H + GROUPS - 1) / GROUPS];
+            load_slice(w1, P + L.w1, Dp, H, rank);       // 4P bytes per action: all of this CTA's share is requested here
+            load_slice(w2, P + L.w2, H, H, rank);
+            for (int c = threadIdx.x; c < Dp; c += kActThreads)
+                xs[c] = c < d.obs_dim ? obs[(size_t)a * stride + c] : 0.f;
+            __syncthreads();
+            gemv_slice(cluster, w1, P + L.b1, xs, h1, part, Dp, H, rank);
+            gemv_slice(cluster, w2, P + L.b2, h1, h2, part, H, H, rank);
+        } else {
+            float4 w2[(H + GROUPS - 1) / GROUPS];
+            load_slice(w2, P + L.w2, H, H, rank);
+            for (int c = threadIdx.x; c < Dp; c += kActThreads)
+                xs[c] = c < d.obs_dim ? obs[(size_t)a * stride + c] : 0.f;
+            __syncthreads();
+            gemv_slice_loop(cluster, P + L.w1, P + L.b1, xs, h1, part, Dp, H, rank);
+            gemv_slice(cluster, w2, P + L.b2, h1, h2, part, H, H, rank);
+        }
     } else {                                             // H = 512: a layer's slice does not fit the register file at once
         for (int c = threadIdx.x; c < Dp; c += kActThreads)
             xs[c] = c < d.obs_dim ? obs[(size_t)a * stride + c] : 0.f;
         __syncthreads();
-        float4 w1[(96 + GROUPS - 1) / GROUPS];
-        load_slice(w1, P + L.w1, Dp, H, rank);
-        gemv_slice(cluster, w1, P + L.b1, xs, h1, part, Dp, H, rank);
+        if (Dp <= kRegRows) {
+            float4 w1[(kRegRows + GROUPS - 1) / GROUPS];
+            load_slice(w1, P + L.w1, Dp, H, rank);
+            gemv_slice(cluster, w1, P + L.b1, xs, h1, part, Dp, H, rank);
+        } else {
+            gemv_slice_loop(cluster, P + L.w1, P + L.b1, xs, h1, part, Dp, H, rank);
+        }
         gemv_slice_loop(cluster, P + L.w2, P + L.b2, h1, h2, part, H, H, rank);
     }
 

@@ -36,6 +36,32 @@ int validate_dims(const dmdqn_dims* d) {
     return DMDQN_OK;
 }
 
+int device_sm_count(int* n_sm) {
+    static int cache[kMaxDevices] = {};
+    int dev = 0;
+    DMDQN_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices || !cache[dev]) {
+        int n = 0;
+        DMDQN_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+        if (dev >= 0 && dev < kMaxDevices) cache[dev] = n;
+        *n_sm = n;
+        return DMDQN_OK;
+    }
+    *n_sm = cache[dev];
+    return DMDQN_OK;
+}
+
+int opt_in_dynamic_smem(const void* kernel, size_t bytes, size_t (&cache)[kMaxDevices]) {
+    if (bytes <= 48 * 1024) return DMDQN_OK;
+    int dev = 0;
+    DMDQN_CUDA(cudaGetDevice(&dev));
+    const bool cached = dev >= 0 && dev < kMaxDevices;
+    if (cached && cache[dev] >= bytes) return DMDQN_OK;
+    DMDQN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (cached) cache[dev] = bytes;
+    return DMDQN_OK;
+}
+
 static int check_workspace(const dmdqn_dims* dims, void* ws, size_t bytes, Workspace* out) {
     int rc = validate_dims(dims);
     if (rc) return rc;

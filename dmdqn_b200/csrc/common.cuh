@@ -111,6 +111,14 @@ inline Workspace make_workspace(const dmdqn_dims& d) {
 
 int validate_dims(const dmdqn_dims* d);
 
+// Per-DEVICE launch state.  The dynamic shared-memory opt-in (cudaFuncSetAttribute) and the SM count belong to a
+// device, not to the process: a host that drives several GPUs from one process (one AgentGroup per device) must
+// opt in on each of them.  `cache` is a zero-initialised static array owned by the call site, indexed by device
+// ordinal; the worst a race between two host threads can do is set the same attribute twice.
+constexpr int kMaxDevices = 64;
+int device_sm_count(int* n_sm);
+int opt_in_dynamic_smem(const void* kernel, size_t bytes, size_t (&cache)[kMaxDevices]);
+
 // Launchers implemented in the .cu files.
 int launch_featurize(int32_t n, const int32_t* halting, const int32_t* phase, const double* next_switch,
                      const double* phase_dur, double sim_time, const uint8_t* signal_valid,

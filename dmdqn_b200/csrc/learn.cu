@@ -640,13 +640,10 @@ int launch_learn_h(const LearnArgs& A, int stages, cudaStream_t s) {
     using T = Tile<H>;
     const size_t smem = Smem<H>::bytes(A.d.obs_stride);
     const size_t smem_w = sizeof(float) * 2 * T::KC * ((T::BM + 4) + T::LDW);
-    static size_t configured = 0;
-    if (smem > configured) {
-        DMDQN_CUDA(cudaFuncSetAttribute(target_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        DMDQN_CUDA(cudaFuncSetAttribute(online_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        DMDQN_CUDA(cudaFuncSetAttribute(wgrad_adam_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
-        configured = smem;
-    }
+    static size_t cfg_t[kMaxDevices] = {}, cfg_o[kMaxDevices] = {}, cfg_w[kMaxDevices] = {};    // per device, not per process
+    if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void*>(target_kernel<H>), smem, cfg_t)) return rc;
+    if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void*>(online_kernel<H>), smem, cfg_o)) return rc;
+    if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void*>(wgrad_adam_kernel<H>), smem_w, cfg_w)) return rc;
     const int grid = A.d.n_nets * A.tiles;
     if (stages & DMDQN_STAGE_TARGET) {
         target_kernel<H><<<grid, T::NT, smem, s>>>(A);

@@ -1348,13 +1348,10 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A) {
 template <int PASSES>
 int launch_tc(const TcArgs& A, int stages, cudaStream_t s) {
     const size_t smem_f = Fwd::TOTAL + 1024, smem_w = Wg::TOTAL + 1024;
-    static bool configured = false;
-    if (!configured) {
-        DMDQN_CUDA(cudaFuncSetAttribute(tc_target_kernel<PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
-        DMDQN_CUDA(cudaFuncSetAttribute(tc_online_kernel<PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
-        DMDQN_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
-        configured = true;
-    }
+    static size_t cfg_t[kMaxDevices] = {}, cfg_o[kMaxDevices] = {}, cfg_w[kMaxDevices] = {};    // per device, not per process
+    if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void*>(tc_target_kernel<PASSES>), smem_f, cfg_t)) return rc;
+    if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void*>(tc_online_kernel<PASSES>), smem_f, cfg_o)) return rc;
+    if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void*>(tc_wgrad_kernel<PASSES>), smem_w, cfg_w)) return rc;
     const int grid = A.d.n_nets * A.tiles;
     if (stages & DMDQN_STAGE_TARGET) {
         tc_target_kernel<PASSES><<<2 * grid, NT_F, smem_f, s>>>(A);
@@ -1365,12 +1362,8 @@ int launch_tc(const TcArgs& A, int stages, cudaStream_t s) {
         DMDQN_CUDA(cudaGetLastError());
     }
     if (stages & DMDQN_STAGE_WGRAD) {
-        static int n_sm = 0;
-        if (!n_sm) {
-            int dev = 0;
-            DMDQN_CUDA(cudaGetDevice(&dev));
-            DMDQN_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        }
+        int n_sm = 0;
+        if (int rc = device_sm_count(&n_sm)) return rc;
         const int items = A.d.n_nets * 3;
         tc_wgrad_kernel<PASSES><<<items < n_sm ? items : n_sm, Wg::NTW, smem_w, s>>>(A);
         DMDQN_CUDA(cudaGetLastError());

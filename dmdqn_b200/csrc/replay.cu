@@ -216,11 +216,8 @@ int launch_sample(const dmdqn_dims& d, const dmdqn_hparams& hp, const dmdqn_repl
                   cudaStream_t s) {
     DMDQN_CHECK_ARG(d.batch <= 4096, "batch %d: the sample kernel serves batches up to 4096", d.batch);
     const size_t smem = (size_t)((d.batch + 1) & ~1) * (3 * 4 + 8);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        DMDQN_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static size_t configured[kMaxDevices] = {};
+    if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void*>(sample_kernel), smem, configured)) return rc;
     sample_kernel<<<d.n_nets, kSampleThreads, smem, s>>>(
         d, hp, rp, nets.learn_step, static_cast<const uint32_t*>(draws), learn_mask, advance,
         reinterpret_cast<int32_t*>(ws + w.rows), reinterpret_cast<float*>(ws + w.r_hat),

@@ -18,6 +18,7 @@ pointers), which is what the per-agent ``DQNAgent`` facade (agent.py) drives.
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import math
 
 import numpy as np
@@ -37,6 +38,18 @@ DEFAULTS = {  # DQNAgent defaults, dqn_agent.py:112-127
 
 def _ptr(t: torch.Tensor | None) -> int | None:
     return None if t is None else t.data_ptr()
+
+
+def _on_device(method):
+    """Native calls launch on the CURRENT device with the stream they are handed: make the group's device current
+    for the duration of the call, so a process that holds groups on several GPUs launches each on its own."""
+    @functools.wraps(method)
+    def wrapper(self, *args, **kwargs):
+        if torch.cuda.current_device() == self.device.index:
+            return method(self, *args, **kwargs)
+        with torch.cuda.device(self.device):
+            return method(self, *args, **kwargs)
+    return wrapper
 
 
 def keras_init(seed: int, state_size: int, hidden: int, action_size: int) -> list[torch.Tensor]:
@@ -77,6 +90,8 @@ class AgentGroup:
         if not torch.cuda.is_available():
             raise N.NativeError("dmdqn_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
 
         self.dims = N.Dims(self.n_agents, self.n_nets, self.state_size, self.obs_stride, self.hidden,
                            self.action_size, self.batch_size, self.capacity)
@@ -200,6 +215,7 @@ class AgentGroup:
         return self.unpack(t[net])
 
     # ------------------------------------------------------------------ K0 --------------
+    @_on_device
     def featurize(self, halting, phase, next_switch, phase_dur, sim_time, signal_valid, nbr_idx,
                   phase_lut=None, snapshot=None, local_weight=0.3, global_weight=0.7, obs_out=None):
         """Returns (obs[N,obs_stride] f32, own[N,17] f64, reward[N] f64, global_reward[1] f64), all on
@@ -223,6 +239,7 @@ class AgentGroup:
                                          _ptr(self._feat_scratch), self._stream))
         return obs, own, reward, glob
 
+    @_on_device
     def featurize_alt(self, halting_nesw, phase, next_switch, sim_time, nbr_idx_nesw, signal_valid=None, prev_own=None,
                       obs_stride: int = 76):
         """The SumoTrafficEnvironment contract (sumo_env.py:532-679): returns (obs[N,obs_stride] f32 whose first 74
@@ -243,10 +260,12 @@ class AgentGroup:
         return obs, own, reward
 
     # ------------------------------------------------------------------ K2 --------------
-    def act(self, obs, eps=None, w_explore=None, w_action=None, return_q: bool = False):
+    @_on_device
+    def act(self, obs, eps=None, w_explore=None, w_action=None, return_q: bool = False, target: bool = False):
         """Batched epsilon-greedy (dqn_agent.py:263-274).  ``eps`` None -> greedy for all.
         Draws default to the group's device generator.  Returns actions[N] int32 (device)
-        and, if asked, q[N,4] (rows of exploring agents are NaN: no forward pass ran)."""
+        and, if asked, q[N,4] (rows of exploring agents are NaN: no forward pass ran).
+        ``target=True`` runs the same kernel on the target parameters (``target_network(x)``)."""
         n = self.n_agents
         obs = self._dev(obs, torch.float32)
         if obs.dim() == 3:
@@ -260,7 +279,9 @@ class AgentGroup:
             w2 = self.draw_words((n,)) if w_action is None else self._words(w_action)
         actions = torch.empty((n,), dtype=torch.int32, device=self.device)
         q = torch.full((n, 4), float("nan"), dtype=torch.float32, device=self.device) if return_q else None
-        N.check(self.lib.dmdqn_act(C.byref(self.dims), C.byref(self.nets), _ptr(obs), obs.shape[1], _ptr(eps_t),
+        nets = self.nets if not target else N.Nets(_ptr(self.theta_tgt), _ptr(self.theta_tgt), _ptr(self.adam_m),
+                                                   _ptr(self.adam_v), _ptr(self.learn_step))
+        N.check(self.lib.dmdqn_act(C.byref(self.dims), C.byref(nets), _ptr(obs), obs.shape[1], _ptr(eps_t),
                                    _ptr(w1), _ptr(w2), _ptr(actions), _ptr(q), self._stream))
         return (actions, q) if return_q else actions
 
@@ -276,6 +297,7 @@ class AgentGroup:
         return torch.from_numpy(np.ascontiguousarray(np.asarray(w).astype(np.uint32)).view(np.int32)).to(self.device)
 
     # ------------------------------------------------------------------ K1a -------------
+    @_on_device
     def push(self, obs, act, rew, next_obs, done, mask=None) -> None:
         """One transition per agent (dqn_agent.py:312-325 for every agent at once)."""
         n = self.n_agents
@@ -321,6 +343,7 @@ class AgentGroup:
             on = on & np.asarray(torch.as_tensor(mask).cpu()).astype(bool).reshape(self.n_nets)
         return on
 
+    @_on_device
     def sample(self, draws=None, sample_mode: str | None = None):
         """ReplayBuffer.sample for every network (dqn_agent.py:59-85).  Returns
         (states[G,B,D], actions[G,B] i32, rewards[G,B], next_states[G,B,D], dones[G,B], active[G])
@@ -342,6 +365,7 @@ class AgentGroup:
         return states, actions, rewards, next_states, dones, active
 
     # ------------------------------------------------------------------ K1b+K3+K4 -------
+    @_on_device
     def learn(self, draws=None, mask=None, sample_mode: str | None = None) -> torch.Tensor:
         """One Double-DQN step for every network whose ring holds >= batch transitions
         (dqn_agent.py:328-380).  Returns metrics[G,8] on the device: loss, q_mean, q_std,
@@ -378,6 +402,7 @@ class AgentGroup:
                 "host": {k: view(host, k) for k in offs}, "dev": {k: view(dev, k) for k in offs},
                 "metrics_host": torch.zeros((g, N.METRICS_STRIDE), dtype=torch.float32).pin_memory()}
 
+    @_on_device
     def step_host(self, sb) -> torch.Tensor:
         """remember + replay for every agent from the HOST block ``sb`` (``make_step_block``): one H2D copy, push, learn,
         metrics back to ``sb["metrics_host"]`` -- all queued on the current stream by ONE library call
@@ -417,6 +442,7 @@ class AgentGroup:
             out["dh2"] = view(v.dh2, torch.float32, (g, b, self.hidden))
         return out
 
+    @_on_device
     def sync_target(self, mask=None, tau: float | None = None) -> None:
         """update_target_network (tau None, dqn_agent.py:382-384) / soft update (:389-399)."""
         mask_t = None if mask is None else self._dev(mask, torch.uint8)

@@ -59,16 +59,42 @@ class SharedParameterStep:
     gradient block (already divided by the global batch) and a [.., 8] metrics tensor whose
     column 0 is the rank's share of the loss; ``apply(grads)`` performs the update.  The two
     callables are the native calls on a GPU (``for_group``) and oracle stand-ins in the CPU
-    (gloo) tests, so the same host logic is exercised in both."""
+    (gloo) tests, so the same host logic is exercised in both.
 
-    def __init__(self, local_grads, apply, local_batch: int, group=None):
+    The learn decision is COLLECTIVE.  Whether a rank's rings hold its share of the batch
+    (dqn_agent.py:333-335 applied to the rank's shard) differs between ranks while the rings
+    fill -- ``shard_range`` gives the first ranks one agent more, masked pushes fill unevenly --
+    and a replica that stepped alone would diverge for good (theta, Adam state, the
+    target-sync counter).  So ``local_ready()`` flags are combined with a MIN all-reduce and
+    either every rank steps or none does; ``step()`` returns None for a skipped step, like
+    ``learn()`` while the buffer is short.  Rings only grow, so once every rank has been
+    ready the exchange is dropped."""
+
+    def __init__(self, local_grads, apply, local_batch: int, group=None, local_ready=None, flag_device="cpu"):
         self.local_grads, self.apply, self.local_batch, self.group = local_grads, apply, int(local_batch), group
+        self.local_ready, self.flag_device = local_ready, flag_device
+        self._all_ready = False
+        self.skipped = 0
 
     @property
     def world(self) -> int:
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
 
+    def everyone_ready(self) -> bool:
+        if self._all_ready:
+            return True
+        ready = True if self.local_ready is None else bool(self.local_ready())
+        if self.world > 1:
+            flag = torch.tensor([1 if ready else 0], dtype=torch.int32, device=self.flag_device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            ready = bool(flag.item())
+        self._all_ready = ready
+        return ready
+
     def step(self):
+        if not self.everyone_ready():
+            self.skipped += 1
+            return None
         grads, metrics = self.local_grads(self.local_batch * self.world)
         allreduce_sum_(grads, self.group)           # 4*P bytes, latency bound (1.24 MB at H=512)
         loss = allreduce_sum_(metrics[..., 0].clone(), self.group)
@@ -84,15 +110,24 @@ class SharedParameterStep:
             raise ValueError("SharedParameterStep needs share_parameters=True")
         grads = torch.zeros_like(grp.theta)
 
+        def local_ready() -> bool:
+            return bool(grp.active_host()[0])
+
         def local_grads(global_batch: int):
+            if not local_ready():                   # cannot happen after everyone_ready(); never reduce a stale block
+                grads.zero_()
+                grp.metrics.zero_()
+                return grads, grp.metrics
             d = grp.draw_words((1, grp.batch_size))
-            N.check(grp.lib.dmdqn_learn_grads(C.byref(grp.dims), C.byref(grp.hp), C.byref(grp.replay), C.byref(grp.nets),
-                                              _ptr(d), None, int(global_batch), _ptr(grads), _ptr(grp.metrics),
-                                              _ptr(grp.workspace), grp.workspace.numel(), grp._stream))
-            grp.learn_step_host += grp.active_host().astype("int64")
+            with torch.cuda.device(grp.device):
+                N.check(grp.lib.dmdqn_learn_grads(C.byref(grp.dims), C.byref(grp.hp), C.byref(grp.replay), C.byref(grp.nets),
+                                                  _ptr(d), None, int(global_batch), _ptr(grads), _ptr(grp.metrics),
+                                                  _ptr(grp.workspace), grp.workspace.numel(), grp._stream))
+            grp.learn_step_host += 1
             return grads, grp.metrics
 
         def apply(g: torch.Tensor):
-            N.check(grp.lib.dmdqn_adam_apply(C.byref(grp.dims), C.byref(grp.hp), C.byref(grp.nets), _ptr(g),
-                                             _ptr(grp.workspace), grp.workspace.numel(), grp._stream))
-        return cls(local_grads, apply, grp.batch_size, group)
+            with torch.cuda.device(grp.device):
+                N.check(grp.lib.dmdqn_adam_apply(C.byref(grp.dims), C.byref(grp.hp), C.byref(grp.nets), _ptr(g),
+                                                 _ptr(grp.workspace), grp.workspace.numel(), grp._stream))
+        return cls(local_grads, apply, grp.batch_size, group, local_ready=local_ready, flag_device=grp.device)

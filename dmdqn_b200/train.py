@@ -189,16 +189,22 @@ def train_agents(config: dict | None = None, episodes: int = EPISODES, mode: str
                 actions_host = np.array([agents[j].select_action(obs[i:i + 1, :89]) for i, j in enumerate(tl_junctions)])
                 actions = torch.as_tensor(actions_host, dtype=torch.int32)
             else:
-                eps = []
-                for j in tl_junctions:
-                    ag = agents[j]
-                    if ag.global_step_count < 8000:
-                        ag.epsilon = 1.0
-                    elif ag.epsilon > ag.epsilon_min:
-                        ag.epsilon = max(0.01, float(np.exp(-(ag.global_step_count - 8000) / 16000)))
-                    eps.append(ag.epsilon)
-                actions = group.act(obs, np.asarray(eps))
+                eps = np.asarray([agents[j].update_epsilon_before_action() for j in tl_junctions], np.float64)
+                # the reference draws rand() (and randint() when exploring) per agent, in agent order (:263-265)
+                u = np.empty(n); ra = np.zeros(n, np.int64)
+                for i in range(n):
+                    u[i] = np.random.rand()
+                    if u[i] < eps[i]:
+                        ra[i] = np.random.randint(0, group.action_size)
+                # supplied-draw contract of dmdqn_act: explore iff w < eps * 2^32; action = (w_a * A) >> 32
+                w_explore = np.where(u < eps, 0, 0xFFFFFFFF).astype(np.uint32)
+                w_action = ((ra.astype(np.uint64) << np.uint64(32)) // np.uint64(group.action_size)
+                            + np.uint64(1)).astype(np.uint32)
+                eps_dev = np.where(u < eps, 1.0, 0.0)
+                actions = group.act(obs, eps_dev, w_explore, w_action)
                 actions_host = actions.cpu().numpy()
+                for j in tl_junctions:
+                    agents[j].update_epsilon_after_action()
             for j, a in zip(tl_junctions, actions_host):                        # train.py:225-226
                 traci.trafficlight.setPhase(j, ACTION_MAP[int(a)])
             target_time = current_time + step_duration                          # train.py:229-236

@@ -92,6 +92,15 @@ def epsilon_schedule(global_step_count: int, epsilon: float, epsilon_min: float)
     return epsilon
 
 
+def epsilon_linear_step(epsilon: float, epsilon_min: float, decay_rate: float) -> float:
+    """Linear decay applied AFTER an action was selected (experimental/agent.py:140-144):
+    ``if eps > eps_min: eps -= rate`` then ``eps = max(eps_min, eps)``; rate =
+    (epsilon_start - epsilon_min) / epsilon_decay_steps (experimental/agent.py:82-84)."""
+    if epsilon > epsilon_min:
+        epsilon -= decay_rate
+    return max(epsilon_min, epsilon)
+
+
 def adam_scalars(t: int, lr: float, form: str = "keras"):
     """(alpha_t, eps_eff) such that  theta -= alpha_t * m / (sqrt(v) + eps_eff).
 
@@ -150,6 +159,9 @@ class OracleDQNAgent:
         self.epsilon = config.get("epsilon_start", 1.0)
         self.epsilon_min = config.get("epsilon_min", 0.01)
         self.epsilon_decay_steps = config.get("epsilon_decay_steps", 100000)
+        self.epsilon_decay_rate = ((self.epsilon - self.epsilon_min) / self.epsilon_decay_steps
+                                   if self.epsilon_decay_steps > 0 else 0)        # experimental/agent.py:82-84
+        self.epsilon_schedule_kind = config.get("epsilon_schedule", "reference")   # 'reference' | 'linear'
         self.buffer_size = config.get("replay_buffer_size", 10000)
         self.batch_size = config.get("batch_size", 128)
         self.target_update_frequency = config.get("target_update_frequency", 1000)
@@ -179,16 +191,23 @@ class OracleDQNAgent:
         """dqn_agent.py:246-274.  With words supplied the decision follows the
         "supplied draws" contract (oracle/replay.py); without, ``np.random`` like
         the reference."""
-        self.epsilon = epsilon_schedule(self.global_step_count, self.epsilon, self.epsilon_min)
+        linear = self.epsilon_schedule_kind == "linear"
+        if not linear:
+            self.epsilon = epsilon_schedule(self.global_step_count, self.epsilon, self.epsilon_min)
         if w_explore is None:
             explore = np.random.rand() < self.epsilon
         else:
             explore = bool(explore_decision(np.uint32(w_explore), self.epsilon))
         if explore:
             if w_action is None:
-                return int(np.random.randint(0, self.action_size))
-            return int(random_action(np.uint32(w_action), self.action_size))
-        return int(torch.argmax(self.q_values(state), dim=1)[0])  # ties -> lowest index
+                action = int(np.random.randint(0, self.action_size))
+            else:
+                action = int(random_action(np.uint32(w_action), self.action_size))
+        else:
+            action = int(torch.argmax(self.q_values(state), dim=1)[0])  # ties -> lowest index
+        if linear:      # experimental/agent.py:140-144: decay after the action was chosen
+            self.epsilon = epsilon_linear_step(self.epsilon, self.epsilon_min, self.epsilon_decay_rate)
+        return action
 
     def select_greedy_action(self, state) -> int:
         """experimental/agent.py:148-152 (used by src/scripts/test.py:88)."""

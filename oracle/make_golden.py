@@ -24,6 +24,8 @@ What is executed for real, and which fixture it lands in:
                      (src/agents/dqn_agent.py:27-89) under ``random.seed``
   ref_epsilon.npz    the epsilon schedule and explore branch of DQNAgent.select_action
                      (src/agents/dqn_agent.py:246-265)
+  ref_epsilon_linear.npz  the variant's linear epsilon decay and explore branch
+                     (src/experimental/agent.py:121-146)
   ref_env_alt.npz    SumoTrafficEnvironment._get_local_observation / _get_observations /
                      _get_neighbor_presence_vector / _calculate_rewards (src/agents/sumo_env.py:532-679)
 The MLP / learn arithmetic (TensorFlow ops) is NOT executed: MagicMock swallows it.
@@ -260,6 +262,27 @@ def golden_epsilon(dqn_agent):
     print("ref_epsilon.npz", len(steps), "steps; eps range", min(eps), max(eps))
 
 
+def golden_epsilon_linear(exp_agent):
+    """The variant's select_action (src/experimental/agent.py:121-146): linear epsilon decay applied after
+    every action, explore branch under ``np.random``.  The greedy branch returns a MagicMock (TensorFlow is
+    stubbed) and is recorded as -1."""
+    cfg = {"epsilon_start": 1.0, "epsilon_min": 0.05, "epsilon_decay_steps": 400}
+    agent = exp_agent.DQNAgent(89, 4, "J_0_0", cfg)
+    np.random.seed(11)
+    eps, explored, action = [], [], []
+    for _ in range(600):
+        act = agent.select_action(np.zeros((1, 89), np.float32))
+        is_explore = isinstance(act, (int, np.integer))
+        eps.append(agent.epsilon)
+        explored.append(is_explore)
+        action.append(int(act) if is_explore else -1)
+    np.savez_compressed(os.path.join(OUT, "ref_epsilon_linear.npz"), eps=np.array(eps, np.float64),
+                        explored=np.array(explored), action=np.array(action, np.int32),
+                        epsilon_start=np.array(1.0), epsilon_min=np.array(0.05), epsilon_decay_steps=np.array(400),
+                        decay_rate=np.array(agent.epsilon_decay_rate, np.float64))
+    print("ref_epsilon_linear.npz", len(eps), "calls; eps range", min(eps), max(eps), "explored", int(np.sum(explored)))
+
+
 def golden_env_alt(FakeTraci):
     """ref_env_alt.npz: SumoTrafficEnvironment._get_local_observation / _get_observations /
     _get_neighbor_presence_vector / _calculate_rewards (src/agents/sumo_env.py:532-679) run unmodified on an
@@ -352,6 +375,8 @@ def main():
     golden_episode(train, order_lanes, FakeTraci, sumolib, live=True, tag="live")
     golden_replay(dqn_agent)
     golden_epsilon(dqn_agent)
+    import src.experimental.agent as exp_agent            # noqa: E402  (the older variant, unmodified)
+    golden_epsilon_linear(exp_agent)
     golden_env_alt(FakeTraci)
 
 

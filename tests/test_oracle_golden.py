@@ -8,7 +8,7 @@ import pytest
 
 from oracle import featurize as F
 from oracle import replay as R
-from oracle.dqn import epsilon_schedule
+from oracle.dqn import OracleDQNAgent, epsilon_linear_step, epsilon_schedule
 
 G = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -109,6 +109,28 @@ def test_epsilon_schedule_matches_reference():
         if explored:
             np.random.randint(0, 4)
     assert z["eps"].min() < 0.05 and z["eps"].max() == 1.0
+
+
+def test_linear_epsilon_variant_matches_reference():
+    """src/experimental/agent.py:121-146 (oracle/make_golden.py golden_epsilon_linear): the oracle agent with
+    epsilon_schedule='linear' consumes np.random like the variant and lands on the same epsilons / explore actions."""
+    z = np.load(os.path.join(G, "ref_epsilon_linear.npz"))
+    cfg = {"epsilon_start": float(z["epsilon_start"]), "epsilon_min": float(z["epsilon_min"]),
+           "epsilon_decay_steps": int(z["epsilon_decay_steps"]), "epsilon_schedule": "linear", "nn_layers": [64, 64]}
+    agent = OracleDQNAgent(89, 4, "J_0_0", cfg)
+    assert agent.epsilon_decay_rate == float(z["decay_rate"])
+    np.random.seed(11)
+    greedy = 0
+    for e_ref, explored, action in zip(z["eps"], z["explored"], z["action"]):
+        a = agent.select_action(np.zeros((1, 89), np.float32))
+        assert agent.epsilon == e_ref
+        if explored:
+            assert a == int(action)
+        else:
+            greedy += 1
+            assert a == agent.select_greedy_action(np.zeros((1, 89), np.float32))
+    assert greedy > 100
+    assert epsilon_linear_step(0.05, 0.05, 0.1) == 0.05 and epsilon_linear_step(0.06, 0.05, 0.1) == 0.05
 
 
 def test_alt_env_contract_matches_reference_fixture():

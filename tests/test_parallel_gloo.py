@@ -109,3 +109,57 @@ def test_shared_parameter_allreduce_equals_single_process_big_batch():
     # replicas stay identical
     for w0, w1 in zip(results[0][2], results[1][2]):
         assert np.array_equal(w0, w1)
+
+
+def _uneven_worker(rank, world, port, q):
+    """9 agents on 2 ranks (5 + 4), local batch 20: rank 0 holds 20 transitions after 4 pushes per agent, rank 1 only
+    after 5 -- the ranks must start learning on the SAME step (replicas diverged otherwise)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dmdqn_b200.parallel import shard_range
+        lo, hi = shard_range(9, world, rank)
+        n_local, b_local = hi - lo, 20
+        state = {"pushed": 0, "theta": torch.zeros(4), "steps": 0, "calls": 0}
+
+        def local_ready():
+            return state["pushed"] * n_local >= b_local
+
+        def local_grads(global_batch):
+            assert local_ready(), "a rank was asked for gradients before its rings held its share of the batch"
+            assert global_batch == b_local * world
+            state["calls"] += 1
+            return torch.full((4,), float(rank + 1)), torch.ones(1, 8)
+
+        def apply(g):
+            state["theta"] -= 0.1 * g
+            state["steps"] += 1
+
+        step = SharedParameterStep(local_grads, apply, b_local, local_ready=local_ready)
+        trace = []
+        for _ in range(8):
+            state["pushed"] += 1
+            out = step.step()
+            trace.append(None if out is None else float(out[0]))
+        q.put((rank, n_local, trace, state["steps"], state["theta"].tolist(), step.skipped))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shared_parameter_learn_decision_is_collective_on_uneven_shards():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_uneven_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, n0, trace0, steps0, theta0, skipped0), (_, n1, trace1, steps1, theta1, skipped1) = results
+    assert (n0, n1) == (5, 4)
+    # rank 0 alone would have started at push 4 (5 * 4 = 20); together they start at push 5 (4 * 5 = 20)
+    assert trace0 == trace1 == [None] * 4 + [2.0] * 4
+    assert steps0 == steps1 == 4 and skipped0 == skipped1 == 4
+    assert theta0 == theta1 == pytest.approx([-0.1 * 3 * 4] * 4)      # summed gradient 1 + 2, four steps

@@ -9,7 +9,10 @@ Workloads (BASELINE.json configs; synthetic replay, observation-shaped integers,
   cfg2  16 agents,  B=64,  H=256      cfg3  256 agents, B=256, H=256  (default, per GPU)
   cfg4  512 agents, B=512, H=256 per GPU (4096 over 8 GPUs)
 N>1 shards agents across ranks with no collective (independent networks): weak scaling,
-every rank holds the per-GPU workload.  One JSON line on stdout (rank 0).
+every rank holds the per-GPU workload.  The same JSON line carries, under "blocks", the other configurations
+BASELINE.json names: cfg3 strong-scaled (256 agents in total over the ranks), cfg4 (512 agents per GPU, batch 512)
+and cfg5 (one shared network, hidden 512, global batch 1024, gradient reduction over the ranks); "act" is measured
+on a working set larger than the L2.  One JSON line on stdout (rank 0).
 """
 from __future__ import annotations
 
@@ -63,7 +66,7 @@ def flops_bytes(w):
     p = m + h + h + A
     k = {"target": dict(flops=2 * 2 * b * m, bytes=b * (D + 2) * 4 + 8 * p),
          "online": dict(flops=2 * b * m + 2 * b * (h * h + h * A), bytes=b * (D + 1) * 4 + 4 * p),
-         "wgrad_adam": dict(flops=2 * b * m, bytes=12 * p),
+         "wgrad_adam": dict(flops=2 * b * m, bytes=24 * p),      # theta, m, v read AND written back (theta_tgt on sync steps: +4P)
          "sample": dict(flops=0, bytes=b * 13 + b * 16)}
     return {"flops": 2 * b * (4 * m + h * h + h * A), "bytes": b * (2 * D + 3) * 4 + 24 * p, "params": p, "kernels": k}
 
@@ -174,10 +177,285 @@ def synth_fill(grp, seed):
     grp.n_written_host[:] = c + 777
 
 
-def run_ours(args):
+def _events(n):
+    return [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+
+
+def _barrier(world):
+    torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def _max_over_ranks(vals, world, device):
+    if world == 1:
+        return list(vals)
+    import torch.distributed as dist
+    t = torch.tensor(list(vals), device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t]
+
+
+def time_learn(grp, draws, K, W, world):
+    """K learn sweeps after W warm-up sweeps: CUDA events on the launching stream, barrier + synchronize on both
+    sides, max over ranks.  Returns ms for the K sweeps."""
+    stream = torch.cuda.current_stream()
+    for i in range(W):
+        grp.learn(draws[i])
+    _barrier(world)
+    e0, e1 = _events(2)
+    e0.record(stream)
+    for i in range(K):
+        grp.learn(draws[W + i])
+    e1.record(stream)
+    _barrier(world)
+    return _max_over_ranks([e0.elapsed_time(e1)], world, grp.device)[0]
+
+
+STAGE_NAMES = ["sample", "target", "online", "wgrad_adam"]
+
+
+def stage_times(grp, draws, K):
+    """The same sweep issued one stage per call (dmdqn_learn_stages) with events in between: mean ms per kernel."""
     from dmdqn_b200 import _native as N
-    from dmdqn_b200.group import AgentGroup
     import ctypes as C
+    stream = torch.cuda.current_stream()
+    evs = [_events(5) for _ in range(K)]
+    for i in range(K):
+        d = draws[i]
+        for s in range(4):
+            evs[i][s].record(stream)
+            N.check(grp.lib.dmdqn_learn_stages(C.byref(grp.dims), C.byref(grp.hp), C.byref(grp.replay), C.byref(grp.nets),
+                                               d.data_ptr(), None, grp.metrics.data_ptr(), grp.workspace.data_ptr(),
+                                               grp.workspace.numel(), 1 << s, stream.cuda_stream))
+        evs[i][4].record(stream)
+    torch.cuda.synchronize()
+    grp.learn_step_host += K
+    return {nm: statistics.mean(evs[i][s].elapsed_time(evs[i][s + 1]) for i in range(K)) for s, nm in enumerate(STAGE_NAMES)}
+
+
+def kernel_table(w, n, stage_ms, workload, precision):
+    """Per kernel: duration, algorithmic flops / bytes per launch, achieved rates, ncu DRAM traffic per launch."""
+    fb = flops_bytes(w)
+    pk = peaks()
+    out = {}
+    for k_ in STAGE_NAMES:
+        ms, kf = stage_ms[k_], fb["kernels"][k_]
+        out[k_] = {"ms": ms, "tflops": n * kf["flops"] / (ms / 1e3) / 1e12, "algorithmic_bytes": n * kf["bytes"],
+                   "gbs": n * kf["bytes"] / (ms / 1e3) / 1e9, "hbm_frac": n * kf["bytes"] / (ms / 1e3) / 1e9 / pk["hbm_gbs"],
+                   "traffic": ncu_traffic(workload, precision, k_)}
+    return out
+
+
+def timed(fn, reps, stream):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b_ = _events(2)
+    a.record(stream)
+    for _ in range(reps):
+        fn()
+    b_.record(stream)
+    torch.cuda.synchronize()
+    return a.elapsed_time(b_) / reps
+
+
+def graph_timed(fn, launches, replays, stream):
+    """Device time of `fn` without the Python call overhead: `launches` calls captured in a CUDA graph, replayed."""
+    side = torch.cuda.Stream()
+    side.wait_stream(stream)
+    with torch.cuda.stream(side):
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            for i in range(launches):
+                fn(i)
+        for _ in range(3):
+            graph.replay()
+        side.synchronize()
+        a_, b_ = _events(2)
+        a_.record(side)
+        for _ in range(replays):
+            graph.replay()
+        b_.record(side)
+        side.synchronize()
+        ms = a_.elapsed_time(b_) / (replays * launches)
+    stream.wait_stream(side)
+    return ms
+
+
+# ---- blocks: the other configurations north_star names, inside the same JSON line ---------------------------
+def block_act(args, rank, world, local):
+    """actions/s with a working set LARGER than the 126 MB L2: 768 agents x 4P bytes = 276 MB of weights are streamed
+    per launch (cyclic access over 2.2x the L2 capacity: no reuse between launches), next to the 256-agent launch
+    whose 92 MB stay L2-resident between replays (the figure round 1 reported)."""
+    from dmdqn_b200.group import AgentGroup
+    w = WORKLOADS["cfg3"]
+    p = flops_bytes(w)["params"]
+    stream = torch.cuda.current_stream()
+    out = {}
+    for tag, n in (("hbm_768_agents", 768), ("l2_resident_256_agents", 256)):
+        grp = AgentGroup(n, dict(agent_cfg(w, args.precision), replay_buffer_size=4, batch_size=4), D, A, seed=7 + rank)
+        obs = torch.randint(-1, 20, (n, D), device=grp.device).float()
+        eps0 = torch.zeros(n, dtype=torch.float64, device=grp.device)
+        wz = torch.zeros(n, dtype=torch.int32, device=grp.device)
+        api_ms = timed(lambda: grp.act(obs, eps0, wz, wz), 200, stream)
+        try:
+            ms = graph_timed(lambda i: grp.act(obs, eps0, wz, wz), 16, 20, stream)
+        except Exception as exc:                                                   # noqa: BLE001
+            print(f"act graph timing unavailable ({exc}); reporting the API loop", file=sys.stderr)
+            ms = api_ms
+        ms = _max_over_ranks([ms], world, grp.device)[0]
+        gbs = n * 4 * p / (ms / 1e3) / 1e9
+        out[tag] = {"agents_per_gpu": n, "value": n * world / (ms / 1e3), "unit": "actions/s", "ms": ms, "api_ms": api_ms,
+                    "weight_bytes_per_launch": n * 4 * p, "hbm_gbs": gbs, "hbm_frac": gbs / peaks()["hbm_gbs"]}
+        del grp, obs
+        torch.cuda.empty_cache()
+    head = out["hbm_768_agents"]
+    return {"value": head["value"], "unit": "actions/s", "ms": head["ms"], "eps": 0.0, "bytes_per_action": 4 * p,
+            "hbm_gbs": head["hbm_gbs"], "hbm_frac": head["hbm_frac"],
+            "timing": "16 launches captured in a CUDA graph, replayed 20x (device time); api_ms = the same call from Python; "
+                      "eps = 0 so every agent runs its network",
+            "cold_ncu_us_256_agents": (ncu_traffic("cfg3", args.precision, "act") and
+                                       json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+                                       [f"cfg3/{args.precision}"]["act"]["ncu_duration_us"]),
+            **out}
+
+
+def block_strong_cfg3(args, rank, world, local, K, W):
+    """BASELINE cfg3 'then sharded 2/4/8': 256 agents in TOTAL, split by contiguous agent range over the ranks
+    (parallel.shard_range), no collective.  value = 256 agents x steps / max-over-ranks time."""
+    from dmdqn_b200.group import AgentGroup
+    from dmdqn_b200.parallel import shard_range
+    w = WORKLOADS["cfg3"]
+    lo, hi = shard_range(w["agents"], world, rank)
+    grp = AgentGroup(hi - lo, agent_cfg(w, args.precision), D, A, seed=1000 + lo)
+    synth_fill(grp, seed=100 + rank)
+    draws = grp.draw_words((K + W, grp.n_agents, grp.batch_size))
+    ms = time_learn(grp, draws, K, W, world)
+    st = stage_times(grp, draws[W:], min(K, 20))
+    del grp
+    torch.cuda.empty_cache()
+    return {"workload": "cfg3 strong: 256 agents total, batch 256, hidden 256, agent ranges over the ranks, no collective",
+            "agents_total": w["agents"], "agents_this_rank": hi - lo, "value": w["agents"] * K / (ms / 1e3),
+            "unit": "agent-updates/s", "ms_per_step": ms / K, "scaling": "strong", "steps": K,
+            "kernels_ms_rank0": st}
+
+
+def block_cfg4(args, rank, world, local, K, W):
+    """BASELINE cfg4: 4096 agents (64x64 city grid), batch 512, sharded 512 per GPU with no collective (weak: the
+    per-GPU shard is the unit; 8 GPUs hold the whole grid)."""
+    from dmdqn_b200.group import AgentGroup
+    w = WORKLOADS["cfg4"]
+    grp = AgentGroup(w["agents"], agent_cfg(w, args.precision), D, A, seed=5000 + 1000 * rank)
+    synth_fill(grp, seed=200 + rank)
+    draws = grp.draw_words((K + W, grp.n_agents, grp.batch_size))
+    ms = time_learn(grp, draws, K, W, world)
+    st = stage_times(grp, draws[W:], min(K, 10))
+    fb = flops_bytes(w)
+    n = grp.n_agents
+    del grp
+    torch.cuda.empty_cache()
+    return {"workload": workload_name("cfg4"), "agents_total": n * world, "value": n * world * K / (ms / 1e3),
+            "unit": "agent-updates/s", "ms_per_step": ms / K, "scaling": "weak", "steps": K,
+            "tflops_per_gpu": n * fb["flops"] / (ms / K / 1e3) / 1e12, "kernels_ms_rank0": st}
+
+
+def block_cfg5(args, rank, world, local, K, W):
+    """BASELINE cfg5: ONE network (hidden 512) shared by 1024 agents; every learn step draws a global batch of 1024
+    transitions, 1024/N per GPU from that GPU's rings (1024/N agents each), gradients summed over the ranks
+    (parallel.SharedParameterStep: NCCL all-reduce of the 4P-byte block, or the fused peer-memory reduce + Adam
+    when the library offers it), identical Adam on every replica.  value = shared updates/s x 1024 agents served
+    (SURVEY.md section 8 D-inputs); raw updates/s and samples/s alongside."""
+    from dmdqn_b200.group import AgentGroup
+    from dmdqn_b200.parallel import SharedParameterStep
+    import torch.distributed as dist
+    agents_total, batch_global, hidden, cap = 1024, 1024, 512, 4096
+    if agents_total % world or batch_global % world:
+        return {"skipped": f"world size {world} does not divide 1024"}
+    cfg = {"learning_rate": 5e-4, "gamma": 0.99, "replay_buffer_size": cap, "batch_size": batch_global // world,
+           "target_update_frequency": 1000, "nn_layers": [hidden, hidden], "share_parameters": True, "precision": "auto"}
+    grp = AgentGroup(agents_total // world, cfg, D, A, seed=42)            # same seed: replicas start identical
+    synth_fill(grp, seed=300 + rank)
+    step = SharedParameterStep.for_group(grp)
+    stream = torch.cuda.current_stream()
+    for _ in range(W):
+        step.step()
+    _barrier(world)
+    e0, e1 = _events(2)
+    e0.record(stream)
+    for _ in range(K):
+        step.step()
+    e1.record(stream)
+    _barrier(world)
+    ms = _max_over_ranks([e0.elapsed_time(e1)], world, grp.device)[0]
+    # phase split of one step: local gradients | reduction | Adam
+    ev = [_events(4) for _ in range(min(K, 20))]
+    for e in ev:
+        e[0].record(stream)
+        grads, _ = step.local_grads(step.local_batch * world)
+        e[1].record(stream)
+        if world > 1:
+            dist.all_reduce(grads)
+        e[2].record(stream)
+        step.apply(grads)
+        e[3].record(stream)
+    torch.cuda.synchronize()
+    phases = {nm: statistics.mean(e[i].elapsed_time(e[i + 1]) for e in ev) for i, nm in enumerate(("local_grads", "allreduce", "adam"))}
+    identical = True
+    if world > 1:
+        chk = grp.theta.double().sum().reshape(1)
+        lo_, hi_ = chk.clone(), chk.clone()
+        dist.all_reduce(lo_, op=dist.ReduceOp.MIN); dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+        identical = bool((lo_ == hi_).item())
+    p = hidden * D + hidden * hidden + hidden * A + 2 * hidden + A
+    ups = K / (ms / 1e3)
+    del grp
+    torch.cuda.empty_cache()
+    return {"workload": f"cfg5: one shared network, hidden [512,512], 1024 agents, global batch 1024 ({batch_global // world} per GPU), "
+                        f"replay capacity {cap} per agent, gradient all-reduce of {4 * p} bytes",
+            "value": ups * agents_total, "unit": "agent-updates/s (shared updates/s x 1024 agents served)",
+            "shared_updates_per_s": ups, "samples_per_s": ups * batch_global, "ms_per_step": ms / K, "scaling": "strong",
+            "steps": K, "phases_ms_rank0": phases, "replicas_identical": identical,
+            "reduction": "none (1 GPU)" if world == 1 else "torch.distributed all_reduce (NCCL) between dmdqn_learn_grads and dmdqn_adam_apply"}
+
+
+def block_gather_featurize(grp, world, K):
+    """K1b's stand-alone gather (ReplayBuffer.sample's five tensors) and K0, with achieved GB/s on algorithmic bytes."""
+    from dmdqn_b200.parallel import grid_neighbor_table
+    stream = torch.cuda.current_stream()
+    n, b = grp.n_agents, grp.batch_size
+    draws = grp.draw_words((n, b))
+    sample_ms = timed(lambda: grp.sample(draws), 30, stream)            # sample + gather + the output allocations
+    # the gather kernel alone: the workspace already holds the sampled rows
+    from dmdqn_b200 import _native as N
+    import ctypes as C
+    states = torch.zeros((n, b, D), device=grp.device); nxt = torch.zeros_like(states)
+    acts = torch.zeros((n, b), dtype=torch.int32, device=grp.device); rew = torch.zeros((n, b), device=grp.device)
+    dn = torch.zeros((n, b), device=grp.device)
+    gather_ms = timed(lambda: N.check(grp.lib.dmdqn_gather(C.byref(grp.dims), C.byref(grp.replay), grp.workspace.data_ptr(),
+                                                           grp.workspace.numel(), states.data_ptr(), acts.data_ptr(), rew.data_ptr(),
+                                                           nxt.data_ptr(), dn.data_ptr(), None, stream.cuda_stream)), 50, stream)
+    g_bytes = n * b * 724 * 2                                                # 724 B read + 724 B written per sampled transition
+    halting = torch.randint(0, 20, (n, 12), dtype=torch.int32, device=grp.device)
+    zi = torch.zeros(n, dtype=torch.int32, device=grp.device); zd = torch.zeros(n, dtype=torch.float64, device=grp.device)
+    zv = torch.zeros(n, dtype=torch.uint8, device=grp.device)
+    side = max(r for r in range(1, int(n ** 0.5) + 1) if n % r == 0)          # this GPU's shard of the grid: side x n/side
+    nbr = torch.as_tensor(grid_neighbor_table(side, n // side)).to(grp.device)
+    feat_ms = timed(lambda: grp.featurize(halting, zi, zd, zd, 0.0, zv, nbr), 200, stream)
+    f_bytes = n * (64 + 96 * 4 + 17 * 8 + 8)
+    pk = peaks()["hbm_gbs"]
+    return {"gather": {"ms": gather_ms, "api_sample_ms": sample_ms, "bytes_per_transition": 724, "algorithmic_bytes": g_bytes,
+                       "gbs": g_bytes / (gather_ms / 1e3) / 1e9, "hbm_frac": g_bytes / (gather_ms / 1e3) / 1e9 / pk,
+                       "note": "dmdqn_gather alone (rows already sampled): B x 724 B read from the rings + the same written densely"},
+            "featurize": {"ms": feat_ms, "agents_per_s": n * world / (feat_ms / 1e3), "bytes_per_agent": 64 + 96 * 4 + 17 * 8 + 8,
+                          "gbs": f_bytes / (feat_ms / 1e3) / 1e9, "hbm_frac": f_bytes / (feat_ms / 1e3) / 1e9 / pk,
+                          "note": "launch bound: a few hundred KB per call"}}
+
+
+def run_ours(args):
+    from dmdqn_b200.group import AgentGroup
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -193,95 +471,23 @@ def run_ours(args):
     draws = grp.draw_words((K + W, n, b))
     stream = torch.cuda.current_stream()
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     # ---- device-resident throughput: K learn sweeps, inputs already in HBM ----------------
+    sampler = ClockSampler(local)
     for i in range(W):
         grp.learn(draws[i])
-    barrier()
-    sampler = ClockSampler(local); sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    _barrier(world)
+    sampler.start()
+    e0, e1 = _events(2)
     e0.record(stream)
     for i in range(K):
         grp.learn(draws[W + i])
     e1.record(stream)
-    barrier()
+    _barrier(world)
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
 
     # ---- per-kernel durations: same sweep, one stage per call, events in between ----------
-    stage_names = ["sample", "target", "online", "wgrad_adam"]
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(K)]
-    lib = grp.lib
-    for i in range(K):
-        d = draws[W + i]
-        for s in range(4):
-            evs[i][s].record(stream)
-            N.check(lib.dmdqn_learn_stages(C.byref(grp.dims), C.byref(grp.hp), C.byref(grp.replay), C.byref(grp.nets),
-                                           d.data_ptr(), None, grp.metrics.data_ptr(), grp.workspace.data_ptr(),
-                                           grp.workspace.numel(), 1 << s, stream.cuda_stream))
-        evs[i][4].record(stream)
-    torch.cuda.synchronize()
-    grp.learn_step_host += K
-    stage_ms = {nm: statistics.mean(evs[i][s].elapsed_time(evs[i][s + 1]) for i in range(K)) for s, nm in enumerate(stage_names)}
-
-    # ---- the other kernels of the path, device-resident (actions/s is BASELINE's second metric) ----
-    obs_dev = grp.obs[:, 0, :].contiguous()
-    eps0 = torch.zeros(n, dtype=torch.float64, device=grp.device)
-    w_zero = torch.zeros(n, dtype=torch.int32, device=grp.device)
-
-    def timed(fn, reps):
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        for _ in range(reps):
-            fn()
-        b_.record(stream)
-        torch.cuda.synchronize()
-        return a.elapsed_time(b_) / reps
-    act_api_ms = timed(lambda: grp.act(obs_dev, eps0, w_zero, w_zero), min(4 * K, 400))   # eps = 0: every agent runs its network
-    act_ms = act_api_ms
-    try:        # the Python call costs about as much as the kernel: replay 16 captured launches for the device time
-        side_stream = torch.cuda.Stream()
-        side_stream.wait_stream(stream)
-        with torch.cuda.stream(side_stream):
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=side_stream):
-                for _ in range(16):
-                    grp.act(obs_dev, eps0, w_zero, w_zero)
-            for _ in range(3):
-                graph.replay()
-            side_stream.synchronize()
-            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a_.record(side_stream)
-            for _ in range(20):
-                graph.replay()
-            b_.record(side_stream)
-            side_stream.synchronize()
-            act_ms = a_.elapsed_time(b_) / (20 * 16)
-        stream.wait_stream(side_stream)
-    except Exception as exc:                                                   # noqa: BLE001
-        print(f"act graph timing unavailable ({exc}); reporting the API loop", file=sys.stderr)
-    halting = torch.randint(0, 20, (n, 12), dtype=torch.int32, device=grp.device)
-    zi = torch.zeros(n, dtype=torch.int32, device=grp.device); zd = torch.zeros(n, dtype=torch.float64, device=grp.device)
-    zv = torch.zeros(n, dtype=torch.uint8, device=grp.device)
-    side = max(r for r in range(1, int(n ** 0.5) + 1) if n % r == 0)          # this GPU's shard of the grid: side x n/side
-    from dmdqn_b200.parallel import grid_neighbor_table
-    nbr = torch.as_tensor(grid_neighbor_table(side, n // side)).to(grp.device)
-    assert nbr.shape[0] == n
-    feat_ms = timed(lambda: grp.featurize(halting, zi, zd, zd, 0.0, zv, nbr), 4 * K)
-    act_bytes = n * 4 * fb["params"]
-    extra = {"act": {"value": n * world / (act_ms / 1e3), "unit": "actions/s", "ms": act_ms, "api_ms": act_api_ms, "eps": 0.0,
-                     "timing": "16 launches captured in a CUDA graph, replayed 20x (device time); api_ms = the same call from Python",
-                     "hbm_gbs": act_bytes / (act_ms / 1e3) / 1e9, "hbm_frac": act_bytes / (act_ms / 1e3) / 1e9 / peaks()["hbm_gbs"],
-                     "bytes_per_action": 4 * fb["params"]},
-             "featurize": {"ms": feat_ms, "agents_per_s": n * world / (feat_ms / 1e3), "bytes_per_agent": 64 + 96 * 4 + 17 * 8 + 8}}
+    stage_ms = stage_times(grp, draws[W:], K)
 
     # ---- end to end: host transitions + draws in, losses out, every step ------------------
     # dmdqn_step_host (include/dmdqn_b200.h): the step's inputs sit in ONE pinned host block (struct of arrays);
@@ -300,55 +506,71 @@ def run_ours(args):
         return float(m[0, 0])
     for _ in range(W):
         e2e_step()
-    barrier()
+    _barrier(world)
     e0.record(stream)
     for _ in range(K):
         e2e_step()
     e1.record(stream)
-    barrier()
+    _barrier(world)
     ms_e2e = e0.elapsed_time(e1)
+    grp.check_errors()                                         # raises if a tcgen05 kernel's bounded wait expired
+    ms, ms_e2e = _max_over_ranks([ms, ms_e2e], world, grp.device)
 
-    tc_err = int(grp.debug_views()["tc_error"][0])
-    if tc_err:
-        raise RuntimeError(f"a tcgen05 kernel timed out on an mbarrier (code {tc_err}): the timings are invalid")
-    if world > 1:
-        t = torch.tensor([ms, ms_e2e], device=grp.device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
+    extra = block_gather_featurize(grp, world, K)
+    del grp, draws
+    torch.cuda.empty_cache()
+
+    # ---- the other configurations north_star names --------------------------------------------
+    blocks = {}
+    want = set(args.blocks.split(",")) if args.blocks not in ("all", "none") else (
+        {"act", "strong_cfg3", "cfg4", "cfg5"} if args.blocks == "all" else set())
+    bk, bw = max(3, min(K, args.block_steps)), 3
+    if "act" in want:
+        extra["act"] = block_act(args, rank, world, local)
+    if "strong_cfg3" in want:
+        blocks["strong_cfg3"] = block_strong_cfg3(args, rank, world, local, bk, bw)
+    if "cfg4" in want:
+        blocks["cfg4"] = block_cfg4(args, rank, world, local, max(3, bk // 3), bw)
+    if "cfg5" in want:
+        blocks["cfg5"] = block_cfg5(args, rank, world, local, bk, bw)
+
     total_agents = n * world
     value = total_agents * K / (ms / 1e3)
     pk = peaks()
     dom = max(("target", "online", "wgrad_adam"), key=lambda k_: stage_ms[k_])
-    kf = fb["kernels"][dom]
-    ach_tf = n * kf["flops"] / (stage_ms[dom] / 1e3) / 1e12
+    kt = kernel_table(w, n, stage_ms, args.workload, args.precision)
+    ach_tf = kt[dom]["tflops"]
     ffma_peak = 148 * 128 * 2 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e12
+    launches_per_step = 4
     out = {
         "metric": "agent-updates/sec", "value": value, "unit": "agent-updates/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic replay (observation-shaped integers, full rings), random-init weights",
-        "config": {"workload": workload_name(args.workload), "precision": args.precision,
-                   "agents_total": total_agents, "sharding": "agent ranges, no collectives" if world > 1 else "single GPU",
-                   "l2_policy": "working set (replay ring 5.9 GB, theta/m/v 368 MB, scratch 200 MB at cfg3) exceeds the 126 MB L2",
-                   "sample_mode": "fisher_yates (device draws)"},
+        "config": {"workload": workload_name(args.workload)},
+        "details": {"precision": args.precision, "agents_total": total_agents,
+                    "sharding": "agent ranges, no collectives" if world > 1 else "single GPU",
+                    "l2_policy": "working set (replay ring 5.9 GB, theta/m/v 368 MB, scratch 200 MB at cfg3) exceeds the 126 MB L2",
+                    "sample_mode": "fisher_yates (device draws)"},
         "e2e": {"value": total_agents * K / (ms_e2e / 1e3), "unit": "agent-updates/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K,
                 "what": "dmdqn_step_host: one pinned host block (transition of every agent + draws) -> one H2D copy -> push -> learn -> losses to pinned host memory, stream synchronised and the loss read every step"},
-        "gpu_launches": 4 * K,
+        "gpu_launches": launches_per_step * K,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": dom, "achieved": ach_tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": ach_tf / pk["bf16_tflops_sustained"], "traffic": ncu_traffic(args.workload, args.precision, dom),
-                     "algorithmic_bytes": n * kf["bytes"], "peak_source": pk["source"],
+                     "frac": ach_tf / pk["bf16_tflops_sustained"], "traffic": kt[dom]["traffic"],
+                     "algorithmic_bytes": kt[dom]["algorithmic_bytes"], "peak_source": pk["source"],
+                     "frac_of_burst_peak": ach_tf / pk["bf16_tflops"],
                      "note": (f"fp32 FFMA kernel: fraction of the fp32 FFMA peak at the sampled clock = {ach_tf / ffma_peak:.3f} of "
                               f"{ffma_peak:.1f} TFLOP/s") if args.precision == "fp32" else
                              ("tcgen05 kind::tf32; achieved counts ALGORITHMIC flops (each product is issued as "
                               f"{3 if args.precision == 'tf32x3' else 1} MMA(s)); peak is the measured bf16 figure (tf32 dense peak is half of it), so the "
                               f"ceiling of this precision is frac = {1 / (6 if args.precision == 'tf32x3' else 2):.3f}")},
-        "kernels": {k_: {"ms": stage_ms[k_], "tflops": n * fb["kernels"][k_]["flops"] / (stage_ms[k_] / 1e3) / 1e12,
-                         "gbs": n * fb["kernels"][k_]["bytes"] / (stage_ms[k_] / 1e3) / 1e9} for k_ in stage_names},
+        "kernels": kt,
         **extra,
         "step": {"flops_per_agent_update": fb["flops"], "bytes_per_agent_update": fb["bytes"],
                  "tflops": n * fb["flops"] / (ms / K / 1e3) / 1e12, "hbm_gbs_algorithmic": n * fb["bytes"] / (ms / K / 1e3) / 1e9,
                  "hbm_frac": n * fb["bytes"] / (ms / K / 1e3) / 1e9 / pk["hbm_gbs"]},
+        "blocks": blocks,
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
@@ -425,7 +647,7 @@ def run_reference(args):
         "impl": "reference", "metric": "agent-updates/sec", "value": v, "unit": "agent-updates/s",
         "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": K, "warmup": W, "ms_per_step": el / K * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic replay",
-        "config": {"workload": workload_name(args.workload), "precision": "fp32 (CPU torch oracle)"},
+        "config": {"workload": workload_name(args.workload)},
         "cpu_baseline": {"value": v, "unit": "agent-updates/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "agent-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0})
@@ -440,6 +662,8 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--blocks", default="all", help="all | none | comma list of act,strong_cfg3,cfg4,cfg5")
+    ap.add_argument("--block-steps", type=int, default=30)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

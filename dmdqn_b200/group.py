@@ -141,6 +141,9 @@ class AgentGroup:
         nbytes = C.c_size_t()
         N.check(self.lib.dmdqn_workspace_bytes(C.byref(self.dims), C.byref(nbytes)))
         self.workspace = torch.zeros((nbytes.value,), dtype=torch.uint8, device=dev)
+        dv = N.DebugViews()
+        N.check(self.lib.dmdqn_debug(C.byref(self.dims), _ptr(self.workspace), self.workspace.numel(), C.byref(dv)))
+        self._tc_error_offset = dv.tc_error - self.workspace.data_ptr()
         self.metrics = torch.zeros((g, N.METRICS_STRIDE), dtype=torch.float32, device=dev)
         self._feat_scratch = torch.zeros((2,), dtype=torch.int64, device=dev)
         self._zero_eps = torch.zeros((n,), dtype=torch.float64, device=dev)
@@ -414,6 +417,16 @@ class AgentGroup:
         self.n_written_host += 1
         self.learn_step_host += self.active_host().astype(np.int64)
         return sb["metrics_host"]
+
+    def check_errors(self) -> None:
+        """Raise if a tcgen05 kernel reported an expired mbarrier wait since the last check (the kernels then skip
+        the weight update instead of applying garbage; learned flag metrics[:, 7] < 0).  Reads one int from the
+        device: call it where the host synchronises anyway (after reading the losses)."""
+        off = self._tc_error_offset
+        code = int(self.workspace[off:off + 4].view(torch.int32).item())
+        if code:
+            self.workspace[off:off + 4].zero_()
+            raise N.NativeError(f"a tcgen05 learn kernel timed out on an mbarrier (code {code}); the step was not applied")
 
     def debug_views(self) -> dict:
         """Intermediate results of the last learn() as device tensors (parity tests)."""

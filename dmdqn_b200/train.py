@@ -95,7 +95,8 @@ def get_traci(config: dict, seed: int = 0):
             if backend == "traci":
                 raise
     from .sim.fake_traci import FakeTraci
-    return FakeTraci(rows=int(config.get("grid_rows", 3)), cols=int(config.get("grid_cols", 3)), seed=seed,
+    return FakeTraci(rows=int(config.get("grid_rows", 3)), cols=int(config.get("grid_cols", 3)),
+                     seed=int(config.get("fake_traci_seed", seed)),
                      max_sim_time=float(config.get("max_sim_time", MAX_SIM_TIME))), True
 
 
@@ -228,6 +229,7 @@ def train_agents(config: dict | None = None, episodes: int = EPISODES, mode: str
             else:
                 group.push(obs, actions, reward, next_obs, dones)
                 total_loss = float(group.learn()[:, 0].sum()) if learn else 0.0
+            group.check_errors()        # the host has just synchronised on the losses: one more 4-byte read
             g_r, t_r = float(glob.item()), float(reward.sum().item())
             smooth_global.update(g_r); smooth_total.update(t_r)
             rec = {"episode": episode, "step": step_count, "total_loss": total_loss, "global_reward": g_r,

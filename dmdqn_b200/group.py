@@ -160,7 +160,9 @@ class AgentGroup:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def _dev(self, x, dtype) -> torch.Tensor:
-        t = torch.as_tensor(x) if not isinstance(x, torch.Tensor) else x
+        # np.asarray first: torch.as_tensor on a list of Python floats makes a float32 tensor, which would round the
+        # float64 rewards the reference keeps as Python floats (dqn_agent.py:43) before they reach the ring
+        t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x))
         return t.to(device=self.device, dtype=dtype, non_blocking=True).contiguous()
 
     def agent_view(self, i: int) -> "AgentGroup":

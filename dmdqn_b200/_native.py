@@ -87,11 +87,15 @@ def lib() -> C.CDLL:
     """The loaded library; raises if it has not been built (``python -m dmdqn_b200.build``)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = LIB_PATH
+        prof = os.environ.get("DMDQN_PROFILING_LIB")  # phase-stamp / debug builds live in their own file (build.py); never the default
+        if prof:
+            path = os.path.join(os.path.dirname(LIB_PATH), prof if prof.endswith(".so") else "libdmdqn_b200_timing.so")
+        if not os.path.exists(path):
             raise NativeError(
-                f"{LIB_PATH} is missing: build it with `python -m dmdqn_b200.build` "
+                f"{path} is missing: build it with `python -m dmdqn_b200.build` "
                 "(nvcc, sm_100a). dmdqn_b200 has no CPU fallback.")
-        handle = C.CDLL(LIB_PATH)
+        handle = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)  # AttributeError if the .so does not export it
             fn.restype, fn.argtypes = res, args

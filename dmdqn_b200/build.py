@@ -31,18 +31,19 @@ def is_stale() -> bool:
     return any(os.path.getmtime(p) > built for p in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+TIMING_LIB = os.path.join(HERE, "libdmdqn_b200_timing.so")
+
+
+def build(force: bool = False, verbose: bool = False, timing: bool = False) -> str:
+    """``timing=True`` builds the phase-stamp variant (-DTC_TIMING: a few CTAs printf clock64 deltas; results are
+    unchanged) into its OWN file, loaded only when DMDQN_PROFILING_LIB is set: the product library is never
+    replaced by a profiling build."""
+    out = TIMING_LIB if timing else LIB
+    if not timing and not force and not is_stale():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
-    if os.environ.get("DMDQN_TC_TIMING"):          # phase stamps printed by a few CTAs (profiling aid only)
-        cmd.insert(1, "-DTC_TIMING")
-        cmd.insert(1, "-DTC_EXP=" + os.environ.get("DMDQN_TC_EXP", "0"))
-    if os.environ.get("DMDQN_TC_EXP_ONLY"):        # experiment switch without the stamps (results are wrong by design)
-        cmd.insert(1, "-DWG_EXP=" + os.environ["DMDQN_TC_EXP_ONLY"])
-    if os.environ.get("DMDQN_NVCC_DEFINES"):       # e.g. "DMDQN_NO_ROW_PREFETCH": A/B switches for tools/exp_timing.sh
-        for dname in os.environ["DMDQN_NVCC_DEFINES"].split(","):
-            cmd.insert(1, "-D" + dname)
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", out, *[os.path.join(CSRC, s) for s in SOURCES]]
+    if timing:
+        cmd.insert(1, "-DTC_TIMING=" + os.environ.get("DMDQN_TC_TIMING", "1"))    # 1: kernel totals, 2: + per-item phase stamps
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -50,8 +51,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, timing="--timing" in sys.argv))

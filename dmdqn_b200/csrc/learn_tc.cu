@@ -10,17 +10,23 @@
 // A_lo*B_hi + A_hi*B_lo + A_hi*B_hi accumulated in fp32 in TMEM ("3xTF32"; measured 3e-7 relative
 // on B200, tools/umma_probe.cu).  PASSES = 1 issues only A*B (plain TF32, ~1e-3, toleranced apart).
 //
-// A CTA owns 128 batch rows of one network (UMMA M = 128, N = 256 = all output columns):
-//   * activations: hi part in shared memory as the next layer's A operand (K-major, 128-byte
-//     swizzle), lo part in TMEM columns 256..511 (A-from-TMEM MMA) -- 128 KB each, so the full
-//     512 TMEM columns are used: 256 accumulator + 256 operand;
-//   * weights: 8 x 256 (x.W) or 256 x 16 (d.W^T) chunks streamed from L2 through registers (loads two own
-//     chunks ahead) into the UMMA canonical layout (MN-major "128B_BASE32B" / K-major 64-byte swizzle),
-//     split hi/lo by the thread that loaded them; a full/empty mbarrier ring (4 / 2 stages, one producer
-//     group per stage) couples the 8 producer warps to the single MMA-issuing lane (warp 8),
-//     tcgen05.commit frees a stage;
-//   * epilogues read the accumulator with tcgen05.ld (thread = batch row), so bias/ReLU, the
-//     4-wide head (layer 3), TD target, loss gradient and dh2 are computed per row in registers.
+// K3 / K4a are PERSISTENT (one CTA per SM walks its (network, 128-row tile) items) and warp-specialised:
+//   warps 0-15  gather / epilogue: thread = batch row of the tile (UMMA M = 128), four warps per TMEM
+//               sub-partition splitting the 256 columns in quarters.  They gather the observation rows of the
+//               NEXT item into registers while the tensor pipe works on the current one, read accumulators with
+//               tcgen05.ld, and write the next layer's A operand: hi part to shared memory (K-major, 128-byte
+//               swizzle), lo part to TMEM columns 256..511 (A-from-TMEM MMA) -- 128 KB each, so all 512 TMEM
+//               columns are used: 256 accumulator + 256 operand;
+//   warp 16     lane 0 issues every tcgen05.mma and commits stages / GEMMs to mbarriers;
+//   warp 17     lane 0 is the TMA producer: raw fp32 weight chunks travel global -> shared memory with
+//               cp.async.bulk (x.W: contiguous 8 x 256 rows) and cp.async.bulk.tensor (d.W^T: a 16-column box of
+//               all 256 rows of W2 through a tensor map), completion on the stage's mbarrier (expect_tx);
+//   warps 18-21 converters: turn a landed raw chunk IN PLACE into the hi | lo halves of the stage in the UMMA
+//               canonical layout (MN-major "128B_BASE32B" for x.W, K-major 64-byte swizzle for d.W^T), then hand
+//               the stage to the MMA lane.  Nobody holds weights in registers across a latency any more, and the
+//               epilogue warps never touch a weight.
+// Stage ring: tma_full (TMA landed) -> conv_full (converted) -> empty (tcgen05.commit: MMAs retired).
+#include <cuda.h>
 #include "common.cuh"
 
 namespace dmdqn {
@@ -29,12 +35,18 @@ namespace {
 
 constexpr int H = 256;          // hidden width served by this path
 constexpr int BM = 128;         // batch rows per CTA (UMMA M)
-constexpr int NT = 256;         // producer / epilogue threads: 8 warps, two per TMEM sub-partition
-constexpr int NT_F = NT + 32;   // K3 / K4a add one warp whose lane 0 only issues tcgen05.mma
-constexpr int KC = 16;          // k-rows of the streamed operand per stage
+constexpr int EW = 16;          // gather / epilogue warps of K3 / K4a
+constexpr int NT = EW * 32;     // 512 threads
+constexpr int W_MMA = EW, W_TMA = EW + 1, W_CONV = EW + 2;   // warps 18..21: two converter groups of two warps; 22, 23 idle
+constexpr int CONV_WARPS = 4, CONV_GROUP_WARPS = 2;          // d.W^T: two groups of two warps, one per in-place stage
+constexpr int NT_F = (EW + 8) * 32;   // 768 threads per K3 / K4a CTA: six warpgroups (setmaxnreg is per warpgroup)
+// Register split (setmaxnreg works per warpgroup, inside the pool the CTA was launched with: 768 x 80): the MMA / TMA
+// warpgroup and the converter warpgroup shrink to 32 and release 2 x 128 x 48 registers, which is exactly what the
+// four gather / epilogue warpgroups need to grow to 104 (4 x 128 x 24).
+constexpr int REGS_EPI = 104, REGS_AUX = 32;
+constexpr int KC = 16;          // k-rows of a K4b operand chunk
 constexpr uint32_t ATOM = BM * 128;           // bytes of one K-major SW128 atom column (128 rows x 32 floats)
-constexpr uint32_t STAGE = 2 * KC * H * 4;    // hi + lo of a 16 x 256 chunk
-constexpr uint32_t SPIN_LIMIT = 1u << 20;
+constexpr unsigned long long WAIT_LIMIT_NS = 2000000000ull;   // a wrong descriptor must end in an error flag, not in a hung GPU
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers (syntax as in the CUTLASS sm100 headers shipped with the image).
@@ -67,18 +79,50 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-// Bounded wait: a wrong descriptor must end in an error flag, not in a hung GPU.
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");   // suspend-time hint (ns): sleep instead of re-polling
+    return done;
+}
+// Bounded wait (wall-clock bound, ~2 s): false = the phase never completed.
+__device__ __forceinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        if (mbar_try(bar, parity)) return true;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > WAIT_LIMIT_NS) return false;
+    }
+}
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    for (uint32_t spin = 0; spin < SPIN_LIMIT && !done; ++spin)
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                     : "=r"(done) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");   // suspend-time hint (ns): sleep instead of re-polling
-    return done != 0;
+    if (mbar_try(bar, parity)) return true;
+    if (mbar_try(bar, parity)) return true;
+    return mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void prod_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 producer warps only
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// TMA, 1-D: `bytes` contiguous bytes global -> shared memory, completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar) : "memory");
+}
+// TMA, tensor map: one box of a rank-3 tensor
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+                 "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+template <int N> __device__ __forceinline__ void regs_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void regs_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }    // the 16 gather / epilogue warps of K3 / K4a
+__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void prod_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 producer warps of K4b
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -162,27 +206,18 @@ struct TcArgs {
     int* error;
 };
 
-// Phase stamps (build with -DTC_TIMING, tools/phase_timing.py): thread 0 of a few CTAs prints clock64 deltas.
-#ifndef TC_EXP
-#define TC_EXP 0
-#endif
-#ifndef WG_EXP
-#define WG_EXP 0      // K4b experiment bits (profiling aid; results are wrong by design)
-#endif
+// Phase stamps (build with -DTC_TIMING, tools/phase_timing.sh): a few threads print clock64 deltas.
 #ifdef TC_TIMING
+#define KT_BEGIN const long long kt0_ = clock64(); long long kt1_ = 0
+#define KT_END(name) do { if (threadIdx.x == 0 && (blockIdx.x % 37 == 0 || blockIdx.x == gridDim.x - 1)) \
+        printf("%s cta %d kernel total %lld cycles, first item at %lld\n", name, blockIdx.x, clock64() - kt0_, kt1_ - kt0_); } while (0)
+#define KT_FIRST() do { if (!kt1_) kt1_ = clock64(); } while (0)
 #define TS_DECL long long ts_[16]; int tsi_ = 0
 #define TS() do { if (tsi_ < 16) ts_[tsi_++] = clock64(); } while (0)
 #define TS_D(i) (i < tsi_ ? ts_[i] - ts_[i - 1] : 0LL)
-#define TS_PRINT(name) do { if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 301 || blockIdx.x == gridDim.x - 1)) \
+#define TS_PRINT(name) do { if (TC_TIMING > 1 && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 77 || blockIdx.x == gridDim.x - 1)) \
         printf("%s cta %d: %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld | total %lld\n", name, blockIdx.x, TS_D(1), TS_D(2), TS_D(3), \
-               TS_D(4), TS_D(5), TS_D(6), TS_D(7), TS_D(8), TS_D(9), TS_D(10), ts_[tsi_ - 1] - ts_[0]); } while (0)
-#else
-#define TS_DECL
-#define TS()
-#define TS_PRINT(name)
-#endif
-
-#ifdef TC_TIMING
+               TS_D(4), TS_D(5), TS_D(6), TS_D(7), TS_D(8), TS_D(9), TS_D(10), ts_[tsi_ - 1] - ts_[0]); tsi_ = 0; } while (0)
 #define WG_TS_DECL long long wts_[20]; int wtsi_ = 0
 #define WG_TS() do { if (wtsi_ < 20) wts_[wtsi_++] = clock64(); } while (0)
 #define WG_D(i) ((i) < wtsi_ ? wts_[i] - wts_[(i) - 1] : 0LL)
@@ -190,6 +225,12 @@ struct TcArgs {
         printf("%s cta %d: %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld\n", name, blockIdx.x, WG_D(1), WG_D(2), WG_D(3), WG_D(4), \
                WG_D(5), WG_D(6), WG_D(7), WG_D(8), WG_D(9), WG_D(10), WG_D(11), WG_D(12), WG_D(13), WG_D(14)); } while (0)
 #else
+#define KT_FIRST()
+#define KT_BEGIN
+#define KT_END(name)
+#define TS_DECL
+#define TS()
+#define TS_PRINT(name)
 #define WG_TS_DECL
 #define WG_TS()
 #define WG_TS_PRINT(name, cond)
@@ -199,49 +240,34 @@ struct TcArgs {
 struct Fwd {
     static constexpr uint32_t R = 0;                          // 128 KB: X hi|lo during layer 1, then activation hi
     static constexpr uint32_t XLO = 3 * ATOM;                 // X lo (K <= 96) inside R
-    static constexpr uint32_t WB = 8 * ATOM;                  // 2 weight stages
-    static constexpr uint32_t BIAS1 = WB + 2 * STAGE;         // b1[256]
+    static constexpr uint32_t WB = 8 * ATOM;                  // 80 KB of weight buffers: x.W: 6 raw slots of 8 KB (TMA targets) + 2 stages of
+                                                              // 16 KB (hi | lo); d.W^T: 2 in-place stages of 32 KB over the first 64 KB
+    static constexpr uint32_t STG = WB + 6 * 8192;            // the two x.W stages
+    static constexpr uint32_t BIAS1 = WB + 81920;             // b1[256]
     static constexpr uint32_t BIAS2 = BIAS1 + 1024;           // b2[256]
     static constexpr uint32_t W3S = BIAS2 + 1024;             // W3[256][4]
-    static constexpr uint32_t QP = W3S + 4096;                // q partials [2][128][4]
-    static constexpr uint32_t ROWF = QP + 4096;               // per-row words [6][128]: loss term, q[4], action
-    static constexpr uint32_t BARS = ROWF + 4096;             // full[4] | empty[4] mbarriers | tmem base
-    static constexpr uint32_t TOTAL = BARS + 128;
+    static constexpr uint32_t QP = W3S + 4096;                // q partials [4][128][4]; K4a: dW3 / db2 partials of the upper row half
+    static constexpr uint32_t ROWF = QP + 8192;               // per-row words: [BM ..] dL/dq 4-vectors, [7 BM ..] warp partials (3760 bytes used)
+    static constexpr uint32_t BARS = ROWF + 3840;             // mbarriers | tmem base: the last 256 bytes of the ROWF block
+    static constexpr uint32_t TOTAL = ROWF + 4096;            // + 1 KB alignment slack = 232 448 bytes: all of the 227 KB a CTA can have
 };
-
-// ------------------------------------------------------------------------------------------
-// Streamed GEMM: D[128 x 256] (TMEM columns 0..255) = A[128 x K] * op(W), fp32 via PASSES MMAs.
-//   A hi: shared memory, K-major SW128 at a_hi; A lo: shared memory (a_lo_smem != 0) or TMEM columns.
-//   BT = false: W is [K][256] row-major (x.W),   staged MN-major, 8-row chunks, 4 stages;
-//   BT = true : W is [256][K] row-major (d.W^T), staged K-major SW64, 16-column chunks, 2 stages.
-// Warp-specialised: the 8 producer warps copy + split weight chunks and arrive on full[stage]; lane 0
-// of warp 8 waits on full[stage], issues the MMAs and commits to empty[stage], which producers wait on
-// before refilling.  No CTA-wide barrier inside the loop.  cnt[] = chunks that have gone through each
-// stage so far (mbarrier phase bookkeeping; both roles run the same sequence).
-// ------------------------------------------------------------------------------------------
-// Barrier block of the K3 / K4a kernels (byte offsets from Fwd::BARS).
+// Barrier block (byte offsets from Fwd::BARS).
 struct Bar {
-    static constexpr uint32_t FULL_F = 0, EMPTY_F = 32;      // x.W pipe: 4 stages
-    static constexpr uint32_t TMEM = 64;                     // TMEM base address (written by tcgen05.alloc)
-    static constexpr uint32_t FULL_B = 72, EMPTY_B = 88;     // d.W^T pipe: 2 stages
-    static constexpr uint32_t AREADY = 104, DONE = 112;      // A operand published (8 warps) / GEMM retired (1 commit)
+    static constexpr uint32_t RAW_FULL = 0, RAW_EMPTY = 48;              // x.W raw ring: 6 slots (TMA landed / converters have read it)
+    static constexpr uint32_t CONV_F = 96, EMPTY_F = 112;                // x.W stage ring: 2 stages (converted / MMAs retired)
+    static constexpr uint32_t TMA_B = 128, CONV_B = 144, EMPTY_B = 160;  // d.W^T ring: 2 in-place stages (same shared memory)
+    static constexpr uint32_t AREADY = 176, DONE = 184;                  // A operand published (16 warps) / GEMM retired (1 commit)
+    static constexpr uint32_t TMEM = 192;                                // TMEM base address (written by tcgen05.alloc)
 };
+constexpr int NRAW = 6, NSF = 2, NSB = 2;                     // raw slots / stages of the x.W pipe, stages of the d.W^T ring
+constexpr uint32_t STG_F = 16384, RAW_F = 8192;               // x.W   stage: hi 8 KB | lo 8 KB   (8 k-rows x 256 columns)
+constexpr uint32_t STG_B = 32768, RAW_B = 16384;              // d.W^T stage: hi 16 KB | lo 16 KB (256 rows x 16 k-columns)
 
-template <bool BT>
-struct Pipe {
-    static constexpr int KCX = BT ? 16 : 8;                   // k extent of a chunk
-    static constexpr int NST = BT ? 2 : 4;                    // shared-memory stages
-    static constexpr int GROUPS = NST;                        // one producer group per stage: chunk c belongs to group c % NST
-    static constexpr int WPC = (NT / 32) / GROUPS;            // warps of a group (2 forward, 4 backward)
-    static constexpr uint32_t HALF = KCX * H * 4;             // bytes of the hi (or lo) part of a stage
-    static constexpr int PIECES = KCX * H / 4 / (32 * WPC);   // 16-byte pieces per lane per chunk (8)
-    static constexpr uint32_t FULL = BT ? Bar::FULL_B : Bar::FULL_F, EMPTY = BT ? Bar::EMPTY_B : Bar::EMPTY_F;
-};
-
-// Phase bookkeeping shared by the producer warps and the MMA lane (both walk the same GEMM sequence):
-// how often every stage of each pipe has been used, and how many GEMMs have retired.
-struct PipeState {
-    uint32_t uses_f = 0, uses_b = 0, gemms = 0;
+// Chunk / GEMM counters.  Every role walks the same sequence of items, GEMMs and chunks, so each keeps its own copy:
+// f / b = chunks that have gone through the x.W / d.W^T ring so far (stage = count % stages, use = count / stages,
+// mbarrier parity = use & 1), gemms = GEMMs retired (parity of AREADY / DONE).
+struct Ring {
+    uint32_t f = 0, b = 0, gemms = 0;
 };
 
 __device__ __forceinline__ float4 ldg_stream(const float* p) {   // volatile: issue order = program order
@@ -257,140 +283,159 @@ __device__ __forceinline__ float4 ldg_plain(const float* p) {    // coherent (th
 __device__ __forceinline__ void sts4(uint32_t a, const float4& v) {
     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
-
-// Every producer thread calls this once its part of the next GEMM's A operand (shared memory and / or
-// TMEM) is written: generic-proxy writes -> async proxy, tcgen05.st -> tcgen05.mma, one arrival per warp.
-__device__ __forceinline__ void a_ready(uint32_t sbase) {
-    fence_async_smem();
-    tc_fence_before();
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(sbase + Fwd::BARS + Bar::AREADY);
+__device__ __forceinline__ float4 lds4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
 }
 
-// Producer side of a streamed GEMM.  Every shared-memory stage is OWNED by one producer group (a warp pair
-// forward, four warps backward): group g stages chunks g, g + NST, ... on its own -- global -> registers ->
-// (hi | lo) -> shared memory -> one arrival per warp on full[g] -- and keeps its next TWO chunks in
-// registers, i.e. the loads of a chunk are issued 2 * NST chunk-times (~3500 cycles of MMA work) before it
-// is staged.  Groups never wait for each other, so the per-chunk latency chain (empty wait, stores, proxy
-// fence, arrive) of one group overlaps with the chains of the others instead of pacing the whole CTA.
-// Because a group sees every phase of its own stage's empty[] barrier, its parity waits are never more than
-// one phase behind (a waiter that skips phases cannot tell "two ahead" from "not yet": that deadlocked an
-// earlier version in which a stage was shared by two groups).
-// begin() can be called ahead of the epilogue that produces the A operand, run() after a_ready().
-template <int PASSES, bool BT>
-struct WStream {
-    using P = Pipe<BT>;
-    float4 buf[2][P::PIECES];
-    const float* src;             // this lane's piece 0 of chunk 0
-    uint32_t dst;                 // its offset inside a stage
-    int nchunks, grp;
-    // forward : lane L of the pair (0..63), piece i -> k-row i, columns 4L: a pair load covers one whole 1 KB row
-    // backward: lane L of the four warps (0..127), piece i -> row n = 32 i + L/4, k piece L%4
+// ------------------------------------------------------------------------------------------
+// TMA producer (lane 0 of warp W_TMA).
+// ------------------------------------------------------------------------------------------
+// x.W: W is [K][256] row-major; chunk c = rows 8c .. 8c+7 = 8 KB contiguous -> a raw slot, as it lies.  Six slots deep:
+// under load an L2 read takes ~2 000 cycles and the tensor pipe wants a chunk every ~470.
+__device__ __forceinline__ bool tma_fwd(uint32_t sbase, const float* __restrict__ W, int K, Ring& r, bool ok) {
+    const uint32_t bars = sbase + Fwd::BARS;
+    for (int c = 0; c < (K >> 3); ++c) {
+        const uint32_t s = r.f % NRAW, u = r.f / NRAW;
+        if (u && ok) ok = mbar_wait(bars + Bar::RAW_EMPTY + 8 * s, (u - 1) & 1);      // the converters have read the previous chunk of this slot
+        mbar_expect_tx(bars + Bar::RAW_FULL + 8 * s, RAW_F);
+        bulk_g2s(sbase + Fwd::WB + s * RAW_F, W + (size_t)c * 8 * H, RAW_F, bars + Bar::RAW_FULL + 8 * s);
+        ++r.f;
+    }
+    return ok;
+}
+// d.W^T: box {16 k-columns, 256 rows, network g} of W2 seen as a rank-3 tensor -> 256 rows of 64 B, dense
+__device__ __forceinline__ bool tma_bwd(uint32_t sbase, const CUtensorMap* tm, int g, Ring& r, bool ok) {
+    const uint32_t bars = sbase + Fwd::BARS;
+    for (int c = 0; c < H / 16; ++c) {
+        const uint32_t s = r.b % NSB, u = r.b / NSB;
+        if (u && ok) ok = mbar_wait(bars + Bar::EMPTY_B + 8 * s, (u - 1) & 1);
+        mbar_expect_tx(bars + Bar::TMA_B + 8 * s, RAW_B);
+        tma_load_3d(sbase + Fwd::WB + s * STG_B, tm, c * 16, 0, g, bars + Bar::TMA_B + 8 * s);      // in place: the hi half of the stage
+        ++r.b;
+    }
+    return ok;
+}
+// The TMA lane must have seen every phase of DONE before it waits for a later one (a parity wait cannot tell
+// "two phases ahead" from "not yet").
+__device__ __forceinline__ bool tma_wait_gemm(uint32_t sbase, uint32_t& seen, uint32_t upto, bool ok) {
+    while (seen <= upto) {
+        if (ok) ok = mbar_wait(sbase + Fwd::BARS + Bar::DONE, seen & 1);
+        ++seen;
+    }
+    return ok;
+}
 
-    __device__ __forceinline__ const float* piece_src(int i, int c) const {
-        if (!BT) return src + (size_t)c * P::KCX * H + (size_t)i * H;
-        return src + (size_t)c * P::KCX + (size_t)i * 32 * H;
-    }
-    __device__ __forceinline__ uint32_t piece_dst(int i) const {
-        // forward: off_mn(H, k = i, mn): k/4 selects a 4 KB block of 8 atoms, k%4 the 128-byte row and the 32-byte xor
-        if (!BT) return (dst + (uint32_t)(i >> 2) * (H >> 5) * 512 + (uint32_t)(i & 3) * 128) ^ ((uint32_t)(i & 3) << 5);
-        return dst + (uint32_t)i * 32 * 64;                   // off_k64: 64-byte rows, the xor pattern repeats every 8 rows
-    }
-    __device__ __forceinline__ void load(int slot, int c) {
-#if TC_EXP == 1
-        return;
-#endif
+// ------------------------------------------------------------------------------------------
+// Converters (warps W_CONV .. W_CONV + 3, tc = 0..127): raw fp32 chunk -> hi | lo halves of a stage in the UMMA canonical layout.
+//   x.W:   all four warps take the chunk out of its raw slot (16 bytes x 4 per thread), free the slot for the TMA lane, and
+//          write the split pieces into one of the two stages (MN-major "128B_BASE32B") as soon as its MMAs have retired;
+//   d.W^T: the chunk was loaded straight into the hi half of its stage and is converted IN PLACE (K-major 64-byte swizzle;
+//          the swizzle permutes the four 16-byte pieces of a 64-byte row among themselves, and those sit on four
+//          neighbouring lanes, so a warp barrier between reading and writing is all it needs).  Two groups of two warps,
+//          group g owns stage g, so each group sees every phase of its stage's mbarriers in order (a parity wait that is
+//          one full phase early succeeds at once).
+// ------------------------------------------------------------------------------------------
+template <int PASSES>
+__device__ __forceinline__ bool conv_fwd(uint32_t sbase, int K, int tc, Ring& r, bool ok) {
+    const uint32_t bars = sbase + Fwd::BARS;
+    const int k0 = tc >> 6, n = (tc & 63) << 2;               // piece p = tc + 128 i: k-row tc / 64 + 2 i, columns 4 (tc % 64) .. + 3
+    for (int c = 0; c < (K >> 3); ++c) {
+        const uint32_t rs = r.f % NRAW, ru = r.f / NRAW, s = r.f % NSF, u = r.f / NSF;
+        if (ok) ok = mbar_wait(bars + Bar::RAW_FULL + 8 * rs, ru & 1);                // the raw chunk has landed
+        float4 x[4];
 #pragma unroll
-        for (int i = 0; i < P::PIECES; ++i) buf[slot][i] = ldg_stream(piece_src(i, TC_EXP == 3 ? 0 : c));
-    }
-    // W: [K][H] row-major (BT = false) or [H][K] row-major with K = H (BT = true)
-    __device__ __forceinline__ void begin(const float* __restrict__ W, int K) {
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        const int L = (warp % P::WPC) * 32 + lane;
-        nchunks = K / P::KCX;
-        grp = warp / P::WPC;
-        if (!BT) {
-            src = W + (L << 2);
-            dst = off_mn(H, 0, L << 2);                       // k = 0: no xor yet
-        } else {
-            src = W + (size_t)(L >> 2) * H + ((L & 3) << 2);
-            dst = off_k64(H, L >> 2, (L & 3) << 2);
+        for (int i = 0; i < 4; ++i) x[i] = lds4(sbase + Fwd::WB + rs * RAW_F + (uint32_t)(tc + 128 * i) * 16u);
+        // Generic-proxy reads of the slot must be ordered before the async-proxy (TMA) write that refills it: without this
+        // fence ptxas issues the arrive right behind the four LDS and ~1 % of the tiles saw a partly refilled chunk under load
+        // (tools/dbg_k3_repeat.py reproduces it in seconds).
+        fence_async_smem();
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(bars + Bar::RAW_EMPTY + 8 * rs);
+        if (u && ok) ok = mbar_wait(bars + Bar::EMPTY_F + 8 * s, (u - 1) & 1);        // the MMAs of the stage's previous chunk have retired
+        const uint32_t st = sbase + Fwd::STG + s * STG_F;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float4 hi, lo;
+            split4<PASSES>(x[i], hi, lo);
+            const uint32_t o = st + off_mn(H, k0 + 2 * i, n);
+            sts4(o, hi);
+            if (PASSES == 3) sts4(o + RAW_F, lo);
         }
-        if (grp < nchunks) load(0, grp);
-        if (grp + P::NST < nchunks) load(1, grp + P::NST);
+        fence_async_smem();
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(bars + Bar::CONV_F + 8 * s);
+        ++r.f;
     }
-    __device__ __forceinline__ bool run(uint32_t sbase, PipeState& ps) {
-        const uint32_t full = sbase + Fwd::BARS + P::FULL + 8 * grp, empty = sbase + Fwd::BARS + P::EMPTY + 8 * grp;
-        const uint32_t st = sbase + Fwd::WB + grp * (2 * P::HALF);
-        uint32_t u = BT ? ps.uses_b : ps.uses_f;              // use number of this group's stage
-        bool ok = true;
-        for (int c0 = grp; c0 < nchunks; c0 += 2 * P::NST) {
+    return ok;
+}
+template <int PASSES>
+__device__ __forceinline__ bool conv_bwd(uint32_t sbase, int grp, int t, Ring& r, bool ok) {
+    const uint32_t bars = sbase + Fwd::BARS;
+    for (int c = 0; c < H / 16; ++c) {
+        const uint32_t b = r.b + (uint32_t)c;
+        if ((int)(b % NSB) != grp) continue;                  // group g owns stage g
+        const uint32_t s = b % NSB, u = b / NSB;
+        const uint32_t st = sbase + Fwd::WB + s * STG_B;
+        if (ok) ok = mbar_wait(bars + Bar::TMA_B + 8 * s, u & 1);
+        // piece p = t + 64 j: row p / 4 = t / 4 + 16 j, 16-byte piece t % 4 of its 64-byte row.  The swizzle permutes the four
+        // pieces of a row among themselves, and those sit on four neighbouring lanes: a warp barrier is all it needs.
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int c = c0 + j * P::NST;
-                if (c < nchunks) {                            // uniform across the group
-                    if (u && ok) ok = mbar_wait(empty, (u - 1) & 1);            // the MMAs of the previous use are done
-                    ++u;
-#if TC_EXP == 4
+        for (int rnd = 0; rnd < 4; ++rnd) {
+            float4 x[4];
 #pragma unroll
-                    for (int i = 0; i < P::PIECES; ++i) asm volatile("" ::"f"(buf[j][i].x), "f"(buf[j][i].y), "f"(buf[j][i].z), "f"(buf[j][i].w));
-#elif TC_EXP != 1
+            for (int i = 0; i < 4; ++i) x[i] = lds4(st + (uint32_t)(t + 64 * (4 * rnd + i)) * 16u);
+            __syncwarp();
 #pragma unroll
-                    for (int i = 0; i < P::PIECES; ++i) {
-                        float4 hi, lo;
-                        split4<PASSES>(buf[j][i], hi, lo);
-                        const uint32_t o = st + piece_dst(i);
-                        sts4(o, hi);
-                        if (PASSES == 3) sts4(o + P::HALF, lo);
-                    }
-#endif
-                    if (c + 2 * P::NST < nchunks) load(j, c + 2 * P::NST);      // two own chunks ahead
-                    fence_async_smem();
-                    __syncwarp();
-                    if ((threadIdx.x & 31) == 0) mbar_arrive(full);             // WPC arrivals complete the stage
-                }
+            for (int i = 0; i < 4; ++i) {
+                const int row = (t >> 2) + 16 * (4 * rnd + i), pc = t & 3;
+                float4 hi, lo;
+                split4<PASSES>(x[i], hi, lo);
+                const uint32_t o = st + (uint32_t)row * 64u + (uint32_t)((pc ^ ((row >> 1) & 3)) << 4);   // off_k64
+                sts4(o, hi);
+                if (PASSES == 3) sts4(o + RAW_B, lo);
             }
         }
-        if (ok) ok = mbar_wait(sbase + Fwd::BARS + Bar::DONE, ps.gemms & 1);     // every MMA of this GEMM has retired
-        tc_fence_after();
-        (BT ? ps.uses_b : ps.uses_f) += (uint32_t)(nchunks / P::NST);
-        ps.gemms += 1;
-        return ok;
+        fence_async_smem();
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(bars + Bar::CONV_B + 8 * s);
     }
-};
+    r.b += (uint32_t)(H / 16);
+    return ok;
+}
 
+// ------------------------------------------------------------------------------------------
+// MMA lane (lane 0 of warp W_MMA): D[128 x 256] (TMEM columns 0..255) = A[128 x K] * op(W), fp32 via PASSES MMAs.
+//   A hi: shared memory, K-major SW128 at a_hi; A lo: shared memory (a_lo_smem != 0) or TMEM columns.
+//   BT = false: x.W, stages MN-major, one k-step per chunk;  BT = true: d.W^T, stages K-major SW64, two k-steps per chunk.
+// ------------------------------------------------------------------------------------------
 template <int PASSES, bool BT>
-__device__ __forceinline__ bool gemm_mma(uint32_t sbase, uint32_t tmem, uint32_t a_hi, uint32_t a_lo_smem,
-                                         uint32_t a_lo_tmem, int K, PipeState& ps) {
-    using P = Pipe<BT>;
-    const uint32_t full0 = sbase + Fwd::BARS + P::FULL, empty0 = sbase + Fwd::BARS + P::EMPTY;
-    const uint32_t uses0 = BT ? ps.uses_b : ps.uses_f;
-    const int nchunks = K / P::KCX;
-    bool ok = true;
+__device__ __forceinline__ bool mma_gemm(uint32_t sbase, uint32_t tmem, uint32_t a_hi, uint32_t a_lo_smem, uint32_t a_lo_tmem,
+                                         int K, Ring& r, bool ok) {
+    const uint32_t bars = sbase + Fwd::BARS;
+    constexpr int KCX = BT ? 16 : 8;
     constexpr uint32_t idesc = make_idesc(false, !BT);
     // Descriptors differ only in their 14-bit start-address field: build each once, then add (bytes >> 4).
     const uint64_t a_hi0 = make_desc(a_hi, 16, 1024, 2);
     const uint64_t a_lo0 = make_desc(a_lo_smem, 16, 1024, 2);
-    const uint64_t b0 = BT ? make_desc(sbase + Fwd::WB, 16, 512, 4) : make_desc(sbase + Fwd::WB, 512, 4096, 1);
-    constexpr uint32_t KSTEP_B = BT ? 32 : 2 * 4096;          // bytes between the k-steps of a chunk in the B stage
-    if (ok) ok = mbar_wait(sbase + Fwd::BARS + Bar::AREADY, ps.gemms & 1);   // all 8 producer warps have published the A operand
+    const uint64_t b0 = BT ? make_desc(sbase + Fwd::WB, 16, 512, 4) : make_desc(sbase + Fwd::STG, 512, 4096, 1);
+    if (ok) ok = mbar_wait(bars + Bar::AREADY, r.gemms & 1);      // all 16 epilogue warps have published the A operand
     tc_fence_after();
+    const int nchunks = K / KCX;
     for (int c = 0; c < nchunks; ++c) {
-        const int b = c % P::NST;
-        const uint32_t u = uses0 + (uint32_t)(c / P::NST);
-        if (ok) ok = mbar_wait(full0 + 8 * b, u & 1);         // the owning group has staged chunk c
+        const uint32_t cnt = BT ? r.b : r.f;
+        const uint32_t s = cnt % (BT ? NSB : NSF), u = cnt / (BT ? NSB : NSF);
+        if (ok) ok = mbar_wait(bars + (BT ? Bar::CONV_B : Bar::CONV_F) + 8 * s, u & 1);   // the converters have finished chunk c
         tc_fence_after();
 #pragma unroll
-        for (int ks = 0; ks < P::KCX / 8; ++ks) {
-            const int kg = c * P::KCX + ks * 8;
+        for (int ks = 0; ks < KCX / 8; ++ks) {
+            const int kg = c * KCX + ks * 8;
             const uint32_t a_off = ((uint32_t)(kg >> 5) * ATOM + (uint32_t)((kg & 31) >> 3) * 32) >> 4;
-            const uint32_t b_off = ((uint32_t)b * (2 * P::HALF) + ks * KSTEP_B) >> 4;
+            const uint32_t b_off = (s * (BT ? STG_B : STG_F) + (BT ? ks * 32u : 0u)) >> 4;
             const uint64_t a_hi_d = a_hi0 + a_off;
-            const uint64_t b_hi = b0 + b_off, b_lo = b0 + b_off + (P::HALF >> 4);
+            const uint64_t b_hi = b0 + b_off, b_lo = b0 + b_off + ((BT ? RAW_B : RAW_F) >> 4);
             uint32_t acc = (c | ks) ? 1u : 0u;
-#if TC_EXP == 2
-            continue;
-#endif
             if (PASSES == 3) {                                // small terms first
                 if (a_lo_smem) mma_ss(tmem, a_lo0 + a_off, b_hi, idesc, acc);
                 else mma_ts(tmem, a_lo_tmem + (uint32_t)kg, b_hi, idesc, acc);
@@ -399,20 +444,40 @@ __device__ __forceinline__ bool gemm_mma(uint32_t sbase, uint32_t tmem, uint32_t
             }
             mma_ss(tmem, a_hi_d, b_hi, idesc, acc);
         }
-        umma_commit(empty0 + 8 * b);
+        umma_commit(bars + (BT ? Bar::EMPTY_B : Bar::EMPTY_F) + 8 * s);   // the stage is free once these MMAs retire
+        if (BT) ++r.b; else ++r.f;
     }
-    umma_commit(sbase + Fwd::BARS + Bar::DONE);
-    (BT ? ps.uses_b : ps.uses_f) += (uint32_t)(nchunks / P::NST);
-    ps.gemms += 1;
+    umma_commit(bars + Bar::DONE);
+    r.gemms += 1;
+    return ok;
+}
+
+// ------------------------------------------------------------------------------------------
+// Gather / epilogue side.
+// ------------------------------------------------------------------------------------------
+// Every epilogue thread calls this once its part of the next GEMM's A operand (shared memory and / or TMEM) is
+// written: generic-proxy writes -> async proxy, tcgen05.st -> tcgen05.mma, one arrival per warp.
+__device__ __forceinline__ void a_ready(uint32_t sbase) {
+    fence_async_smem();
+    tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(sbase + Fwd::BARS + Bar::AREADY);
+}
+// ... and this to wait for the GEMM that consumes it (every MMA retired, accumulator readable)
+__device__ __forceinline__ bool wait_gemm(uint32_t sbase, Ring& r, bool ok) {
+    if (ok) ok = mbar_wait(sbase + Fwd::BARS + Bar::DONE, r.gemms & 1);
+    tc_fence_after();
+    r.gemms += 1;
     return ok;
 }
 
 // Gather 128 observation rows -> hi (R) and lo (R + XLO), K-major SW128; rows past the batch are zero.
-// begin() issues every load of the thread (row ids first, then up to 12 independent 16-byte pieces, the
-// pieces of a row on consecutive lanes); store() splits and writes them once R is free.
+// begin() issues every load of the thread (row ids first, then up to 6 independent 16-byte pieces, the
+// pieces of a row on consecutive lanes) -- it is called one item AHEAD, while the tensor pipe works on the
+// current tile; store() splits and writes them once R is free.
 template <int PASSES>
 struct XGather {
-    static constexpr int MAXP = BM * 96 / 4 / NT;             // 12 pieces per thread at obs_stride = 96
+    static constexpr int MAXP = BM * 96 / 4 / NT;             // 6 pieces per thread at obs_stride = 96
     float4 x[MAXP];
     uint32_t off[MAXP];
     int n;
@@ -453,36 +518,34 @@ struct XGather {
     }
 };
 
-// Per-thread epilogue coordinates: thread = batch row of the tile, two warps share a TMEM
-// sub-partition and split the 256 columns in halves.
+// Per-thread epilogue coordinates: thread = batch row of the tile, four warps share a TMEM
+// sub-partition and split the 256 columns in quarters (two 32-column blocks each).
 struct Epi {
-    int row, half;
+    int row, part;
     uint32_t lane_addr;
     __device__ __forceinline__ Epi() {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         row = (warp & 3) * 32 + lane;
-        half = warp >> 2;
+        part = warp >> 2;
         lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     }
 };
 
-// Epilogue of a hidden layer feeding another GEMM: a = relu(D + bias) (or D * mask for dh2 built by
-// the caller); hi -> shared memory R (next A operand), lo -> TMEM columns 256.., raw -> global (optional),
-// returns the relu mask bits of this thread's 128 columns.
+// Epilogue of a hidden layer feeding another GEMM: a = relu(D + bias); hi -> shared memory R (next A operand),
+// lo -> TMEM columns 256.., raw -> global (optional), returns the relu mask bits of this thread's 64 columns.
 // Scratch activations are stored TRANSPOSED, [feature][batch]: a warp's 32 lanes are 32 consecutive
 // batch rows, so every store below is one full 128-byte line, and K4b can stream them K-major.
 template <int PASSES>
 __device__ __forceinline__ void epi_hidden(uint32_t sbase, uint32_t tmem, const Epi& e, uint32_t bias_off,
-                                           float* __restrict__ gout_t, int ldt, uint32_t (&mask)[4]) {
+                                           float* __restrict__ gout_t, int ldt, uint32_t (&mask)[2]) {
 #pragma unroll 1
-    for (int cc = 0; cc < 4; ++cc) {
-        const int c0 = e.half * 128 + cc * 32;
+    for (int cc = 0; cc < 2; ++cc) {
+        const int c0 = e.part * 64 + cc * 32;
         float v[32], lo[32];
         float4 bq[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j)       // every bias load of the block before the first (volatile) store below
-            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bq[j].x), "=f"(bq[j].y), "=f"(bq[j].z), "=f"(bq[j].w)
-                         : "r"(sbase + bias_off + (uint32_t)(c0 + 4 * j) * 4));
+            bq[j] = lds4(sbase + bias_off + (uint32_t)(c0 + 4 * j) * 4);
         tmem_ld32(tmem + e.lane_addr + (uint32_t)c0, v);
         uint32_t m = 0;
 #pragma unroll
@@ -498,26 +561,25 @@ __device__ __forceinline__ void epi_hidden(uint32_t sbase, uint32_t tmem, const 
             }
             float4 hi, l4;
             split4<PASSES>(x, hi, l4);
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sbase + Fwd::R + off_k128(BM, e.row, c0 + j)), "f"(hi.x),
-                         "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+            sts4(sbase + Fwd::R + off_k128(BM, e.row, c0 + j), hi);
             lo[j] = l4.x; lo[j + 1] = l4.y; lo[j + 2] = l4.z; lo[j + 3] = l4.w;
         }
         mask[cc] = m;
         if (PASSES == 3) tmem_st32(tmem + e.lane_addr + 256u + (uint32_t)c0, lo);
     }
     if (PASSES == 3) tmem_st_wait();
-    // visibility to the MMA warp comes with this thread's next arrive on a full[] barrier
+    // visibility to the MMA lane comes with this thread's a_ready()
 }
 
-// Epilogue of layer 2 feeding the 4-wide head: q[a] = b3[a] + sum_j relu(D[j] + b2[j]) * W3[j][a]; the two
-// column halves of a row are combined in fixed order through shared memory.  Optionally stores the raw
+// Epilogue of layer 2 feeding the 4-wide head: q[a] = b3[a] + sum_j relu(D[j] + b2[j]) * W3[j][a]; the four
+// column quarters of a row are combined in fixed order through shared memory.  Optionally stores the raw
 // h2 row (for dW3) and returns the relu mask.
 __device__ __forceinline__ void epi_head(uint32_t sbase, uint32_t tmem, const Epi& e, bool keep_h2,
-                                         uint32_t (&mask)[4], float (&q)[4], const float* __restrict__ b3) {
+                                         uint32_t (&mask)[2], float (&q)[4], const float* __restrict__ b3) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
-    for (int cc = 0; cc < 4; ++cc) {
-        const int c0 = e.half * 128 + cc * 32;
+    for (int cc = 0; cc < 2; ++cc) {
+        const int c0 = e.part * 64 + cc * 32;
         float v[32];
         tmem_ld32(tmem + e.lane_addr + (uint32_t)c0, v);
         uint32_t m = 0;
@@ -528,9 +590,7 @@ __device__ __forceinline__ void epi_head(uint32_t sbase, uint32_t tmem, const Ep
             const float x = fmaxf(v[j] + b, 0.f);
             v[j] = x;
             m |= (x > 0.f ? 1u : 0u) << j;
-            float4 w;
-            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w)
-                         : "r"(sbase + Fwd::W3S + (uint32_t)(c0 + j) * 16));
+            const float4 w = lds4(sbase + Fwd::W3S + (uint32_t)(c0 + j) * 16);
             acc.x = fmaf(x, w.x, acc.x); acc.y = fmaf(x, w.y, acc.y);
             acc.z = fmaf(x, w.z, acc.z); acc.w = fmaf(x, w.w, acc.w);
         }
@@ -538,51 +598,58 @@ __device__ __forceinline__ void epi_head(uint32_t sbase, uint32_t tmem, const Ep
         if (keep_h2) {      // raw h2 tile -> R (free once layer 2 has run), read back column-wise for dW3 / db2
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
-                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sbase + Fwd::R + off_k128(BM, e.row, c0 + j)), "f"(v[j]),
-                             "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+                sts4(sbase + Fwd::R + off_k128(BM, e.row, c0 + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
         }
     }
     float4* qp = reinterpret_cast<float4*>(__cvta_shared_to_generic((size_t)(sbase + Fwd::QP)));
-    qp[e.half * BM + e.row] = acc;
-    prod_sync();
-    const float4 p0 = qp[e.row], p1 = qp[BM + e.row];
-    q[0] = (p0.x + p1.x) + __ldg(b3 + 0); q[1] = (p0.y + p1.y) + __ldg(b3 + 1);
-    q[2] = (p0.z + p1.z) + __ldg(b3 + 2); q[3] = (p0.w + p1.w) + __ldg(b3 + 3);
+    qp[e.part * BM + e.row] = acc;
+    epi_sync();
+    const float4 p0 = qp[e.row], p1 = qp[BM + e.row], p2 = qp[2 * BM + e.row], p3 = qp[3 * BM + e.row];
+    q[0] = ((p0.x + p1.x) + (p2.x + p3.x)) + __ldg(b3 + 0); q[1] = ((p0.y + p1.y) + (p2.y + p3.y)) + __ldg(b3 + 1);
+    q[2] = ((p0.z + p1.z) + (p2.z + p3.z)) + __ldg(b3 + 2); q[3] = ((p0.w + p1.w) + (p2.w + p3.w)) + __ldg(b3 + 3);
 }
 
 __device__ __forceinline__ void load_small_params(uint32_t sbase, const float* __restrict__ P, const Layout& L) {
     float* s = reinterpret_cast<float*>(__cvta_shared_to_generic((size_t)sbase));
-    for (int j = threadIdx.x; j < H; j += NT) {
+    const int j = threadIdx.x;
+    if (j < H) {
         s[Fwd::BIAS1 / 4 + j] = __ldg(P + L.b1 + j);
         s[Fwd::BIAS2 / 4 + j] = __ldg(P + L.b2 + j);
-        reinterpret_cast<float4*>(s + Fwd::W3S / 4)[j] = __ldg(reinterpret_cast<const float4*>(P + L.w3) + j);
+    } else {
+        reinterpret_cast<float4*>(s + Fwd::W3S / 4)[j - H] = __ldg(reinterpret_cast<const float4*>(P + L.w3) + (j - H));
     }
 }
 
 __device__ __forceinline__ uint32_t tc_prologue(uint32_t sbase) {
     const int warp = threadIdx.x >> 5;
+    const uint32_t bars = sbase + Fwd::BARS;
     if (threadIdx.x == 0) {
-        for (int b = 0; b < 4; ++b) {
-            mbar_init(sbase + Fwd::BARS + Bar::FULL_F + 8 * b, Pipe<false>::WPC);    // full[b]: the owning producer group
-            mbar_init(sbase + Fwd::BARS + Bar::EMPTY_F + 8 * b, 1);                  // empty[b]: one tcgen05.commit
+        for (int b = 0; b < NRAW; ++b) {
+            mbar_init(bars + Bar::RAW_FULL + 8 * b, 1);           // one arrive.expect_tx + the bytes of the chunk
+            mbar_init(bars + Bar::RAW_EMPTY + 8 * b, CONV_WARPS); // one arrival per converter warp
         }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(sbase + Fwd::BARS + Bar::FULL_B + 8 * b, Pipe<true>::WPC);
-            mbar_init(sbase + Fwd::BARS + Bar::EMPTY_B + 8 * b, 1);
+        for (int b = 0; b < NSF; ++b) {
+            mbar_init(bars + Bar::CONV_F + 8 * b, CONV_WARPS);    // one arrival per converter warp
+            mbar_init(bars + Bar::EMPTY_F + 8 * b, 1);            // one tcgen05.commit
         }
-        mbar_init(sbase + Fwd::BARS + Bar::AREADY, NT / 32);
-        mbar_init(sbase + Fwd::BARS + Bar::DONE, 1);
+        for (int b = 0; b < NSB; ++b) {
+            mbar_init(bars + Bar::TMA_B + 8 * b, 1);
+            mbar_init(bars + Bar::CONV_B + 8 * b, CONV_GROUP_WARPS);
+            mbar_init(bars + Bar::EMPTY_B + 8 * b, 1);
+        }
+        mbar_init(bars + Bar::AREADY, EW);
+        mbar_init(bars + Bar::DONE, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + Fwd::BARS + Bar::TMEM), "r"(512));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars + Bar::TMEM), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     uint32_t tmem;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(sbase + Fwd::BARS + Bar::TMEM));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(bars + Bar::TMEM));
     return tmem;
 }
 __device__ __forceinline__ void tc_epilogue(uint32_t tmem) {
@@ -592,283 +659,359 @@ __device__ __forceinline__ void tc_epilogue(uint32_t tmem) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K3: one CTA = (network, 128-row tile, which parameter set): Q(s') of the online net (-> q_next) or of the
-// target net (-> tq_all).  The two halves are independent CTAs (twice as many, half as long: less tail on
-// 148 SMs); K4a combines them into the TD target of its rows (reference :342-347).
+// K3: item = (network, 128-row tile, which parameter set): Q(s') of the online net (-> q_next) or of the
+// target net (-> tq_all).  The two halves are independent items (twice as many, half as long: less tail on
+// 148 SMs); K4a combines them into the TD target of its rows (reference :342-347).  A CTA walks the items
+// blockIdx.x, + gridDim.x, ... of active networks; every role runs the same walk.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int k3_next(const TcArgs& A, int q, int n_items) {
+    while (q < n_items && !A.active[(q >> 1) / A.tiles]) q += gridDim.x;
+    return q;
+}
+
 template <int PASSES>
 __global__ void __launch_bounds__(NT_F, 1) tc_target_kernel(const TcArgs A) {
     extern __shared__ uint8_t smem_raw[];
-    const int item = blockIdx.x >> 1, pass = blockIdx.x & 1;          // 0: online(s')  1: target(s')
-    const int g = item / A.tiles, rt = item % A.tiles;
-    if (!A.active[g]) return;
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const int B = A.d.batch, Dp = A.d.obs_stride, r0 = rt * BM;
+    const int B = A.d.batch, Dp = A.d.obs_stride;
+    const int n_items = 2 * A.d.n_nets * A.tiles;
+    const int warp = threadIdx.x >> 5;
+    KT_BEGIN;
     const uint32_t tmem = tc_prologue(sbase);
-    PipeState ps;
+    Ring ring;
     bool ok = true;
-    if (threadIdx.x >= NT) {
-        // ---- MMA warp: lane 0 issues every tcgen05.mma of this CTA ----
-        if (threadIdx.x == NT) {
-            ok = ok && gemm_mma<PASSES, false>(sbase, tmem, sbase + Fwd::R, sbase + Fwd::XLO, 0, Dp, ps);
-            ok = ok && gemm_mma<PASSES, false>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, H, ps);
+    if (warp >= EW) {
+        regs_dec<REGS_AUX>();          // one instruction for both auxiliary warpgroups (.aligned)
+      if (warp == W_MMA) {
+        if ((threadIdx.x & 31) == 0) {
+            for (int q = k3_next(A, blockIdx.x, n_items); q < n_items; q = k3_next(A, q + gridDim.x, n_items)) {
+                ok = mma_gemm<PASSES, false>(sbase, tmem, sbase + Fwd::R, sbase + Fwd::XLO, 0, Dp, ring, ok);
+                ok = mma_gemm<PASSES, false>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, H, ring, ok);
+            }
             if (!ok) atomicExch(A.error, 13);
         }
         __syncwarp();
+      } else if (warp == W_TMA) {
+        if ((threadIdx.x & 31) == 0) {
+            for (int q = k3_next(A, blockIdx.x, n_items); q < n_items; q = k3_next(A, q + gridDim.x, n_items)) {
+                const int g = (q >> 1) / A.tiles;
+                const float* P = ((q & 1) ? A.nets.theta_tgt : A.nets.theta) + (size_t)g * A.L.stride;
+                ok = tma_fwd(sbase, P + A.L.w1, Dp, ring, ok);
+                ok = tma_fwd(sbase, P + A.L.w2, H, ring, ok);
+            }
+            if (!ok) atomicExch(A.error, 23);
+        }
+        __syncwarp();
+      } else if (warp < W_CONV + CONV_WARPS) {   // converters (the last two warps only fill the warpgroup)
+        const int tc = threadIdx.x - W_CONV * 32;
+        for (int q = k3_next(A, blockIdx.x, n_items); q < n_items; q = k3_next(A, q + gridDim.x, n_items)) {
+            ok = conv_fwd<PASSES>(sbase, Dp, tc, ring, ok);
+            ok = conv_fwd<PASSES>(sbase, H, tc, ring, ok);
+        }
+        if (!ok && tc == 0) atomicExch(A.error, 33);
+      }
     } else {
+        regs_inc<REGS_EPI>();
         const Epi e;
-        const float* P = (pass == 0 ? A.nets.theta : A.nets.theta_tgt) + (size_t)g * A.L.stride;
-        float q[4];
-        TS_DECL;
-        TS();
-        WStream<PASSES, false> ws;
-        ws.begin(P + A.L.w1, Dp);                      // first W1 chunks in flight before anything else
-        {
-            XGather<PASSES> xg;
-            xg.begin(A.rp.next_obs, A.rows + (size_t)g * B, r0, B, Dp);
+        XGather<PASSES> xg;
+        int q = k3_next(A, blockIdx.x, n_items);
+        if (q < n_items) {
+            const int g = (q >> 1) / A.tiles, rt = (q >> 1) % A.tiles;
+            xg.begin(A.rp.next_obs, A.rows + (size_t)g * B, rt * BM, B, Dp);
+        }
+        while (q < n_items) {
+            const int item = q >> 1, pass = q & 1;            // 0: online(s')  1: target(s')
+            const int g = item / A.tiles, rt = item % A.tiles, r0 = rt * BM;
+            const float* P = (pass == 0 ? A.nets.theta : A.nets.theta_tgt) + (size_t)g * A.L.stride;
+            TS_DECL;
+            TS();
+            KT_FIRST();
             load_small_params(sbase, P, A.L);
             xg.store(sbase);
+            a_ready(sbase);
+            epi_sync();        // biases / head weights visible to every epilogue thread
+            TS();
+            ok = wait_gemm(sbase, ring, ok);
+            TS();
+            uint32_t mask[2];
+            epi_hidden<PASSES>(sbase, tmem, e, Fwd::BIAS1, nullptr, 0, mask);
+            a_ready(sbase);
+            TS();
+            const int qn = k3_next(A, q + gridDim.x, n_items);
+            if (qn < n_items) {                                // the next tile's rows travel while layer 2 runs
+                const int gn = (qn >> 1) / A.tiles, rtn = (qn >> 1) % A.tiles;
+                xg.begin(A.rp.next_obs, A.rows + (size_t)gn * B, rtn * BM, B, Dp);
+            }
+            ok = wait_gemm(sbase, ring, ok);
+            TS();
+            float qv[4];
+            epi_head(sbase, tmem, e, false, mask, qv, P + A.L.b3);
+            TS();
+            TS_PRINT("K3 store L1 epi1 L2 epi2");
+            const int gr = r0 + e.row;
+            if (e.part == 0 && gr < B) {
+                float* out = (pass == 0 ? A.q_next : A.tq_all) + ((size_t)g * B + gr) * 4;
+                *reinterpret_cast<float4*>(out) = make_float4(qv[0], qv[1], qv[2], qv[3]);
+            }
+            q = qn;
         }
-        a_ready(sbase);
-        prod_sync();   // biases / head weights visible to every epilogue thread
-        TS();
-        ok = ok && ws.run(sbase, ps);
-        TS();
-        ws.begin(P + A.L.w2, H);                       // W2 chunks travel while the epilogue runs
-        uint32_t mask[4];
-        epi_hidden<PASSES>(sbase, tmem, e, Fwd::BIAS1, nullptr, 0, mask);
-        a_ready(sbase);
-        TS();
-        ok = ok && ws.run(sbase, ps);
-        TS();
-        epi_head(sbase, tmem, e, false, mask, q, P + A.L.b3);
-        TS();
-        TS_PRINT("K3 gather L1 epi1 L2 epi2");
-        const int gr = r0 + e.row;
-        if (e.half == 0 && gr < B) {
-            float* out = (pass == 0 ? A.q_next : A.tq_all) + ((size_t)g * B + gr) * 4;
-            *reinterpret_cast<float4*>(out) = make_float4(q[0], q[1], q[2], q[3]);
-        }
+        if (!ok && threadIdx.x == 0) atomicExch(A.error, 3);
+        KT_END("K3");
     }
-    if (!ok && threadIdx.x == 0) atomicExch(A.error, 3);
     tc_epilogue(tmem);
 }
 
 // ------------------------------------------------------------------------------------------
-// K4a
+// K4a: item = (network, 128-row tile).
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int k4_next(const TcArgs& A, int q, int n_items) {
+    while (q < n_items && !A.active[q / A.tiles]) q += gridDim.x;
+    return q;
+}
+
 template <int PASSES>
-__global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A) {
+__global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A, const __grid_constant__ CUtensorMap tmap_w2) {
     extern __shared__ uint8_t smem_raw[];
-    const int g = blockIdx.x / A.tiles, rt = blockIdx.x % A.tiles;
-    if (!A.active[g]) return;
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     float* sf = reinterpret_cast<float*>(__cvta_shared_to_generic((size_t)sbase));
-    const int B = A.d.batch, Dp = A.d.obs_stride, r0 = rt * BM;
-    const size_t sb = (size_t)g * B;
-    const int32_t* rows = A.rows + sb;
-    const float* P = A.nets.theta + (size_t)g * A.L.stride;
+    const int B = A.d.batch, Dp = A.d.obs_stride;
+    const int n_items = A.d.n_nets * A.tiles;
+    const int warp = threadIdx.x >> 5;
+    KT_BEGIN;
     const uint32_t tmem = tc_prologue(sbase);
-    PipeState ps;
+    Ring ring;
     bool ok = true;
-    if (threadIdx.x >= NT) {
-        // ---- MMA warp: lane 0 issues every tcgen05.mma of this CTA ----
-        if (threadIdx.x == NT) {
-            ok = ok && gemm_mma<PASSES, false>(sbase, tmem, sbase + Fwd::R, sbase + Fwd::XLO, 0, Dp, ps);
-            ok = ok && gemm_mma<PASSES, false>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, H, ps);
-            ok = ok && gemm_mma<PASSES, true>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, H, ps);
+    if (warp >= EW) {
+        regs_dec<REGS_AUX>();          // one instruction for both auxiliary warpgroups (.aligned)
+      if (warp == W_MMA) {
+        if ((threadIdx.x & 31) == 0) {
+            for (int q = k4_next(A, blockIdx.x, n_items); q < n_items; q = k4_next(A, q + gridDim.x, n_items)) {
+                ok = mma_gemm<PASSES, false>(sbase, tmem, sbase + Fwd::R, sbase + Fwd::XLO, 0, Dp, ring, ok);
+                ok = mma_gemm<PASSES, false>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, H, ring, ok);
+                ok = mma_gemm<PASSES, true>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, H, ring, ok);
+            }
             if (!ok) atomicExch(A.error, 14);
         }
         __syncwarp();
-        tc_epilogue(tmem);
-        return;
-    }
-    const Epi e;
-    const int gr = r0 + e.row;
-    const bool valid = gr < B;
-
-    TS_DECL;
-    TS();
-    WStream<PASSES, false> ws;
-    ws.begin(P + A.L.w1, Dp);
-    {
+      } else if (warp == W_TMA) {
+        if ((threadIdx.x & 31) == 0) {
+            uint32_t seen = 0, gemm = 0;
+            for (int q = k4_next(A, blockIdx.x, n_items); q < n_items; q = k4_next(A, q + gridDim.x, n_items)) {
+                const int g = q / A.tiles;
+                const float* P = A.nets.theta + (size_t)g * A.L.stride;
+                ok = tma_fwd(sbase, P + A.L.w1, Dp, ring, ok);
+                ok = tma_fwd(sbase, P + A.L.w2, H, ring, ok);
+                ok = tma_wait_gemm(sbase, seen, gemm + 1, ok);       // the d.W^T stages alias the x.W stages: layer 2 must have retired
+                ok = tma_bwd(sbase, &tmap_w2, g, ring, ok);
+                ok = tma_wait_gemm(sbase, seen, gemm + 2, ok);       // ... and the backward GEMM before the next item's W1 chunks
+                gemm += 3;
+            }
+            if (!ok) atomicExch(A.error, 24);
+        }
+        __syncwarp();
+      } else if (warp < W_CONV + CONV_WARPS) {   // converters (the last two warps only fill the warpgroup)
+        const int tc = threadIdx.x - W_CONV * 32, cg = (warp - W_CONV) / CONV_GROUP_WARPS, t = tc % (CONV_GROUP_WARPS * 32);
+        for (int q = k4_next(A, blockIdx.x, n_items); q < n_items; q = k4_next(A, q + gridDim.x, n_items)) {
+            ok = conv_fwd<PASSES>(sbase, Dp, tc, ring, ok);
+            ok = conv_fwd<PASSES>(sbase, H, tc, ring, ok);
+            ok = conv_bwd<PASSES>(sbase, cg, t, ring, ok);
+        }
+        if (!ok && tc == 0) atomicExch(A.error, 34);
+      }
+    } else {
+        regs_inc<REGS_EPI>();
+        const Epi e;
         XGather<PASSES> xg;
-        xg.begin(A.rp.obs, rows, r0, B, Dp);
-        load_small_params(sbase, P, A.L);
-        xg.store(sbase);
-    }
-    // TD target of this row from the two halves of K3 (reference :342-347), ties -> lowest index
-    float yi = 0.f;
-    if (valid) {
-        const float4 qo = *reinterpret_cast<const float4*>(A.q_next + (sb + gr) * 4);
-        const float4 qt = *reinterpret_cast<const float4*>(A.tq_all + (sb + gr) * 4);
-        const float q_on[4] = {qo.x, qo.y, qo.z, qo.w}, q_tg[4] = {qt.x, qt.y, qt.z, qt.w};
-        float bmax = q_on[0], tq = q_tg[0], tmax = q_tg[0];
+        int q = k4_next(A, blockIdx.x, n_items);
+        if (q < n_items) xg.begin(A.rp.obs, A.rows + (size_t)(q / A.tiles) * B, (q % A.tiles) * BM, B, Dp);
+        while (q < n_items) {
+            const int g = q / A.tiles, rt = q % A.tiles, r0 = rt * BM;
+            const size_t sb = (size_t)g * B;
+            const float* P = A.nets.theta + (size_t)g * A.L.stride;
+            const int gr = r0 + e.row;
+            const bool valid = gr < B;
+            TS_DECL;
+            TS();
+            KT_FIRST();
+            load_small_params(sbase, P, A.L);
+            xg.store(sbase);
+            // TD target of this row from the two halves of K3 (reference :342-347), ties -> lowest index
+            float yi = 0.f;
+            if (valid) {
+                const float4 qo = *reinterpret_cast<const float4*>(A.q_next + (sb + gr) * 4);
+                const float4 qt = *reinterpret_cast<const float4*>(A.tq_all + (sb + gr) * 4);
+                const float q_on[4] = {qo.x, qo.y, qo.z, qo.w}, q_tg[4] = {qt.x, qt.y, qt.z, qt.w};
+                float bmax = q_on[0], tq = q_tg[0], tmax = q_tg[0];
 #pragma unroll
-        for (int k = 1; k < 4; ++k) {
-            if (k < A.d.n_actions) {
-                if (q_on[k] > bmax) { bmax = q_on[k]; tq = q_tg[k]; }
-                tmax = fmaxf(tmax, q_tg[k]);
+                for (int k = 1; k < 4; ++k) {
+                    if (k < A.d.n_actions) {
+                        if (q_on[k] > bmax) { bmax = q_on[k]; tq = q_tg[k]; }
+                        tmax = fmaxf(tmax, q_tg[k]);
+                    }
+                }
+                tq = A.double_dqn ? tq : tmax;
+                yi = A.r_hat[sb + gr] + (A.gamma * (1.0f - A.done_b[sb + gr])) * tq;
+                if (e.part == 0) A.y[sb + gr] = yi;
             }
-        }
-        tq = A.double_dqn ? tq : tmax;
-        yi = A.r_hat[sb + gr] + (A.gamma * (1.0f - A.done_b[sb + gr])) * tq;
-        if (e.half == 0) A.y[sb + gr] = yi;
-    }
-    a_ready(sbase);
-    prod_sync();   // biases / head weights visible to every epilogue thread
-    TS();
-    ok = ok && ws.run(sbase, ps);
-    TS();
-    ws.begin(P + A.L.w2, H);
-    uint32_t mask1[4], mask2[4];
-    epi_hidden<PASSES>(sbase, tmem, e, Fwd::BIAS1, valid ? A.h1 + sb * H + gr : nullptr, B, mask1);
-    a_ready(sbase);
-    TS();
-    ok = ok && ws.run(sbase, ps);
-    TS();
-    float q[4];
-    epi_head(sbase, tmem, e, true, mask2, q, P + A.L.b3);
-    TS();
+            a_ready(sbase);
+            epi_sync();        // biases / head weights visible to every epilogue thread
+            TS();
+            ok = wait_gemm(sbase, ring, ok);
+            TS();
+            uint32_t mask1[2], mask2[2];
+            epi_hidden<PASSES>(sbase, tmem, e, Fwd::BIAS1, valid ? A.h1 + sb * H + gr : nullptr, B, mask1);
+            a_ready(sbase);
+            TS();
+            ok = wait_gemm(sbase, ring, ok);
+            TS();
+            float qv[4];
+            epi_head(sbase, tmem, e, true, mask2, qv, P + A.L.b3);
+            TS();
 
-    // loss term and dL/dpred of this row (reference :349-352)
-    float gi = 0.f, term = 0.f;
-    int ai = 0;
-    if (valid) {
-        ai = A.act_b[sb + gr];
-        const float qa = ai == 0 ? q[0] : ai == 1 ? q[1] : ai == 2 ? q[2] : q[3];
-        const float err = qa - yi;
-        if (A.loss == DMDQN_LOSS_MSE) {
-            term = err * err;
-            gi = (2.0f * err) / (float)A.loss_batch;
-        } else {
-            const float ae = fabsf(err);
-            term = ae <= 1.0f ? 0.5f * err * err : ae - 0.5f;
-            gi = fminf(fmaxf(err, -1.0f), 1.0f) / (float)A.loss_batch;
-        }
-        if (e.half == 0) {
-            A.gcoef[sb + gr] = gi;
-            A.ga[sb + gr] = make_float2(gi, __int_as_float(ai));
-            for (int k = 0; k < 4; ++k) A.q_all[(sb + gr) * 4 + k] = q[k];
-        }
-    }
-    float* rowf = sf + Fwd::ROWF / 4;                     // [1..4]: per row float4 g * onehot(action), [7]: warp partials
-    if (e.half == 0) {
-        // dL/dq of this row as a 4-vector (one non-zero): the column loop below then needs no selects
-        reinterpret_cast<float4*>(rowf + BM)[e.row] = make_float4(ai == 0 ? gi : 0.f, ai == 1 ? gi : 0.f, ai == 2 ? gi : 0.f, ai == 3 ? gi : 0.f);
-        // per-tile loss / metric / db3 partials: butterfly over the 32 rows of this warp (fixed order), then
-        // the four warp partials are added in warp order by thread 0
-        float red[11];
-        red[0] = term;
-        red[1] = 0.f; red[2] = 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float qq = (valid && k < A.d.n_actions) ? q[k] : 0.f;
-            red[1] += qq;
-            red[2] = fmaf(qq, qq, red[2]);
-            red[3 + k] = (valid && ai == k) ? 1.f : 0.f;
-            red[7 + k] = (valid && ai == k) ? gi : 0.f;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-            for (int v = 0; v < 11; ++v) red[v] += __shfl_xor_sync(0xffffffffu, red[v], o);
-        if ((threadIdx.x & 31) == 0)
-#pragma unroll
-            for (int v = 0; v < 11; ++v) rowf[7 * BM + (threadIdx.x >> 5) * 11 + v] = red[v];
-    }
-    prod_sync();
-    if (threadIdx.x < 11) {
-        const float* wp = rowf + 7 * BM + threadIdx.x;
-        const float tot = ((wp[0] + wp[11]) + wp[22]) + wp[33];
-        const size_t pt = (size_t)g * A.tiles + rt;
-        if (threadIdx.x < 7) A.part_loss[pt * 8 + threadIdx.x] = tot;      // loss, q sum, q^2 sum, action histogram
-        else A.part_b3[pt * 4 + (threadIdx.x - 7)] = tot;
-    }
-    {   // dW3[j][a] = sum_i h2[i][j] g_i [a_i = a] and db2[j] = sum_i dh2[i][j] over this tile's rows (in order):
-        // thread = column j, rows read back from the h2 tile left in R by epi_head
-        const int j = threadIdx.x;
-        float4 w3;
-        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w3.x), "=f"(w3.y), "=f"(w3.z), "=f"(w3.w)
-                     : "r"(sbase + Fwd::W3S + (uint32_t)j * 16));
-        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, s2 = 0.f;
-        // h2 column j of the tile: K-major SW128, the 16-byte piece index is xor-ed with row % 8
-        const uint32_t hcol = sbase + Fwd::R + (uint32_t)(j >> 5) * ATOM + (uint32_t)((j & 3) << 2);
-        const uint32_t jq = (uint32_t)((j & 31) >> 2);
-        const uint32_t gsel = sbase + Fwd::ROWF + BM * 4;
-#pragma unroll 1
-        for (int i0 = 0; i0 < BM; i0 += 8) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int i = i0 + u;
-                float h;
-                float4 gs;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(h) : "r"(hcol + (uint32_t)i * 128u + ((jq ^ (uint32_t)u) << 4)));
-                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(gs.x), "=f"(gs.y), "=f"(gs.z), "=f"(gs.w) : "r"(gsel + (uint32_t)i * 16u));
-                d0 = fmaf(h, gs.x, d0); d1 = fmaf(h, gs.y, d1); d2 = fmaf(h, gs.z, d2); d3 = fmaf(h, gs.w, d3);
-                const float gw = fmaf(gs.w, w3.w, fmaf(gs.z, w3.z, fmaf(gs.y, w3.y, gs.x * w3.x)));   // = g * W3[j][a]: the other terms are exact zeros
-                s2 += h > 0.f ? gw : 0.f;
+            // loss term and dL/dpred of this row (reference :349-352)
+            float gi = 0.f, term = 0.f;
+            int ai = 0;
+            if (valid) {
+                ai = A.act_b[sb + gr];
+                const float qa = ai == 0 ? qv[0] : ai == 1 ? qv[1] : ai == 2 ? qv[2] : qv[3];
+                const float err = qa - yi;
+                if (A.loss == DMDQN_LOSS_MSE) {
+                    term = err * err;
+                    gi = (2.0f * err) / (float)A.loss_batch;
+                } else {
+                    const float ae = fabsf(err);
+                    term = ae <= 1.0f ? 0.5f * err * err : ae - 0.5f;
+                    gi = fminf(fmaxf(err, -1.0f), 1.0f) / (float)A.loss_batch;
+                }
+                if (e.part == 0) {
+                    A.gcoef[sb + gr] = gi;
+                    A.ga[sb + gr] = make_float2(gi, __int_as_float(ai));
+                    *reinterpret_cast<float4*>(A.q_all + (sb + gr) * 4) = make_float4(qv[0], qv[1], qv[2], qv[3]);
+                }
             }
-        }
-        const size_t pt = (size_t)g * A.tiles + rt;
-        reinterpret_cast<float4*>(A.part_w3 + pt * H * 4)[j] = make_float4(d0, d1, d2, d3);
-        A.part_b2[pt * H + j] = s2;
-    }
-    prod_sync();          // R is rewritten with dh2 below
-    TS();
-
-    WStream<PASSES, true> wsb;
-    wsb.begin(P + A.L.w2, H);
-    // dh2[j] = relu'(h2[j]) * g * W3[j][a]  (dq has one non-zero per row): hi -> R, lo -> TMEM.  It is not
-    // written to global memory: K4b rebuilds its dh2^T operand from relu'(h2) bits, g, the action and W3.
-    if (valid) {
-        reinterpret_cast<uint4*>(A.mask2)[(sb + gr) * 2 + e.half] = make_uint4(mask2[0], mask2[1], mask2[2], mask2[3]);
-    }
-    if (rt == 0)    // W3 as this step saw it (K4b updates W3 while other CTAs of the network still need the old values)
-        reinterpret_cast<float4*>(A.w3_copy + (size_t)g * H * 4)[threadIdx.x] =
-            *reinterpret_cast<const float4*>(sf + Fwd::W3S / 4 + threadIdx.x * 4);
+            float* rowf = sf + Fwd::ROWF / 4;                     // [BM ..]: per row float4 g * onehot(action), [7 BM ..]: warp partials
+            if (e.part == 0) {
+                // dL/dq of this row as a 4-vector (one non-zero): the column loop below then needs no selects
+                reinterpret_cast<float4*>(rowf + BM)[e.row] = make_float4(ai == 0 ? gi : 0.f, ai == 1 ? gi : 0.f, ai == 2 ? gi : 0.f, ai == 3 ? gi : 0.f);
+                // per-tile loss / metric / db3 partials: butterfly over the 32 rows of this warp (fixed order), then
+                // the four warp partials are added in warp order by thread 0
+                float red[11];
+                red[0] = term;
+                red[1] = 0.f; red[2] = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float qq = (valid && k < A.d.n_actions) ? qv[k] : 0.f;
+                    red[1] += qq;
+                    red[2] = fmaf(qq, qq, red[2]);
+                    red[3 + k] = (valid && ai == k) ? 1.f : 0.f;
+                    red[7 + k] = (valid && ai == k) ? gi : 0.f;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int v = 0; v < 11; ++v) red[v] += __shfl_xor_sync(0xffffffffu, red[v], o);
+                if ((threadIdx.x & 31) == 0)
+#pragma unroll
+                    for (int v = 0; v < 11; ++v) rowf[7 * BM + (threadIdx.x >> 5) * 11 + v] = red[v];
+            }
+            epi_sync();
+            if (threadIdx.x < 11) {
+                const float* wp = rowf + 7 * BM + threadIdx.x;
+                const float tot = ((wp[0] + wp[11]) + wp[22]) + wp[33];
+                const size_t pt = (size_t)g * A.tiles + rt;
+                if (threadIdx.x < 7) A.part_loss[pt * 8 + threadIdx.x] = tot;      // loss, q sum, q^2 sum, action histogram
+                else A.part_b3[pt * 4 + (threadIdx.x - 7)] = tot;
+            }
+            {   // dW3[j][a] = sum_i h2[i][j] g_i [a_i = a] and db2[j] = sum_i dh2[i][j] over this tile's rows: thread = (column j,
+                // row half), rows read back in order from the h2 tile left in R by epi_head; lower half + upper half
+                const int j = threadIdx.x & (H - 1), rh = threadIdx.x >> 8;
+                const float4 w3 = lds4(sbase + Fwd::W3S + (uint32_t)j * 16);
+                float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, s2 = 0.f;
+                // h2 column j of the tile: K-major SW128, the 16-byte piece index is xor-ed with row % 8
+                const uint32_t hcol = sbase + Fwd::R + (uint32_t)(j >> 5) * ATOM + (uint32_t)((j & 3) << 2);
+                const uint32_t jq = (uint32_t)((j & 31) >> 2);
+                const uint32_t gsel = sbase + Fwd::ROWF + BM * 4;
 #pragma unroll 1
-    for (int cc = 0; cc < 4; ++cc) {
-        const int c0 = e.half * 128 + cc * 32;
-        float lo[32], wv[32];
+                for (int i0 = rh * (BM / 2); i0 < (rh + 1) * (BM / 2); i0 += 8) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)      // all 32 loads first: the volatile stores below would otherwise serialise load -> store chains
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(wv[j]) : "r"(sbase + Fwd::W3S + (uint32_t)(c0 + j) * 16 + (uint32_t)ai * 4));
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            float x[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) x[t] = ((mask2[cc] >> (j + t)) & 1u) ? gi * wv[j + t] : 0.f;
-            const float4 x4 = make_float4(x[0], x[1], x[2], x[3]);
-            float4 hi, l4;
-            split4<PASSES>(x4, hi, l4);
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sbase + Fwd::R + off_k128(BM, e.row, c0 + j)), "f"(hi.x),
-                         "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
-            lo[j] = l4.x; lo[j + 1] = l4.y; lo[j + 2] = l4.z; lo[j + 3] = l4.w;
-        }
-        if (PASSES == 3) tmem_st32(tmem + e.lane_addr + 256u + (uint32_t)c0, lo);
-    }
-    if (PASSES == 3) tmem_st_wait();
-    a_ready(sbase);
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = i0 + u;
+                        float h;
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(h) : "r"(hcol + (uint32_t)i * 128u + ((jq ^ (uint32_t)u) << 4)));
+                        const float4 gs = lds4(gsel + (uint32_t)i * 16u);
+                        d0 = fmaf(h, gs.x, d0); d1 = fmaf(h, gs.y, d1); d2 = fmaf(h, gs.z, d2); d3 = fmaf(h, gs.w, d3);
+                        const float gw = fmaf(gs.w, w3.w, fmaf(gs.z, w3.z, fmaf(gs.y, w3.y, gs.x * w3.x)));   // = g * W3[j][a]: the other terms are exact zeros
+                        s2 += h > 0.f ? gw : 0.f;
+                    }
+                }
+                float* up = sf + Fwd::QP / 4;                     // [256][8] floats: partials of the upper row half
+                if (rh == 1) {
+                    reinterpret_cast<float4*>(up)[j * 2] = make_float4(d0, d1, d2, d3);
+                    up[j * 8 + 4] = s2;
+                }
+                epi_sync();
+                if (rh == 0) {
+                    const float4 u4 = reinterpret_cast<const float4*>(up)[j * 2];
+                    const size_t pt = (size_t)g * A.tiles + rt;
+                    reinterpret_cast<float4*>(A.part_w3 + pt * H * 4)[j] = make_float4(d0 + u4.x, d1 + u4.y, d2 + u4.z, d3 + u4.w);
+                    A.part_b2[pt * H + j] = s2 + up[j * 8 + 4];
+                }
+            }
+            epi_sync();          // R is rewritten with dh2 below
+            TS();
 
-    TS();
-    // dh1 = (dh2 W2^T) * relu'(h1)
-    ok = ok && wsb.run(sbase, ps);
-    TS();
+            // dh2[j] = relu'(h2[j]) * g * W3[j][a]  (dq has one non-zero per row): hi -> R, lo -> TMEM.  It is not
+            // written to global memory: K4b rebuilds its dh2^T operand from relu'(h2) bits, g, the action and W3.
+            if (valid) reinterpret_cast<uint2*>(A.mask2)[(sb + gr) * 4 + e.part] = make_uint2(mask2[0], mask2[1]);
+            if (rt == 0 && threadIdx.x < H)    // W3 as this step saw it (K4b updates W3 while other CTAs of the network still need the old values)
+                reinterpret_cast<float4*>(A.w3_copy + (size_t)g * H * 4)[threadIdx.x] =
+                    *reinterpret_cast<const float4*>(sf + Fwd::W3S / 4 + threadIdx.x * 4);
 #pragma unroll 1
-    for (int cc = 0; cc < 4; ++cc) {
-        const int c0 = e.half * 128 + cc * 32;
-        float v[32];
-        tmem_ld32(tmem + e.lane_addr + (uint32_t)c0, v);
-        if (valid) {
+            for (int cc = 0; cc < 2; ++cc) {
+                const int c0 = e.part * 64 + cc * 32;
+                float lo[32], wv[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-                A.dh1[sb * H + (size_t)(c0 + j) * B + gr] = ((mask1[cc] >> j) & 1u) ? v[j] : 0.f;
+                for (int j = 0; j < 32; ++j)      // all 32 loads first: the volatile stores below would otherwise serialise load -> store chains
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(wv[j]) : "r"(sbase + Fwd::W3S + (uint32_t)(c0 + j) * 16 + (uint32_t)ai * 4));
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float x[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) x[t] = ((mask2[cc] >> (j + t)) & 1u) ? gi * wv[j + t] : 0.f;
+                    float4 hi, l4;
+                    split4<PASSES>(make_float4(x[0], x[1], x[2], x[3]), hi, l4);
+                    sts4(sbase + Fwd::R + off_k128(BM, e.row, c0 + j), hi);
+                    lo[j] = l4.x; lo[j + 1] = l4.y; lo[j + 2] = l4.z; lo[j + 3] = l4.w;
+                }
+                if (PASSES == 3) tmem_st32(tmem + e.lane_addr + 256u + (uint32_t)c0, lo);
+            }
+            if (PASSES == 3) tmem_st_wait();
+            a_ready(sbase);
+            TS();
+            const int qn = k4_next(A, q + gridDim.x, n_items);
+            if (qn < n_items)                                     // the next tile's rows travel while the backward GEMM runs
+                xg.begin(A.rp.obs, A.rows + (size_t)(qn / A.tiles) * B, (qn % A.tiles) * BM, B, Dp);
+            // dh1 = (dh2 W2^T) * relu'(h1)
+            ok = wait_gemm(sbase, ring, ok);
+            TS();
+#pragma unroll 1
+            for (int cc = 0; cc < 2; ++cc) {
+                const int c0 = e.part * 64 + cc * 32;
+                float v[32];
+                tmem_ld32(tmem + e.lane_addr + (uint32_t)c0, v);
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        A.dh1[sb * H + (size_t)(c0 + j) * B + gr] = ((mask1[cc] >> j) & 1u) ? v[j] : 0.f;
+                }
+            }
+            TS();
+            TS_PRINT("K4a store L1 epi1 L2 epi2 loss+dW3 dh2 bwdGEMM dh1store");
+            q = qn;
         }
+        if (!ok && threadIdx.x == 0) atomicExch(A.error, 4);
+        KT_END("K4a");
     }
-    TS();
-    TS_PRINT("K4a gather L1 epi1 L2 epi2 loss+dW3 dh2 bwdGEMM dh1store");
-    if (!ok && threadIdx.x == 0) atomicExch(A.error, 4);
     tc_epilogue(tmem);
 }
 
@@ -891,9 +1034,6 @@ __device__ __forceinline__ AdamK adam_k(const TcArgs& A, int g) {   // scalars p
     return k;
 }
 __device__ __forceinline__ void adam1(const AdamK& k, float g, float& th, float& m, float& v, float& tg) {
-#if WG_EXP & 1
-    th -= g; m += g; v += g; return;
-#endif
     m = m + (g - m) * k.omb1;
     v = v + (g * g - v) * k.omb2;
     // MUFU square root and reciprocal (each within ~2 ulp): the quotient is a step of at most ~lr, so a few
@@ -908,9 +1048,6 @@ __device__ __forceinline__ void adam1(const AdamK& k, float g, float& th, float&
 
 // Adam on one element without the target sync (the caller applies it per 16-byte group)
 __device__ __forceinline__ void adam_fast(const AdamK& k, float g, float& th, float& m, float& v) {
-#if WG_EXP & 1
-    th -= g; m += g; v += g; return;
-#endif
     m = m + (g - m) * k.omb1;
     v = v + (g * g - v) * k.omb2;
     float sq;
@@ -929,6 +1066,7 @@ struct Wg {     // persistent wgrad kernel, one CTA per SM
     static constexpr uint32_t BARS = W3T + 2 * 4 * H * 4;
     static constexpr uint32_t FULL = 0, EMPTY = 24, ACC_FULL = 48, ACC_FREE = 64, TMEM = 80;   // byte offsets from BARS
     static constexpr uint32_t TOTAL = BARS + 128;
+    static constexpr int NPROD = 8 * 32;                      // producer threads
     static constexpr int NTW = 16 * 32;                       // 8 producer warps (lane 0 of warp 0 also issues the MMAs), 8 epilogue warps
 };
 
@@ -1027,7 +1165,6 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A) {
                         b_lo = make_desc(st + 2 * Wg::A_BYTES + Wg::B_BYTES + ks * 32, 16, 512, 4);
                     }
                     uint32_t acc = (!pend_first || ks) ? 1u : 0u;
-                    if (WG_EXP & 32) continue;
                     if (PASSES == 3) {
                         mma_ss(d_tmem, a_lo, b_hi, idesc, acc);
                         mma_ss(d_tmem, a_hi, b_lo, idesc, 1u);
@@ -1058,7 +1195,6 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A) {
             if (++stage == (uint32_t)Wg::STAGES) { stage = 0; ph ^= 1u; }
         };
         auto put = [&](uint32_t o, uint32_t lo_off, const float4& x) {
-            if (WG_EXP & 64) { asm volatile("" ::"f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w)); return; }
             float4 hi, lo;
             split4<PASSES>(x, hi, lo);
             sts4(o, hi);
@@ -1106,7 +1242,6 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A) {
                     ra[slot][0] = z4; ra[slot][1] = z4;
                     gq[slot] = make_float2(0.f, 0.f);
                     mq[slot] = make_uint4(0u, 0u, 0u, 0u);
-                    if (WG_EXP & 4) return;
                     if (c * KC + ka0 < B) {
                         ra[slot][0] = ldg_stream(pa + c * KC);
                         ra[slot][1] = ldg_stream(pa + c * KC + a_half);
@@ -1162,14 +1297,13 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A) {
                     for (int r = 0; r < 2; ++r) {
                         const int k = c * KC + ak + 8 * r;
                         ra[slot][r] = z4;
-                        if (WG_EXP & 4) continue;
                         if (a_ones) ra[slot][r].x = k < B ? 1.f : 0.f;
                         else if (a_live && k < B) ra[slot][r] = ldg_stream(A.rp.obs + (size_t)__ldg(rows + k) * Dp + am);
                     }
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
                         rb[slot][r] = z4;
-                        if (!(WG_EXP & 4) && c * KC + ((tid & 3) << 2) < B) rb[slot][r] = ldg_stream(b_src + (size_t)c * KC + (size_t)(64 * r) * B);
+                        if (c * KC + ((tid & 3) << 2) < B) rb[slot][r] = ldg_stream(b_src + (size_t)c * KC + (size_t)(64 * r) * B);
                     }
                 };
 #pragma unroll
@@ -1199,7 +1333,7 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A) {
         if (!ok && tid == 0) atomicExch(A.error, 5);
     } else {
         // ------------------------------------------------------------------ epilogue -------------------
-        const int et = tid - NT, ew = warp - 8;                   // 0..255 / 0..7
+        const int et = tid - Wg::NPROD, ew = warp - 8;                   // 0..255 / 0..7
         const int ehalf = ew >> 2;                                // TMEM lane = weight row (ew & 3) * 32 + lane of the tile; column half
         const uint32_t lane_addr = (uint32_t)((ew & 3) * 32) << 16;
         float* tile = reinterpret_cast<float*>(__cvta_shared_to_generic((size_t)(sbase + Wg::TILES))) + ew * (32 * Wg::TLD);
@@ -1213,6 +1347,10 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A) {
                 if (t == 2 && et < DMDQN_METRICS_STRIDE && A.metrics) A.metrics[g * DMDQN_METRICS_STRIDE + et] = 0.f;
                 continue;
             }
+            // A bounded mbarrier wait that expired (here or in K3 / K4a of this step) means the accumulators are garbage:
+            // leave theta / m / v alone and report it through the learned flag instead of applying the update.
+            const int err_code = *reinterpret_cast<volatile int*>(A.error);
+            const bool poisoned = __any_sync(0xffffffffu, err_code != 0 || !ok);   // warp-uniform
             const size_t pb = (size_t)g * A.L.stride;
             float* th = A.nets.theta + pb;
             float* tg = A.nets.theta_tgt + pb;
@@ -1221,7 +1359,9 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A) {
             const AdamK k = adam_k(A, g);
             const bool is_w2 = t < 2;
             const int m0 = is_w2 ? t * BM : 0;
-            if (t == 2) {
+            if (t == 2 && poisoned) {
+                if (et < DMDQN_METRICS_STRIDE && A.metrics) A.metrics[g * DMDQN_METRICS_STRIDE + et] = et == 7 ? -(float)(err_code ? err_code : 6) : 0.f;
+            } else if (t == 2) {
                 // head / bias gradients: per-row-tile partials from K4a summed in tile order, then Adam
                 auto upd = [&](int64_t off, float grad) {
                     if (A.grads) { A.grads[pb + off] = grad; return; }
@@ -1279,6 +1419,7 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A) {
                     if (lane == 0) mbar_arrive(bars + Wg::ACC_FREE + 8 * acc_buf);
                 }
                 __syncwarp();
+                if (poisoned) continue;                           // warp-uniform: the accumulator has been released above
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     *reinterpret_cast<float4*>(tile + lane * Wg::TLD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -1345,25 +1486,58 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A) {
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
+// The rank-3 tensor map K4a's TMA lane uses for d.W^T: W2 of every network as {256 columns, 256 rows, n_nets}, box =
+// {16 columns, 256 rows, 1} (dense 256 x 64 B in shared memory).  Encoded per launch (the library keeps no state
+// and the caller's theta pointer may be a per-agent view); the driver entry point is looked up once.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int make_w2_tensor_map(const TcArgs& A, CUtensorMap* out) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        DMDQN_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !fn) {
+            set_error("cuTensorMapEncodeTiled is not available from this driver");
+            return DMDQN_ERR_CUDA;
+        }
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)H, (cuuint64_t)H, (cuuint64_t)A.d.n_nets};
+    const cuuint64_t strides[2] = {(cuuint64_t)H * sizeof(float), (cuuint64_t)A.L.stride * sizeof(float)};
+    const cuuint32_t box[3] = {16, (cuuint32_t)H, 1}, estr[3] = {1, 1, 1};
+    const CUresult rc = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, A.nets.theta + A.L.w2, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)rc);
+        return DMDQN_ERR_CUDA;
+    }
+    return DMDQN_OK;
+}
+
 template <int PASSES>
 int launch_tc(const TcArgs& A, int stages, cudaStream_t s) {
     const size_t smem_f = Fwd::TOTAL + 1024, smem_w = Wg::TOTAL + 1024;
+    int n_sm = 0;
+    if (int rc = device_sm_count(&n_sm)) return rc;
     static size_t cfg_t[kMaxDevices] = {}, cfg_o[kMaxDevices] = {}, cfg_w[kMaxDevices] = {};    // per device, not per process
     if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void*>(tc_target_kernel<PASSES>), smem_f, cfg_t)) return rc;
     if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void*>(tc_online_kernel<PASSES>), smem_f, cfg_o)) return rc;
     if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void*>(tc_wgrad_kernel<PASSES>), smem_w, cfg_w)) return rc;
-    const int grid = A.d.n_nets * A.tiles;
+    const int items = A.d.n_nets * A.tiles;                       // persistent: one CTA per SM walks its items
     if (stages & DMDQN_STAGE_TARGET) {
-        tc_target_kernel<PASSES><<<2 * grid, NT_F, smem_f, s>>>(A);
+        tc_target_kernel<PASSES><<<2 * items < n_sm ? 2 * items : n_sm, NT_F, smem_f, s>>>(A);
         DMDQN_CUDA(cudaGetLastError());
     }
     if (stages & DMDQN_STAGE_ONLINE) {
-        tc_online_kernel<PASSES><<<grid, NT_F, smem_f, s>>>(A);
+        CUtensorMap tmap;
+        if (int rc = make_w2_tensor_map(A, &tmap)) return rc;
+        tc_online_kernel<PASSES><<<items < n_sm ? items : n_sm, NT_F, smem_f, s>>>(A, tmap);
         DMDQN_CUDA(cudaGetLastError());
     }
     if (stages & DMDQN_STAGE_WGRAD) {
-        int n_sm = 0;
-        if (int rc = device_sm_count(&n_sm)) return rc;
         const int items = A.d.n_nets * 3;
         tc_wgrad_kernel<PASSES><<<items < n_sm ? items : n_sm, Wg::NTW, smem_w, s>>>(A);
         DMDQN_CUDA(cudaGetLastError());

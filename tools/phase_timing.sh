@@ -1,6 +1,6 @@
 #!/bin/bash
-# Profiling aid: build with phase stamps (and optionally an experiment), run two bench steps, keep the stamp lines.
-# usage: tools/phase_timing.sh <exp 0|1|2> <out log>
+# Profiling aid: build the phase-stamp variant into libdmdqn_b200_timing.so (the product library is untouched), run two
+# bench steps against it, keep the stamp lines.   usage: tools/phase_timing.sh <out log> [lines]
 set -e
-DMDQN_TC_TIMING=1 DMDQN_TC_EXP=$1 python -m dmdqn_b200.build --force > /dev/null
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline 2>&1 | grep -E "^K3|^K4" | tail -${3:-27} > $2
+python -m dmdqn_b200.build --timing > /dev/null
+DMDQN_PROFILING_LIB=1 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --blocks none 2>&1 | grep -E "^K3|^K4" | tail -${2:-40} > $1

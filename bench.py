@@ -378,18 +378,22 @@ def block_cfg5(args, rank, world, local, K, W):
            "target_update_frequency": 1000, "nn_layers": [hidden, hidden], "share_parameters": True, "precision": "auto"}
     grp = AgentGroup(agents_total // world, cfg, D, A, seed=42)            # same seed: replicas start identical
     synth_fill(grp, seed=300 + rank)
-    step = SharedParameterStep.for_group(grp)
+    step = SharedParameterStep.for_group(grp)                              # world > 1: fused peer-memory reduce + Adam
     stream = torch.cuda.current_stream()
-    for _ in range(W):
-        step.step()
-    _barrier(world)
-    e0, e1 = _events(2)
-    e0.record(stream)
-    for _ in range(K):
-        step.step()
-    e1.record(stream)
-    _barrier(world)
-    ms = _max_over_ranks([e0.elapsed_time(e1)], world, grp.device)[0]
+
+    def run_steps(st):
+        for _ in range(W):
+            st.step()
+        _barrier(world)
+        e0, e1 = _events(2)
+        e0.record(stream)
+        for _ in range(K):
+            st.step()
+        e1.record(stream)
+        _barrier(world)
+        return _max_over_ranks([e0.elapsed_time(e1)], world, grp.device)[0]
+    ms = run_steps(step)
+    ms_nccl = run_steps(SharedParameterStep.for_group(grp, fused=False)) if world > 1 else None
     # phase split of one step: local gradients | reduction | Adam
     ev = [_events(4) for _ in range(min(K, 20))]
     for e in ev:
@@ -418,7 +422,9 @@ def block_cfg5(args, rank, world, local, K, W):
             "value": ups * agents_total, "unit": "agent-updates/s (shared updates/s x 1024 agents served)",
             "shared_updates_per_s": ups, "samples_per_s": ups * batch_global, "ms_per_step": ms / K, "scaling": "strong",
             "steps": K, "phases_ms_rank0": phases, "replicas_identical": identical,
-            "reduction": "none (1 GPU)" if world == 1 else "torch.distributed all_reduce (NCCL) between dmdqn_learn_grads and dmdqn_adam_apply"}
+            "reduction": "none (1 GPU)" if world == 1 else "dmdqn_allreduce_adam: flag exchange + peer loads over NVLink (CUDA IPC) + Adam in one kernel",
+            "nccl_baseline": None if ms_nccl is None else {"ms_per_step": ms_nccl / K, "value": K / (ms_nccl / 1e3) * agents_total,
+                                                          "what": "torch.distributed all_reduce (NCCL) between dmdqn_learn_grads and dmdqn_adam_apply; phases_ms_rank0 splits this path"}}
 
 
 def block_gather_featurize(grp, world, K):

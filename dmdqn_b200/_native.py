@@ -43,6 +43,14 @@ class DebugViews(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("y", "q_all", "q_next", "tq_all", "rows", "r_hat", "active", "tc_error", "dh1", "dh2", "relu2_bits")]
 
 
+MAX_PEERS, PEER_BLOCKS, PEER_TIMEOUT = 8, 128, 77
+
+
+class Peers(C.Structure):
+    _fields_ = [("grads", C.c_void_p * MAX_PEERS), ("loss", C.c_void_p * MAX_PEERS), ("flags", C.c_void_p * MAX_PEERS),
+                ("rank", C.c_int32), ("world", C.c_int32), ("epoch", C.c_uint32)]
+
+
 class StepBlock(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in ("bytes", "obs_off", "next_obs_off", "act_off", "rew_off", "done_off", "draws_off")] + \
                [("in_stride", C.c_int32)]
@@ -72,6 +80,11 @@ SIGNATURES = {
     "dmdqn_learn_grads": (C.c_int, [C.POINTER(Dims), C.POINTER(HParams), C.POINTER(Replay), C.POINTER(Nets), _P, _P,
                                     C.c_int32, _P, _P, _P, C.c_size_t, _P]),
     "dmdqn_adam_apply": (C.c_int, [C.POINTER(Dims), C.POINTER(HParams), C.POINTER(Nets), _P, _P, C.c_size_t, _P]),
+    "dmdqn_allreduce_adam": (C.c_int, [C.POINTER(Dims), C.POINTER(HParams), C.POINTER(Nets), C.POINTER(Peers), _P, _P, _P,
+                                       C.c_size_t, _P]),
+    "dmdqn_ipc_export": (C.c_int, [_P, _P, C.POINTER(C.c_uint64)]),
+    "dmdqn_ipc_open": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "dmdqn_ipc_close": (C.c_int, [_P, C.c_uint64]),
     "dmdqn_debug": (C.c_int, [C.POINTER(Dims), _P, C.c_size_t, C.POINTER(DebugViews)]),
     "dmdqn_sync_target": (C.c_int, [C.POINTER(Dims), C.POINTER(Nets), _P, C.c_double, _P]),
 }

@@ -262,6 +262,70 @@ int dmdqn_adam_apply(const dmdqn_dims* dims, const dmdqn_hparams* hp, const dmdq
     return launch_learn(*dims, *hp, none, *nets, nullptr, (char*)workspace, w, 0, nullptr, 0, grads, (cudaStream_t)stream);
 }
 
+int dmdqn_allreduce_adam(const dmdqn_dims* dims, const dmdqn_hparams* hp, const dmdqn_nets* nets, const dmdqn_peers* peers,
+                         const float* my_loss_src, float* loss_out, void* workspace, size_t workspace_bytes, void* stream) {
+    Workspace w;
+    int rc = check_workspace(dims, workspace, workspace_bytes, &w);
+    if (rc) return rc;
+    DMDQN_CHECK_ARG(hp && nets && nets->theta && nets->theta_tgt && nets->adam_m && nets->adam_v && peers && my_loss_src,
+                    "allreduce_adam: NULL argument");
+    DMDQN_CHECK_ARG(dims->n_nets == 1, "allreduce_adam serves the shared network (n_nets == 1), got n_nets=%d", dims->n_nets);
+    DMDQN_CHECK_ARG(peers->world >= 1 && peers->world <= DMDQN_MAX_PEERS && peers->rank >= 0 && peers->rank < peers->world,
+                    "allreduce_adam: rank %d of world %d (at most %d peers)", peers->rank, peers->world, DMDQN_MAX_PEERS);
+    DMDQN_CHECK_ARG(peers->epoch != 0, "allreduce_adam: epoch starts at 1 (the flag arrays are zero-initialised)");
+    for (int p = 0; p < peers->world; ++p)
+        DMDQN_CHECK_ARG(peers->grads[p] && peers->loss[p] && peers->flags[p], "allreduce_adam: NULL pointer for peer %d", p);
+    return launch_peer_adam(*dims, *hp, *nets, *peers, my_loss_src, loss_out, (char*)workspace, w, (cudaStream_t)stream);
+}
+
+// CUDA IPC: the handle names a whole cudaMalloc allocation, so the offset of the pointer inside it travels along
+// (a torch tensor is a slice of the caching allocator's block).  The driver entry point is looked up at run time
+// (the library links cudart only).
+int dmdqn_ipc_export(const void* dev_ptr, void* handle64, uint64_t* offset) {
+    DMDQN_CHECK_ARG(dev_ptr && handle64 && offset, "ipc_export: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI carries the handle as 64 bytes");
+    typedef int (*RangeFn)(unsigned long long*, size_t*, unsigned long long);
+    static RangeFn range = nullptr;
+    if (!range) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        DMDQN_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q));
+        if (q != cudaDriverEntryPointSuccess || !fn) {
+            set_error("cuMemGetAddressRange is not available from this driver");
+            return DMDQN_ERR_CUDA;
+        }
+        range = reinterpret_cast<RangeFn>(fn);
+    }
+    unsigned long long base = 0;
+    size_t size = 0;
+    const int drc = range(&base, &size, (unsigned long long)(uintptr_t)dev_ptr);
+    if (drc != 0) {
+        set_error("cuMemGetAddressRange failed with CUresult %d", drc);
+        return DMDQN_ERR_CUDA;
+    }
+    cudaIpcMemHandle_t h;
+    DMDQN_CUDA(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>((uintptr_t)base)));
+    memcpy(handle64, &h, sizeof(h));
+    *offset = (uint64_t)((uintptr_t)dev_ptr - (uintptr_t)base);
+    return DMDQN_OK;
+}
+
+int dmdqn_ipc_open(const void* handle64, uint64_t offset, void** dev_ptr) {
+    DMDQN_CHECK_ARG(handle64 && dev_ptr, "ipc_open: NULL argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    void* base = nullptr;
+    DMDQN_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    *dev_ptr = static_cast<char*>(base) + offset;
+    return DMDQN_OK;
+}
+
+int dmdqn_ipc_close(void* dev_ptr, uint64_t offset) {
+    DMDQN_CHECK_ARG(dev_ptr != nullptr, "ipc_close: NULL argument");
+    DMDQN_CUDA(cudaIpcCloseMemHandle(static_cast<char*>(dev_ptr) - offset));
+    return DMDQN_OK;
+}
+
 int dmdqn_debug(const dmdqn_dims* dims, void* workspace, size_t workspace_bytes, dmdqn_debug_views* out) {
     Workspace w;
     int rc = check_workspace(dims, workspace, workspace_bytes, &w);

@@ -149,5 +149,7 @@ int launch_learn_tc(const dmdqn_dims& d, const dmdqn_hparams& hp, const dmdqn_re
                     cudaStream_t s);
 int launch_sync_target(const dmdqn_dims& d, const dmdqn_nets& nets, const uint8_t* mask, double tau,
                        cudaStream_t s);
+int launch_peer_adam(const dmdqn_dims& d, const dmdqn_hparams& hp, const dmdqn_nets& nets, const dmdqn_peers& peers,
+                     const float* my_loss_src, float* loss_out, char* ws, const Workspace& w, cudaStream_t s);
 
 }  // namespace dmdqn

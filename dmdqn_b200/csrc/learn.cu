@@ -635,6 +635,67 @@ __global__ void adam_apply_kernel(const LearnArgs A, const float* __restrict__ g
     }
 }
 
+// K5: all-reduce of the shared network's gradient block over NVLink peer memory fused with Adam + target sync
+// (include/dmdqn_b200.h dmdqn_allreduce_adam).  Block b of every rank exchanges its own flag with block b of every
+// peer, so there is no grid-wide dependency inside a GPU and no co-residency requirement; the gradient blocks were
+// completed by the previous kernel of each rank's stream, the flag only says "that kernel is done".
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__global__ void __launch_bounds__(256)
+peer_reduce_adam_kernel(const LearnArgs A, const dmdqn_peers P, const float* __restrict__ my_loss_src,
+                        float* __restrict__ loss_out, int* __restrict__ error) {
+    __shared__ int timed_out;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) timed_out = 0;
+    if (b == 0 && tid == 0) {                       // this rank's share of the loss travels with block 0's flag
+        *P.loss[P.rank] = *my_loss_src;
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (tid < P.world) st_release_sys(P.flags[tid] + P.rank * DMDQN_PEER_BLOCKS + b, P.epoch);
+    if (tid < P.world) {
+        const uint32_t* f = P.flags[P.rank] + tid * DMDQN_PEER_BLOCKS + b;
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while ((int32_t)(ld_acquire_sys(f) - P.epoch) < 0) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 2000000000ull) { timed_out = 1; break; }    // ~2 s: a missing peer is an error, not a hang
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+    if (timed_out) {
+        if (tid == 0) atomicExch(error, DMDQN_PEER_TIMEOUT);
+        return;
+    }
+    if (!A.active[0]) return;                       // (the learn decision is collective: every rank or none)
+    const AdamCoef k = adam_coef(A, A.step_t[0]);
+    const int64_t n4 = (A.L.b3 + 4) / 4;
+    for (int64_t i = b * (int64_t)blockDim.x + tid; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 v[DMDQN_MAX_PEERS];
+#pragma unroll
+        for (int p = 0; p < DMDQN_MAX_PEERS; ++p)   // every peer's piece in flight before the first add
+            if (p < P.world) v[p] = __ldcv(reinterpret_cast<const float4*>(P.grads[p]) + i);
+        float4 sum = v[0];
+#pragma unroll
+        for (int p = 1; p < DMDQN_MAX_PEERS; ++p)   // rank order on every rank: bit-identical replicas
+            if (p < P.world) { sum.x += v[p].x; sum.y += v[p].y; sum.z += v[p].z; sum.w += v[p].w; }
+        const float gv[4] = {sum.x, sum.y, sum.z, sum.w};
+        adam_vec4(k, gv, A.nets.theta + i * 4, A.nets.adam_m + i * 4, A.nets.adam_v + i * 4, A.nets.theta_tgt + i * 4);
+    }
+    if (b == 0 && tid == 0 && loss_out) {
+        float ls = 0.f;
+        for (int p = 0; p < P.world; ++p) ls += __ldcv(P.loss[p]);
+        *loss_out = ls;
+    }
+}
+
 template <int H>
 int launch_learn_h(const LearnArgs& A, int stages, cudaStream_t s) {
     using T = Tile<H>;
@@ -721,6 +782,23 @@ int launch_learn(const dmdqn_dims& d, const dmdqn_hparams& hp, const dmdqn_repla
     }
     set_error("unsupported hidden width %d", d.hidden);
     return DMDQN_ERR_ARG;
+}
+
+int launch_peer_adam(const dmdqn_dims& d, const dmdqn_hparams& hp, const dmdqn_nets& nets, const dmdqn_peers& peers,
+                     const float* my_loss_src, float* loss_out, char* ws, const Workspace& w, cudaStream_t s) {
+    LearnArgs A = {};
+    A.d = d;
+    A.L = make_layout(d.obs_stride, d.hidden);
+    A.nets = nets;
+    A.adam_form = hp.adam_form;
+    A.freq = hp.target_update_frequency > 0 ? hp.target_update_frequency : 1;
+    A.lr = hp.learning_rate; A.beta1 = hp.beta1; A.beta2 = hp.beta2; A.adam_eps = hp.adam_eps; A.tau = hp.tau;
+    A.active = reinterpret_cast<const int32_t*>(ws + w.active);
+    A.step_t = reinterpret_cast<const int32_t*>(ws + w.step_t);
+    peer_reduce_adam_kernel<<<DMDQN_PEER_BLOCKS, 256, 0, s>>>(A, peers, my_loss_src, loss_out,
+                                                              reinterpret_cast<int*>(ws + w.tc_error));
+    DMDQN_CUDA(cudaGetLastError());
+    return DMDQN_OK;
 }
 
 int launch_sync_target(const dmdqn_dims& d, const dmdqn_nets& nets, const uint8_t* mask, double tau,

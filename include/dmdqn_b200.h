@@ -269,6 +269,37 @@ int dmdqn_learn_grads(const dmdqn_dims* dims, const dmdqn_hparams* hp, const dmd
 int dmdqn_adam_apply(const dmdqn_dims* dims, const dmdqn_hparams* hp, const dmdqn_nets* nets,
                      const float* grads, void* workspace, size_t workspace_bytes, void* stream);
 
+/* K5, shared-parameter mode over NVLink peer memory (BASELINE.json cfg5): ONE kernel per
+ * rank that (1) announces its gradient block of this step to every peer (release store of `epoch` into the peers'
+ * flag arrays), (2) waits for the peers' announcements, (3) reads every rank's block through peer pointers, sums
+ * them in rank order 0..world-1 (the same order on every rank: replicas stay bit-identical) and (4) applies Adam +
+ * the target sync to the local replica -- the all-reduce and the optimizer step of dmdqn_learn_grads ->
+ * ncclAllReduce -> dmdqn_adam_apply in one launch, with no host round trip and no NCCL on the path.
+ * grads[p] / loss[p] / flags[p] are device pointers valid on THIS device: the rank's own buffers at [rank], the
+ * peers' through dmdqn_ipc_open.  The caller double-buffers grads / loss by epoch parity (a peer may already be
+ * writing step t+1 while this rank still reads step t); flags[p] is uint32[DMDQN_MAX_PEERS][DMDQN_PEER_BLOCKS],
+ * zero-initialised once; epoch = 1, 2, 3, ... identical on every rank.  my_loss_src is this rank's share of the loss
+ * (metrics_out[0] of dmdqn_learn_grads), published to loss[rank] by the kernel; loss_out receives the sum.
+ * A peer that never arrives ends in DMDQN_PEER_TIMEOUT in the workspace error flag (no update applied), not in a hang. */
+#define DMDQN_MAX_PEERS 8
+#define DMDQN_PEER_TIMEOUT 77     /* value of the workspace error flag after a peer never arrived */
+#define DMDQN_PEER_BLOCKS 128
+typedef struct dmdqn_peers {
+    const float* grads[DMDQN_MAX_PEERS];
+    float* loss[DMDQN_MAX_PEERS];
+    uint32_t* flags[DMDQN_MAX_PEERS];
+    int32_t rank, world;
+    uint32_t epoch;
+} dmdqn_peers;
+int dmdqn_allreduce_adam(const dmdqn_dims* dims, const dmdqn_hparams* hp, const dmdqn_nets* nets,
+                         const dmdqn_peers* peers, const float* my_loss_src, float* loss_out, void* workspace,
+                         size_t workspace_bytes, void* stream);
+/* CUDA IPC plumbing for the peer pointers above: export the allocation that contains dev_ptr (64-byte handle +
+ * offset of dev_ptr inside it), map a peer's export on the current device (peer access is enabled lazily), unmap. */
+int dmdqn_ipc_export(const void* dev_ptr, void* handle64, uint64_t* offset);
+int dmdqn_ipc_open(const void* handle64, uint64_t offset, void** dev_ptr);
+int dmdqn_ipc_close(void* dev_ptr, uint64_t offset);
+
 /* Debug / parity views into the workspace after dmdqn_learn (device pointers into it):
  * y[n_nets][B], q_all[n_nets][B][4] (online Q of s), q_next[n_nets][B][4] (online Q of s'),
  * tq_all[n_nets][B][4] (target Q of s'), rows int32[n_nets][B] (agent*C + slot). */

@@ -535,3 +535,106 @@ def test_two_devices_in_one_process():
     obs = rng.integers(-1, 20, (3, 89)).astype(np.float32)
     assert torch.equal(a.act(obs).cpu(), b.act(obs).cpu())
     assert torch.cuda.current_device() == 0
+
+
+# ------------------------------------------------------------------ E2: fused peer-memory all-reduce + Adam ------------
+def _shared_pair(n_groups, h, n_agents, batch, cap, precision, seed):
+    """n_groups replicas of one shared network (same weights) with DIFFERENT ring contents: the ranks of cfg5."""
+    from oracle.dqn import StackedOracle
+    cfg = {"nn_layers": [h, h], "replay_buffer_size": cap, "batch_size": batch, "learning_rate": 5e-4, "gamma": 0.99,
+           "target_update_frequency": 2, "share_parameters": True, "precision": precision}
+    stk = StackedOracle(1, 89, [h, h], 4, gamma=0.99, learning_rate=5e-4, target_update_frequency=2, seed0=21)
+    groups = []
+    for r in range(n_groups):
+        grp = _group(n_agents, cfg)
+        _load(grp, stk)
+        _fill(grp, None, np.random.default_rng(seed + 17 * r), cap + 2)
+        groups.append(grp)
+    return groups
+
+
+def _fixed_draws(grp, words):
+    grp.draw_words = lambda shape, w=words: torch.as_tensor(w.view(np.int32)).to(grp.device)
+
+
+@pytest.mark.parametrize("h,precision", [(256, "tf32x3"), (64, "fp32")])
+def test_fused_peer_step_single_rank_equals_grads_then_adam_apply(h, precision):
+    """dmdqn_allreduce_adam with one rank is dmdqn_learn_grads -> dmdqn_adam_apply: same bits in theta / m / v /
+    theta_tgt and the same loss, over steps that cross a hard target sync."""
+    from dmdqn_b200.parallel import PeerExchange, SharedParameterStep
+    a = _shared_pair(1, h, 3, 64, 60, precision, seed=5)[0]
+    b = _shared_pair(1, h, 3, 64, 60, precision, seed=5)[0]          # same weights, same rings
+    plain = SharedParameterStep.for_group(a, fused=False)
+    fused = SharedParameterStep.for_group(b, exchange=PeerExchange(b, 0, 1))
+    rng = np.random.default_rng(1)
+    for it in range(4):
+        words = rng.integers(0, 2**32, (1, 64), dtype=np.uint64).astype(np.uint32)
+        _fixed_draws(a, words); _fixed_draws(b, words)
+        la, lb = plain.step().cpu().numpy(), fused.step().cpu().numpy()
+        assert np.array_equal(la.ravel(), lb.ravel())
+        for name in ("theta", "theta_tgt", "adam_m", "adam_v"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), f"step {it}: {name} differs"
+        b.check_errors()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_fused_peer_step_ranks_in_one_process_match_the_summed_gradient(world):
+    """`world` replicas with different rings on ONE device, each step launched on its own stream so the kernels
+    really wait for each other's flags: every replica ends bit-identical, and equal to a reference replica that
+    applies dmdqn_adam_apply to the rank-ordered sum of the per-rank gradient blocks (what NCCL's all-reduce
+    path computes, in a fixed order)."""
+    from dmdqn_b200.parallel import PeerExchange, SharedParameterStep
+    import ctypes as C
+    from dmdqn_b200 import _native as N
+    h, n_agents, batch, cap = 256, 2, 128, 150
+    ranks = _shared_pair(world, h, n_agents, batch, cap, "tf32x3", seed=40)
+    twins = _shared_pair(world, h, n_agents, batch, cap, "tf32x3", seed=40)      # same rings: produce the per-rank gradients
+    exchanges = [PeerExchange(g, r, world) for r, g in enumerate(ranks)]
+    PeerExchange.connect_local(exchanges)
+    steps = [SharedParameterStep.for_group(g, exchange=e) for g, e in zip(ranks, exchanges)]
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    rng = np.random.default_rng(3)
+    for it in range(4):
+        words = [rng.integers(0, 2**32, (1, batch), dtype=np.uint64).astype(np.uint32) for _ in range(world)]
+        torch.cuda.synchronize()
+        losses = []
+        if world == 2:      # whole steps back to back, one stream per rank: rank 0's kernel spins until rank 1's arrives
+            for r in range(world):
+                _fixed_draws(ranks[r], words[r])
+                with torch.cuda.stream(streams[r]):
+                    losses.append(steps[r].step())
+        else:               # (more simulated ranks than that would fill the ONE device with spinning blocks before the
+            for r in range(world):      # later ranks' learn kernels get an SM: gradients first, then the exchange kernels)
+                _fixed_draws(ranks[r], words[r])
+                with torch.cuda.stream(streams[r]):
+                    steps[r].fused_begin(batch * world)
+            torch.cuda.synchronize()
+            for r in range(world):
+                with torch.cuda.stream(streams[r]):
+                    losses.append(steps[r].fused_finish())
+        torch.cuda.synchronize()
+        for g in ranks:
+            g.check_errors()
+        # reference: per-rank gradient blocks from the twins, summed in rank order, one adam_apply
+        total, loss_sum = None, np.float32(0)
+        for r in range(world):
+            tw = twins[r]
+            _fixed_draws(tw, words[r])
+            gb = torch.zeros_like(tw.theta)
+            d = tw.draw_words((1, batch))
+            N.check(tw.lib.dmdqn_learn_grads(C.byref(tw.dims), C.byref(tw.hp), C.byref(tw.replay), C.byref(tw.nets), d.data_ptr(), None,
+                                             batch * world, gb.data_ptr(), tw.metrics.data_ptr(), tw.workspace.data_ptr(),
+                                             tw.workspace.numel(), torch.cuda.current_stream().cuda_stream))
+            total = gb.clone() if total is None else total + gb
+            loss_sum = np.float32(loss_sum + tw.metrics[0, 0].item())
+        first = twins[0]
+        # every twin carries the replica: apply the summed block on each so they stay in step with the ranks
+        for tw in twins:
+            N.check(tw.lib.dmdqn_adam_apply(C.byref(tw.dims), C.byref(tw.hp), C.byref(tw.nets), total.data_ptr(), tw.workspace.data_ptr(),
+                                            tw.workspace.numel(), torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert np.float32(losses[r].item()) == loss_sum, f"step {it}: loss of rank {r}"
+            for name in ("theta", "theta_tgt", "adam_m", "adam_v"):
+                assert torch.equal(getattr(ranks[r], name), getattr(ranks[0], name)), f"step {it}: replica {r} {name} diverged"
+                assert torch.equal(getattr(ranks[r], name), getattr(first, name)), f"step {it}: rank {r} {name} != summed-gradient reference"

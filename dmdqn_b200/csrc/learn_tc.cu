@@ -122,7 +122,6 @@ __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 512;" :::
 __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void prod_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 producer warps of K4b
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -1059,16 +1058,23 @@ struct Wg {     // persistent wgrad kernel, one CTA per SM
     static constexpr int STAGES = 3;
     static constexpr uint32_t A_BYTES = KC * BM * 4;          // 8 KB
     static constexpr uint32_t B_BYTES = KC * H * 4;           // 16 KB
-    static constexpr uint32_t STG = 2 * A_BYTES + 2 * B_BYTES;   // A hi|lo, B hi|lo: 48 KB
+    static constexpr uint32_t AUX = 2 * A_BYTES + 2 * B_BYTES;   // A hi|lo, B hi|lo: 48 KB, then the side area of the stage
+    static constexpr uint32_t AUX_MASK = 128;                 // dW2: (g, action) pairs [16] at + 0, relu'(h2) words [16][8] at + 128
+    static constexpr uint32_t AUX_BYTES = 6144;               // dW1: the 16 gathered observation rows of the chunk (<= 96 floats each)
+    static constexpr uint32_t STG = AUX + AUX_BYTES;          // 54 KB (a multiple of 1 KB: every stage starts swizzle-aligned)
     static constexpr int TLD = 36;                            // floats per row of an epilogue transpose tile
     static constexpr uint32_t TILES = STAGES * STG;           // 8 epilogue warps x 32 x TLD floats
     static constexpr uint32_t W3T = TILES + 8 * 32 * TLD * 4; // W3^T [2 item parities][4 actions][256] floats
     static constexpr uint32_t BARS = W3T + 2 * 4 * H * 4;
-    static constexpr uint32_t FULL = 0, EMPTY = 24, ACC_FULL = 48, ACC_FREE = 64, TMEM = 80;   // byte offsets from BARS
+    static constexpr uint32_t FULL = 0, CONV = 24, EMPTY = 48, ACC_FULL = 72, ACC_FREE = 88, TMEM = 104;   // byte offsets from BARS
     static constexpr uint32_t TOTAL = BARS + 128;
-    static constexpr int NPROD = 8 * 32;                      // producer threads
-    static constexpr int NTW = 16 * 32;                       // 8 producer warps (lane 0 of warp 0 also issues the MMAs), 8 epilogue warps
+    static constexpr int EPI_WARPS = 8, CONV_WARPS = 8;       // warps 0-7 / 8-15; warp 16: MMA lane, warp 17: TMA, 18-19 fill the warpgroup
+    static constexpr int NCONV = CONV_WARPS * 32;
+    static constexpr int NTW = 20 * 32;                       // five warpgroups
+    // setmaxnreg per warpgroup inside the pool the CTA was launched with (640 x 96): 2 x 128 x 152 + 2 x 128 x 72 + 128 x 32
+    static constexpr int REGS_EPI = 152, REGS_CONV = 72, REGS_AUX = 32;
 };
+__device__ __forceinline__ void conv_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 converter warps of K4b
 
 // Work items of K4b: per network two dW2 tiles (rows t*128..) and one dW1 tile.  The dW2 tiles come first in
 // the item order (they are the longer ones), so a static round-robin over the CTAs ends on the short items.
@@ -1083,17 +1089,24 @@ __device__ __forceinline__ void wg_item(int q, int G, int& g, int& t) {
 //            A column m = obs_stride is set to 1, so row obs_stride of the tile is db1 = sum_k dh1[k][:] for free;
 //            the epilogue of this item also folds the per-row-tile partials of db2 / dW3 / db3 (from K4a) and
 //            emits the metrics.
-// Persistent and warp-specialised: a CTA walks its items q = blockIdx.x, + gridDim.x, ...;
-//   warps 0-7  stage operand chunks (global -> registers -> hi | lo -> shared memory, 3 stages) and run ahead
-//              into the next item;
-//   lane 0 of warp 0 also issues the tcgen05.mma of the chunk staged one step earlier, alternating between two
-//              TMEM accumulators (columns 0..255 / 256..511), and
-//   warps 8-15 read a finished accumulator and do the Adam read-modify-write of theta / m / v / theta_tgt.
-// The epilogue is pure HBM traffic (24 bytes per parameter) and the GEMM needs almost none, so running them
-// concurrently on every SM keeps HBM busy for the whole kernel instead of only during the epilogue phase of a
-// wave of lock-stepped CTAs.
+// Persistent and warp-specialised like K3 / K4a: a CTA walks its items q = blockIdx.x, + gridDim.x, ...; per 16-row chunk
+//   warp 17    TMA producer: the K-major scratch operand (h1^T / dh1^T) lands IN PLACE in the hi half of its stage
+//              through a tensor map with the 64-byte swizzle the UMMA layout uses (a box of {16 batch columns, 128 or 256
+//              feature rows}; columns past the batch are zero-filled by the hardware); the small inputs of the other
+//              operand travel with cp.async.bulk into the stage's side area -- (g, action) pairs + relu'(h2) words for
+//              dW2, one copy per gathered observation row for dW1 (lane = row) -- all on the stage's mbarrier;
+//   warps 8-15 converters: split the landed operand into hi | lo in place (same address: the swizzle is already
+//              applied), and BUILD the other operand in the UMMA MN-major layout: dW2's dh2[k][n] = relu'(h2) ? g_k *
+//              W3[n][a_k] : 0 from the side area and W3^T in shared memory, dW1's observation rows + ones column;
+//   warp 16    lane 0 issues the chunk's six tcgen05.mma, alternating between two TMEM accumulators per item;
+//   warps 0-7  read a finished accumulator and do the Adam read-modify-write of theta / m / v / theta_tgt.
+// Stage ring: FULL (TMA landed) -> CONV (converted / built) -> EMPTY (tcgen05.commit).  Nobody waits on a global load
+// with operands in registers any more (the previous version's producers spent ~3.3 k cycles per chunk on exactly that,
+// against 768 cycles of tensor time).  The epilogue is pure HBM traffic (24 bytes per parameter) and the GEMM needs
+// almost none, so running them concurrently on every SM keeps HBM busy for the whole kernel.
 template <int PASSES>
-__global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A) {
+__global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A, const __grid_constant__ CUtensorMap tmap_h1,
+                                                              const __grid_constant__ CUtensorMap tmap_dh1) {
     extern __shared__ uint8_t smem_raw[];
     const int B = A.d.batch, Dp = A.d.obs_stride, G = A.d.n_nets;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1104,12 +1117,13 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A) {
 
     if (tid == 0) {
         for (int s = 0; s < Wg::STAGES; ++s) {
-            mbar_init(bars + Wg::FULL + 8 * s, 8);            // one arrival per producer warp
-            mbar_init(bars + Wg::EMPTY + 8 * s, 1);           // one tcgen05.commit
+            mbar_init(bars + Wg::FULL + 8 * s, 1);                    // one arrive.expect_tx + the bytes of the chunk
+            mbar_init(bars + Wg::CONV + 8 * s, Wg::CONV_WARPS);       // one arrival per converter warp
+            mbar_init(bars + Wg::EMPTY + 8 * s, 1);                   // one tcgen05.commit
         }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(bars + Wg::ACC_FULL + 8 * b, 1);        // one tcgen05.commit
-            mbar_init(bars + Wg::ACC_FREE + 8 * b, 8);        // one arrival per epilogue warp
+            mbar_init(bars + Wg::ACC_FULL + 8 * b, 1);                // one tcgen05.commit
+            mbar_init(bars + Wg::ACC_FREE + 8 * b, Wg::EPI_WARPS);    // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1124,216 +1138,218 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(bars + Wg::TMEM));
     bool ok = true;
 
-    if (warp < 8) {
-        // ------------------------------------------------------------------ producers ------------------
-        // Operand chunks (16 batch rows) travel global -> registers -> (hi | lo) -> shared memory; the loads of
-        // chunk c + 2 are issued when chunk c is staged, so two chunks of latency are covered by registers and
-        // the shared-memory stages only have to cover the MMAs.
-        uint32_t stage = 0, ph = 0, used = 0;
-        // Lane 0 of warp 0 is also the MMA issuer: after staging chunk c it issues the tcgen05.mma of chunk
-        // c - 1 (which the other warps have normally finished staging by then), so no thread sits in a wait
-        // that paces the others.  pend_* describe the chunk whose MMAs are still to be issued.
-        bool pend = false, pend_w2 = false, pend_first = false, pend_last = false;
-        uint32_t pend_stage = 0, pend_ph = 0;
-        int pend_n = 0, n = 0;
-        auto issue_pending = [&]() {
+    if (warp >= Wg::EPI_WARPS + Wg::CONV_WARPS) {
+        regs_dec<Wg::REGS_AUX>();
+        if (warp == Wg::EPI_WARPS + Wg::CONV_WARPS) {
+            // ------------------------------------------------------------------ MMA lane -------------------
             if (lane == 0) {
-                const uint32_t acc_buf = (uint32_t)(pend_n & 1);
-                if (pend_first && pend_n >= 2 && ok)              // the epilogue has read item n - 2 out of this accumulator
-                    ok = mbar_wait(bars + Wg::ACC_FREE + 8 * acc_buf, (uint32_t)((pend_n >> 1) - 1) & 1u);
-                if (ok) ok = mbar_wait(bars + Wg::FULL + 8 * pend_stage, pend_ph);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem + acc_buf * 256u;
-                const uint32_t idesc = make_idesc(!pend_w2, pend_w2);
-                const uint32_t st = sbase + pend_stage * Wg::STG;
+                uint32_t used = 0;
+                int n = 0;
+                for (int q = blockIdx.x; q < n_items; q += gridDim.x) {
+                    int g, t;
+                    wg_item(q, G, g, t);
+                    if (!A.active[g]) continue;
+                    const bool is_w2 = t < 2;
+                    const uint32_t acc_buf = (uint32_t)(n & 1);
+                    const uint32_t d_tmem = tmem + acc_buf * 256u;
+                    const uint32_t idesc = make_idesc(!is_w2, is_w2);
+                    if (n >= 2 && ok)                                 // the epilogue has read item n - 2 out of this accumulator
+                        ok = mbar_wait(bars + Wg::ACC_FREE + 8 * acc_buf, (uint32_t)((n >> 1) - 1) & 1u);
+                    for (int c = 0; c < nchunks; ++c) {
+                        const uint32_t s = used % Wg::STAGES, u = used / Wg::STAGES;
+                        if (ok) ok = mbar_wait(bars + Wg::CONV + 8 * s, u & 1u);
+                        tc_fence_after();
+                        const uint32_t st = sbase + s * Wg::STG;
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                    uint64_t a_hi, a_lo;
-                    if (pend_w2) {
-                        a_hi = make_desc(st + ks * 32, 16, 512, 4);
-                        a_lo = make_desc(st + Wg::A_BYTES + ks * 32, 16, 512, 4);
-                    } else {      // MN-major: 4 m-groups per k-group -> k-group stride 2048 B
-                        a_hi = make_desc(st + ks * 2 * 2048, 512, 2048, 1);
-                        a_lo = make_desc(st + Wg::A_BYTES + ks * 2 * 2048, 512, 2048, 1);
+                        for (int ks = 0; ks < 2; ++ks) {
+                            uint64_t a_hi, a_lo, b_hi, b_lo;
+                            if (is_w2) {      // A K-major SW64; B MN-major: 8 n-groups per k-group -> k-group stride 4096 B, a k-step is two k-groups
+                                a_hi = make_desc(st + ks * 32, 16, 512, 4);
+                                a_lo = make_desc(st + Wg::A_BYTES + ks * 32, 16, 512, 4);
+                                b_hi = make_desc(st + 2 * Wg::A_BYTES + ks * 2 * 4096, 512, 4096, 1);
+                                b_lo = make_desc(st + 2 * Wg::A_BYTES + Wg::B_BYTES + ks * 2 * 4096, 512, 4096, 1);
+                            } else {          // A MN-major: 4 m-groups per k-group -> k-group stride 2048 B; B K-major SW64
+                                a_hi = make_desc(st + ks * 2 * 2048, 512, 2048, 1);
+                                a_lo = make_desc(st + Wg::A_BYTES + ks * 2 * 2048, 512, 2048, 1);
+                                b_hi = make_desc(st + 2 * Wg::A_BYTES + ks * 32, 16, 512, 4);
+                                b_lo = make_desc(st + 2 * Wg::A_BYTES + Wg::B_BYTES + ks * 32, 16, 512, 4);
+                            }
+                            uint32_t acc = (c | ks) ? 1u : 0u;
+                            if (PASSES == 3) {
+                                mma_ss(d_tmem, a_lo, b_hi, idesc, acc);
+                                mma_ss(d_tmem, a_hi, b_lo, idesc, 1u);
+                                acc = 1u;
+                            }
+                            mma_ss(d_tmem, a_hi, b_hi, idesc, acc);
+                        }
+                        umma_commit(bars + Wg::EMPTY + 8 * s);
+                        if (c == nchunks - 1) umma_commit(bars + Wg::ACC_FULL + 8 * acc_buf);
+                        ++used;
                     }
-                    uint64_t b_hi, b_lo;
-                    if (pend_w2) {    // MN-major: 8 n-groups per k-group -> k-group stride 4096 B, a k-step is two k-groups
-                        b_hi = make_desc(st + 2 * Wg::A_BYTES + ks * 2 * 4096, 512, 4096, 1);
-                        b_lo = make_desc(st + 2 * Wg::A_BYTES + Wg::B_BYTES + ks * 2 * 4096, 512, 4096, 1);
-                    } else {
-                        b_hi = make_desc(st + 2 * Wg::A_BYTES + ks * 32, 16, 512, 4);
-                        b_lo = make_desc(st + 2 * Wg::A_BYTES + Wg::B_BYTES + ks * 32, 16, 512, 4);
-                    }
-                    uint32_t acc = (!pend_first || ks) ? 1u : 0u;
-                    if (PASSES == 3) {
-                        mma_ss(d_tmem, a_lo, b_hi, idesc, acc);
-                        mma_ss(d_tmem, a_hi, b_lo, idesc, 1u);
-                        acc = 1u;
-                    }
-                    mma_ss(d_tmem, a_hi, b_hi, idesc, acc);
+                    ++n;
                 }
-                umma_commit(bars + Wg::EMPTY + 8 * pend_stage);
-                if (pend_last) umma_commit(bars + Wg::ACC_FULL + 8 * acc_buf);
+                if (!ok) atomicExch(A.error, 15);
             }
             __syncwarp();
-        };
-        // Called by every producer thread before / after it writes its pieces of a chunk into stage `stage`.
-        auto stage_begin = [&]() -> uint32_t {
-            if (used >= (uint32_t)Wg::STAGES && ok) ok = mbar_wait(bars + Wg::EMPTY + 8 * stage, ph ^ 1u);   // MMAs of the previous use are done
-            return sbase + stage * Wg::STG;
-        };
-        auto stage_end = [&](bool is_w2, int c) {
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bars + Wg::FULL + 8 * stage);
-            if (warp == 0) {
-                if (pend) issue_pending();
-                pend = true; pend_w2 = is_w2; pend_first = c == 0; pend_last = c == nchunks - 1;
-                pend_stage = stage; pend_ph = ph; pend_n = n;
+        } else if (warp == Wg::EPI_WARPS + Wg::CONV_WARPS + 1) {
+            // ------------------------------------------------------------------ TMA producer ---------------
+            uint32_t used = 0;
+            for (int q = blockIdx.x; q < n_items; q += gridDim.x) {
+                int g, t;
+                wg_item(q, G, g, t);
+                if (!A.active[g]) continue;
+                const size_t sb = (size_t)g * B;
+                int32_t rid = 0;
+                if (t == 2 && lane < KC && lane < B) rid = __ldg(A.rows + sb + lane);
+                for (int c = 0; c < nchunks; ++c) {
+                    const uint32_t s = used % Wg::STAGES, u = used / Wg::STAGES;
+                    const uint32_t st = sbase + s * Wg::STG, full = bars + Wg::FULL + 8 * s;
+                    const int nvalid = min(KC, B - c * KC);
+                    int32_t rid_next = 0;
+                    if (t == 2 && c + 1 < nchunks && (c + 1) * KC + lane < B && lane < KC) rid_next = __ldg(A.rows + sb + (c + 1) * KC + lane);
+                    if (u && ok) ok = mbar_wait(bars + Wg::EMPTY + 8 * s, (u - 1) & 1u);     // the MMAs of the stage's previous chunk have retired
+                    if (t < 2) {
+                        if (lane == 0) {
+                            mbar_expect_tx(full, Wg::A_BYTES + (uint32_t)nvalid * 40u);
+                            tma_load_3d(st, &tmap_h1, c * KC, t * BM, g, full);
+                            bulk_g2s(st + Wg::AUX, A.ga + sb + c * KC, (uint32_t)nvalid * 8u, full);
+                            bulk_g2s(st + Wg::AUX + Wg::AUX_MASK, A.mask2 + (sb + c * KC) * 8, (uint32_t)nvalid * 32u, full);
+                        }
+                    } else {
+                        if (lane == 0) {
+                            mbar_expect_tx(full, Wg::B_BYTES + (uint32_t)(nvalid * Dp) * 4u);
+                            tma_load_3d(st + 2 * Wg::A_BYTES, &tmap_dh1, c * KC, 0, g, full);
+                        }
+                        __syncwarp();                                 // expect_tx is posted before any row copy can complete
+                        if (lane < nvalid) bulk_g2s(st + Wg::AUX + (uint32_t)(lane * Dp) * 4u, A.rp.obs + (size_t)rid * Dp, (uint32_t)Dp * 4u, full);
+                    }
+                    __syncwarp();
+                    rid = rid_next;
+                    ++used;
+                }
             }
-            ++used;
-            if (++stage == (uint32_t)Wg::STAGES) { stage = 0; ph ^= 1u; }
-        };
+            if (!ok && lane == 0) atomicExch(A.error, 25);
+        }
+    } else if (warp >= Wg::EPI_WARPS) {
+        // ------------------------------------------------------------------ converters ------------------
+        regs_dec<Wg::REGS_CONV>();
+        const int tc = tid - Wg::EPI_WARPS * 32;                      // 0..255
+        uint32_t used = 0;
+        int n = 0;
         auto put = [&](uint32_t o, uint32_t lo_off, const float4& x) {
             float4 hi, lo;
             split4<PASSES>(x, hi, lo);
             sts4(o, hi);
             if (PASSES == 3) sts4(o + lo_off, lo);
         };
+        auto in_place = [&](uint32_t o, uint32_t lo_off) {            // landed raw piece -> hi at the same address, lo beside it
+            const float4 x = lds4(o);
+            put(o, lo_off, x);
+        };
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        // W3 (as K4a saw it) of the first dW2 item; the next item's copy is fetched while this one is converted
+        float4 w3n = z4;
+        {
+            int g, t;
+            for (int q = blockIdx.x; q < n_items; q += gridDim.x) {
+                wg_item(q, G, g, t);
+                if (A.active[g] && t < 2) { w3n = __ldg(reinterpret_cast<const float4*>(A.w3_copy + (size_t)g * H * 4) + tc); break; }
+            }
+        }
         WG_TS_DECL;
         for (int q = blockIdx.x; q < n_items; q += gridDim.x) {
             int g, t;
             wg_item(q, G, g, t);
             if (!A.active[g]) continue;
             WG_TS();
-            const size_t sb = (size_t)g * B;
             if (t < 2) {
-                // ---- dW2 rows t*128..: A = h1^T scratch [m][k] (K-major SW64), register prefetch DW2 chunks ahead;
-                // B = dh2 rebuilt, staged MN-major ([k][n], n contiguous): dh2[k][n] = relu'(h2)[k][n] ? g_k * W3[n][a_k] : 0,
-                // thread = (k-row bu of the chunk, 16 columns n = 64 i + 4 ng + 0..3, i = 0..3), so one (g, action) pair
-                // and four mask words serve 16 values, W3^T comes from shared memory as four conflict-free 16-byte
-                // loads, and every store is a 16-byte piece of the UMMA layout.
-                constexpr int DW2 = 2;
-                const int bu = tid >> 4, ng = tid & 15, hh = ng >> 3, l7 = ng & 7;
+                // ---- dW2: A in place; B = dh2 rebuilt, staged MN-major ([k][n], n contiguous): thread = (k-row bu of the chunk,
+                // 16 columns n = 128 hh + 32 i + 4 l7 + 0..3, i = 0..3), so one (g, action) pair and four mask words serve 16
+                // values, W3^T comes from shared memory as four conflict-free 16-byte loads, every store is a 16-byte piece.
+                const int bu = tc >> 4, ng = tc & 15, hh = ng >> 3, l7 = ng & 7;
                 const uint32_t w3t = sbase + Wg::W3T + (uint32_t)(n & 1) * (4 * H * 4);
-                {
-                    const float4 w3n = __ldg(reinterpret_cast<const float4*>(A.w3_copy + (size_t)g * H * 4) + tid);
-                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(w3t + (uint32_t)(0 * H + tid) * 4), "f"(w3n.x) : "memory");
-                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(w3t + (uint32_t)(1 * H + tid) * 4), "f"(w3n.y) : "memory");
-                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(w3t + (uint32_t)(2 * H + tid) * 4), "f"(w3n.z) : "memory");
-                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(w3t + (uint32_t)(3 * H + tid) * 4), "f"(w3n.w) : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(w3t + (uint32_t)(0 * H + tc) * 4), "f"(w3n.x) : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(w3t + (uint32_t)(1 * H + tc) * 4), "f"(w3n.y) : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(w3t + (uint32_t)(2 * H + tc) * 4), "f"(w3n.z) : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(w3t + (uint32_t)(3 * H + tc) * 4), "f"(w3n.w) : "memory");
+                conv_sync();      // every item: a warp two items ahead would overwrite the buffer a slower warp still reads
+                {                 // prefetch W3 of this CTA's next dW2 item
+                    int g2, t2;
+                    for (int q2 = q + gridDim.x; q2 < n_items; q2 += gridDim.x) {
+                        wg_item(q2, G, g2, t2);
+                        if (t2 >= 2) break;
+                        if (A.active[g2]) { w3n = __ldg(reinterpret_cast<const float4*>(A.w3_copy + (size_t)g2 * H * 4) + tc); break; }
+                    }
                 }
-                prod_sync();      // every item: a warp two items ahead would overwrite the buffer a slower warp still reads
-                // A: pieces p = tid, tid + 256: row m = p/4, k piece p%4.  B: piece i of the thread = columns 32 (4 hh + i) + 4 l7 + 0..3,
-                // i.e. mask words 4 hh .. 4 hh + 3 of its batch row (one 16-byte load), W3^T at + 128 i bytes, stage atom + i.
-                const float* pa = A.h1 + sb * H + (size_t)(t * BM + (tid >> 2)) * B + ((tid & 3) << 2);
-                const size_t a_half = (size_t)64 * B;
-                const uint32_t a_dst = off_k64(BM, tid >> 2, (tid & 3) << 2);       // second piece: + 64 rows = + 4096 B
-                const float2* pga = A.ga + sb + bu;
-                const uint4* pmk = reinterpret_cast<const uint4*>(A.mask2) + (sb + bu) * 2 + hh;
-                const int mshift = l7 << 2, ka0 = (tid & 3) << 2;
+                const int mshift = l7 << 2;
                 const uint32_t w3t_thr = w3t + (uint32_t)(128 * hh + 4 * l7) * 4;
                 const uint32_t b_dst = 2 * Wg::A_BYTES + off_mn(H, bu, 128 * hh + 4 * l7);   // piece i: + i atoms of 512 B
-                float4 ra[DW2][2];
-                float2 gq[DW2];
-                uint4 mq[DW2];
-                auto load = [&](int slot, int c) {
-                    ra[slot][0] = z4; ra[slot][1] = z4;
-                    gq[slot] = make_float2(0.f, 0.f);
-                    mq[slot] = make_uint4(0u, 0u, 0u, 0u);
-                    if (c * KC + ka0 < B) {
-                        ra[slot][0] = ldg_stream(pa + c * KC);
-                        ra[slot][1] = ldg_stream(pa + c * KC + a_half);
+                for (int c = 0; c < nchunks; ++c) {
+                    const uint32_t s = used % Wg::STAGES, u = used / Wg::STAGES;
+                    const uint32_t st = sbase + s * Wg::STG;
+                    if (ok) ok = mbar_wait(bars + Wg::FULL + 8 * s, u & 1u);
+                    in_place(st + (uint32_t)tc * 16u, Wg::A_BYTES);
+                    in_place(st + (uint32_t)(tc + Wg::NCONV) * 16u, Wg::A_BYTES);
+                    float gg = 0.f;
+                    uint32_t wa = w3t_thr;
+                    uint4 mq = make_uint4(0u, 0u, 0u, 0u);
+                    if (c * KC + bu < B) {                            // rows past the batch: the side area holds stale bytes
+                        float2 gq;
+                        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(gq.x), "=f"(gq.y) : "r"(st + Wg::AUX + (uint32_t)bu * 8u));
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(mq.x), "=r"(mq.y), "=r"(mq.z), "=r"(mq.w)
+                                     : "r"(st + Wg::AUX + Wg::AUX_MASK + (uint32_t)bu * 32u + (uint32_t)hh * 16u));
+                        gg = gq.x;
+                        wa += (uint32_t)__float_as_int(gq.y) * (H * 4);
                     }
-                    if (c * KC + bu < B) {
-                        gq[slot] = __ldg(pga + c * KC);
-                        mq[slot] = __ldg(pmk + c * (KC * 2));
+                    const uint32_t mw[4] = {mq.x, mq.y, mq.z, mq.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 w4 = lds4(wa + (uint32_t)i * 128u);
+                        const uint32_t bits = mw[i] >> mshift;
+                        const float4 x = make_float4((bits & 1u) ? gg * w4.x : 0.f, (bits & 2u) ? gg * w4.y : 0.f,
+                                                     (bits & 4u) ? gg * w4.z : 0.f, (bits & 8u) ? gg * w4.w : 0.f);
+                        put(st + b_dst + (uint32_t)i * 512u, Wg::B_BYTES, x);
                     }
-                };
-#pragma unroll
-                for (int j = 0; j < DW2; ++j)
-                    if (j < nchunks) load(j, j);
-                for (int c0 = 0; c0 < nchunks; c0 += DW2) {
-#pragma unroll
-                    for (int j = 0; j < DW2; ++j) {
-                        const int c = c0 + j;
-                        if (c < nchunks) {                        // uniform across the CTA
-                            const uint32_t st = stage_begin();
-                            put(st + a_dst, Wg::A_BYTES, ra[j][0]);
-                            put(st + a_dst + 4096u, Wg::A_BYTES, ra[j][1]);
-                            const uint32_t wa = w3t_thr + (uint32_t)__float_as_int(gq[j].y) * (H * 4);
-                            const float gg = gq[j].x;
-                            const uint32_t mw[4] = {mq[j].x, mq[j].y, mq[j].z, mq[j].w};
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                float4 w4;
-                                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w4.x), "=f"(w4.y), "=f"(w4.z), "=f"(w4.w)
-                                             : "r"(wa + (uint32_t)i * 128u));
-                                const uint32_t bits = mw[i] >> mshift;
-                                const float4 x = make_float4((bits & 1u) ? gg * w4.x : 0.f, (bits & 2u) ? gg * w4.y : 0.f,
-                                                             (bits & 4u) ? gg * w4.z : 0.f, (bits & 8u) ? gg * w4.w : 0.f);
-                                put(st + b_dst + (uint32_t)i * 512u, Wg::B_BYTES, x);
-                            }
-                            if (c + DW2 < nchunks) load(j, c + DW2);
-                            stage_end(true, c);
-                        }
-                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bars + Wg::CONV + 8 * s);
+                    ++used;
                 }
             } else {
-                // ---- dW1 (+ db1): A = s rows gathered from the ring [k][m] (MN-major; column m = Dp is the ones column),
-                // B = dh1^T scratch [n][k] (K-major SW64); register prefetch DW1 chunks ahead.  The sampled row ids
-                // of the item are read once (one per thread and pass) instead of once per gathered piece.
-                constexpr int DW1 = 2;
-                const float* b_src = A.dh1 + sb * H + (size_t)(tid >> 2) * B + ((tid & 3) << 2);   // pieces p = tid + 256 r: row n = p/4 = tid/4 + 64 r
-                const uint32_t b_dst = 2 * Wg::A_BYTES + off_k64(H, tid >> 2, (tid & 3) << 2);  // + r * 64 rows * 64 B
-                const int am = (tid & 31) << 2, ak = tid >> 5;                   // pieces p = tid, tid + 256: k = p/32 = ak, ak + 8
+                // ---- dW1 (+ db1): B in place; A = the chunk's observation rows [k][m] (MN-major; column m = Dp is the ones column)
+                const int am = (tc & 31) << 2, ak = tc >> 5;          // pieces p = tc, tc + 256: k = ak, ak + 8
                 const bool a_live = am < Dp, a_ones = am == Dp;
-                const uint32_t a_dst = off_mn(BM, ak, am);                       // k + 8: two k-groups further = + 2 * 2048 B
-                const int32_t* rows = A.rows + sb;
-                float4 ra[DW1][2], rb[DW1][4];
-                auto load = [&](int slot, int c) {
+                const uint32_t a_dst = off_mn(BM, ak, am);            // k + 8: two k-groups further = + 2 * 2048 B
+                for (int c = 0; c < nchunks; ++c) {
+                    const uint32_t s = used % Wg::STAGES, u = used / Wg::STAGES;
+                    const uint32_t st = sbase + s * Wg::STG;
+                    if (ok) ok = mbar_wait(bars + Wg::FULL + 8 * s, u & 1u);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) in_place(st + 2 * Wg::A_BYTES + (uint32_t)(tc + Wg::NCONV * r) * 16u, Wg::B_BYTES);
 #pragma unroll
                     for (int r = 0; r < 2; ++r) {
-                        const int k = c * KC + ak + 8 * r;
-                        ra[slot][r] = z4;
-                        if (a_ones) ra[slot][r].x = k < B ? 1.f : 0.f;
-                        else if (a_live && k < B) ra[slot][r] = ldg_stream(A.rp.obs + (size_t)__ldg(rows + k) * Dp + am);
+                        const int kk = ak + 8 * r;
+                        const bool in_batch = c * KC + kk < B;
+                        float4 x = z4;
+                        if (a_ones) x.x = in_batch ? 1.f : 0.f;
+                        else if (a_live && in_batch) x = lds4(st + Wg::AUX + (uint32_t)(kk * Dp + am) * 4u);
+                        put(st + a_dst + (uint32_t)r * 4096u, Wg::A_BYTES, x);
                     }
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        rb[slot][r] = z4;
-                        if (c * KC + ((tid & 3) << 2) < B) rb[slot][r] = ldg_stream(b_src + (size_t)c * KC + (size_t)(64 * r) * B);
-                    }
-                };
-#pragma unroll
-                for (int j = 0; j < DW1; ++j)
-                    if (j < nchunks) load(j, j);
-                for (int c0 = 0; c0 < nchunks; c0 += DW1) {
-#pragma unroll
-                    for (int j = 0; j < DW1; ++j) {
-                        const int c = c0 + j;
-                        if (c < nchunks) {
-                            const uint32_t st = stage_begin();
-                            put(st + a_dst, Wg::A_BYTES, ra[j][0]);
-                            put(st + a_dst + 4096u, Wg::A_BYTES, ra[j][1]);
-#pragma unroll
-                            for (int r = 0; r < 4; ++r) put(st + b_dst + (uint32_t)r * 4096u, Wg::B_BYTES, rb[j][r]);
-                            if (c + DW1 < nchunks) load(j, c + DW1);
-                            stage_end(false, c);
-                        }
-                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bars + Wg::CONV + 8 * s);
+                    ++used;
                 }
             }
             ++n;
         }
-        if (warp == 0 && pend) issue_pending();
         WG_TS();
-        WG_TS_PRINT("K4b producer", tid == 0);
-        if (!ok && tid == 0) atomicExch(A.error, 5);
+        WG_TS_PRINT("K4b converters", tc == 0);
+        if (!ok && tc == 0) atomicExch(A.error, 5);
     } else {
+        regs_inc<Wg::REGS_EPI>();
         // ------------------------------------------------------------------ epilogue -------------------
-        const int et = tid - Wg::NPROD, ew = warp - 8;                   // 0..255 / 0..7
+        const int et = tid, ew = warp;                            // 0..255 / 0..7
         const int ehalf = ew >> 2;                                // TMEM lane = weight row (ew & 3) * 32 + lane of the tile; column half
         const uint32_t lane_addr = (uint32_t)((ew & 3) * 32) << 16;
         float* tile = reinterpret_cast<float*>(__cvta_shared_to_generic((size_t)(sbase + Wg::TILES))) + ew * (32 * Wg::TLD);
@@ -1492,7 +1508,8 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A) {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-int make_w2_tensor_map(const TcArgs& A, CUtensorMap* out) {
+int encode_map3(CUtensorMap* out, const float* base, cuuint64_t d0, cuuint64_t d1, cuuint64_t d2, cuuint64_t stride1_bytes,
+                cuuint64_t stride2_bytes, cuuint32_t box0, cuuint32_t box1, CUtensorMapSwizzle swz) {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -1504,17 +1521,27 @@ int make_w2_tensor_map(const TcArgs& A, CUtensorMap* out) {
         }
         encode = reinterpret_cast<EncodeTiledFn>(fn);
     }
-    const cuuint64_t dims[3] = {(cuuint64_t)H, (cuuint64_t)H, (cuuint64_t)A.d.n_nets};
-    const cuuint64_t strides[2] = {(cuuint64_t)H * sizeof(float), (cuuint64_t)A.L.stride * sizeof(float)};
-    const cuuint32_t box[3] = {16, (cuuint32_t)H, 1}, estr[3] = {1, 1, 1};
-    const CUresult rc = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, A.nets.theta + A.L.w2, dims, strides, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+    const cuuint64_t dims[3] = {d0, d1, d2};
+    const cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+    const cuuint32_t box[3] = {box0, box1, 1}, estr[3] = {1, 1, 1};
+    const CUresult rc = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)rc);
         return DMDQN_ERR_CUDA;
     }
     return DMDQN_OK;
+}
+int make_w2_tensor_map(const TcArgs& A, CUtensorMap* out) {
+    return encode_map3(out, A.nets.theta + A.L.w2, H, H, A.d.n_nets, (cuuint64_t)H * sizeof(float),
+                       (cuuint64_t)A.L.stride * sizeof(float), 16, H, CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+// K4b's K-major operands: the transposed scratch [n_nets][H features][B batch] as {B, H, n_nets}, box = {16 batch columns,
+// `rows` features}, landing with the 64-byte swizzle of the UMMA K-major SW64 layout (16-byte piece ^= (row / 2) % 4).
+int make_scratch_tensor_map(const TcArgs& A, const float* scratch, int rows, CUtensorMap* out) {
+    return encode_map3(out, scratch, A.d.batch, H, A.d.n_nets, (cuuint64_t)A.d.batch * sizeof(float),
+                       (cuuint64_t)A.d.batch * H * sizeof(float), KC, (cuuint32_t)rows, CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
 template <int PASSES>
@@ -1539,7 +1566,10 @@ int launch_tc(const TcArgs& A, int stages, cudaStream_t s) {
     }
     if (stages & DMDQN_STAGE_WGRAD) {
         const int items = A.d.n_nets * 3;
-        tc_wgrad_kernel<PASSES><<<items < n_sm ? items : n_sm, Wg::NTW, smem_w, s>>>(A);
+        CUtensorMap tmap_h1, tmap_dh1;
+        if (int rc = make_scratch_tensor_map(A, A.h1, BM, &tmap_h1)) return rc;
+        if (int rc = make_scratch_tensor_map(A, A.dh1, H, &tmap_dh1)) return rc;
+        tc_wgrad_kernel<PASSES><<<items < n_sm ? items : n_sm, Wg::NTW, smem_w, s>>>(A, tmap_h1, tmap_dh1);
         DMDQN_CUDA(cudaGetLastError());
     }
     return DMDQN_OK;

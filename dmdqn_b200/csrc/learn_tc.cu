@@ -1071,8 +1071,8 @@ struct Wg {     // persistent wgrad kernel, one CTA per SM
     static constexpr int EPI_WARPS = 8, CONV_WARPS = 8;       // warps 0-7 / 8-15; warp 16: MMA lane, warp 17: TMA, 18-19 fill the warpgroup
     static constexpr int NCONV = CONV_WARPS * 32;
     static constexpr int NTW = 20 * 32;                       // five warpgroups
-    // setmaxnreg per warpgroup inside the pool the CTA was launched with (640 x 96): 2 x 128 x 152 + 2 x 128 x 72 + 128 x 32
-    static constexpr int REGS_EPI = 152, REGS_CONV = 72, REGS_AUX = 32;
+    // setmaxnreg per warpgroup inside the pool the CTA was launched with (640 x 96): 2 x 128 x 160 + 2 x 128 x 64 + 128 x 32
+    static constexpr int REGS_EPI = 160, REGS_CONV = 64, REGS_AUX = 32;
 };
 __device__ __forceinline__ void conv_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 converter warps of K4b
 
@@ -1451,41 +1451,39 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A, co
                                 *reinterpret_cast<const float4*>(trow + 4 * up * Wg::TLD);
                     }
                 } else {
-                    // two batches of four row groups: every load of a batch is issued before its first use, so twelve
-                    // (sixteen with Polyak) 16-byte loads per thread are in flight while the HBM latency elapses
-#pragma unroll 1
-                    for (int it0 = 0; it0 < 8; it0 += 4) {
-                        int off[4];
-                        float4 gr4[4], t4[4], m4[4], v4[4], g4[4];
+                    // one batch of eight row groups: every theta / m / v load of the column block is issued before the first
+                    // use, so twenty-four 16-byte loads per thread are in flight while the HBM latency elapses (the gradient
+                    // comes from the tile at use; the Polyak target is read late: it is the rare mode)
+                    int off[8];
+                    float4 t4[8], m4[8], v4[8];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int m = mrow0 + 4 * (it0 + u);
-                            off[u] = wbase + 4 * (it0 + u) * H + c0;
-                            if (!is_w2) off[u] = m == Dp ? (int)A.L.b1 + c0 + c4 : (m < Dp ? off[u] : -1);   // db1 from the ones column
-                            gr4[u] = *reinterpret_cast<const float4*>(trow + 4 * (it0 + u) * Wg::TLD);
-                            if (is_w2 || off[u] >= 0) {
-                                t4[u] = ldg_plain(th + off[u]);
-                                m4[u] = ldg_plain(am + off[u]);
-                                v4[u] = ldg_plain(av + off[u]);
-                                if (sync == 2) g4[u] = ldg_plain(tg + off[u]);
-                            }
+                    for (int u = 0; u < 8; ++u) {
+                        const int m = mrow0 + 4 * u;
+                        off[u] = wbase + 4 * u * H + c0;
+                        if (!is_w2) off[u] = m == Dp ? (int)A.L.b1 + c0 + c4 : (m < Dp ? off[u] : -1);   // db1 from the ones column
+                        if (is_w2 || off[u] >= 0) {
+                            t4[u] = ldg_plain(th + off[u]);
+                            m4[u] = ldg_plain(am + off[u]);
+                            v4[u] = ldg_plain(av + off[u]);
                         }
+                    }
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            if (!is_w2 && off[u] < 0) continue;
-                            adam_fast(k, gr4[u].x, t4[u].x, m4[u].x, v4[u].x); adam_fast(k, gr4[u].y, t4[u].y, m4[u].y, v4[u].y);
-                            adam_fast(k, gr4[u].z, t4[u].z, m4[u].z, v4[u].z); adam_fast(k, gr4[u].w, t4[u].w, m4[u].w, v4[u].w);
-                            *reinterpret_cast<float4*>(th + off[u]) = t4[u];
-                            *reinterpret_cast<float4*>(am + off[u]) = m4[u];
-                            *reinterpret_cast<float4*>(av + off[u]) = v4[u];
-                            if (sync == 1) {
-                                *reinterpret_cast<float4*>(tg + off[u]) = t4[u];
-                            } else if (sync == 2) {
-                                const float omt = 1.0f - k.tau;
-                                g4[u] = make_float4(k.tau * t4[u].x + omt * g4[u].x, k.tau * t4[u].y + omt * g4[u].y,
-                                                    k.tau * t4[u].z + omt * g4[u].z, k.tau * t4[u].w + omt * g4[u].w);
-                                *reinterpret_cast<float4*>(tg + off[u]) = g4[u];
-                            }
+                    for (int u = 0; u < 8; ++u) {
+                        if (!is_w2 && off[u] < 0) continue;
+                        const float4 gr = *reinterpret_cast<const float4*>(trow + 4 * u * Wg::TLD);
+                        adam_fast(k, gr.x, t4[u].x, m4[u].x, v4[u].x); adam_fast(k, gr.y, t4[u].y, m4[u].y, v4[u].y);
+                        adam_fast(k, gr.z, t4[u].z, m4[u].z, v4[u].z); adam_fast(k, gr.w, t4[u].w, m4[u].w, v4[u].w);
+                        *reinterpret_cast<float4*>(th + off[u]) = t4[u];
+                        *reinterpret_cast<float4*>(am + off[u]) = m4[u];
+                        *reinterpret_cast<float4*>(av + off[u]) = v4[u];
+                        if (sync == 1) {
+                            *reinterpret_cast<float4*>(tg + off[u]) = t4[u];
+                        } else if (sync == 2) {
+                            const float omt = 1.0f - k.tau;
+                            const float4 g4 = ldg_plain(tg + off[u]);
+                            *reinterpret_cast<float4*>(tg + off[u]) =
+                                make_float4(k.tau * t4[u].x + omt * g4.x, k.tau * t4[u].y + omt * g4.y,
+                                            k.tau * t4[u].z + omt * g4.z, k.tau * t4[u].w + omt * g4.w);
                         }
                     }
                 }

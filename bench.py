@@ -378,7 +378,12 @@ def block_cfg5(args, rank, world, local, K, W):
            "target_update_frequency": 1000, "nn_layers": [hidden, hidden], "share_parameters": True, "precision": "auto"}
     grp = AgentGroup(agents_total // world, cfg, D, A, seed=42)            # same seed: replicas start identical
     synth_fill(grp, seed=300 + rank)
-    step = SharedParameterStep.for_group(grp)                              # world > 1: fused peer-memory reduce + Adam
+    fused_note = None
+    try:
+        step = SharedParameterStep.for_group(grp)                          # world > 1: fused peer-memory reduce + Adam
+    except Exception as exc:                                               # CUDA IPC refused on this box: measure the NCCL path, say so
+        fused_note = f"peer-memory exchange unavailable ({type(exc).__name__}: {str(exc)[:120]}): NCCL all_reduce path measured instead"
+        step = SharedParameterStep.for_group(grp, fused=False)
     stream = torch.cuda.current_stream()
 
     def run_steps(st):
@@ -422,7 +427,7 @@ def block_cfg5(args, rank, world, local, K, W):
             "value": ups * agents_total, "unit": "agent-updates/s (shared updates/s x 1024 agents served)",
             "shared_updates_per_s": ups, "samples_per_s": ups * batch_global, "ms_per_step": ms / K, "scaling": "strong",
             "steps": K, "phases_ms_rank0": phases, "replicas_identical": identical,
-            "reduction": "none (1 GPU)" if world == 1 else "dmdqn_allreduce_adam: flag exchange + peer loads over NVLink (CUDA IPC) + Adam in one kernel",
+            "reduction": "none (1 GPU)" if world == 1 else (fused_note or "dmdqn_allreduce_adam: flag exchange + peer loads over NVLink (CUDA IPC) + Adam in one kernel"),
             "nccl_baseline": None if ms_nccl is None else {"ms_per_step": ms_nccl / K, "value": K / (ms_nccl / 1e3) * agents_total,
                                                           "what": "torch.distributed all_reduce (NCCL) between dmdqn_learn_grads and dmdqn_adam_apply; phases_ms_rank0 splits this path"}}
 

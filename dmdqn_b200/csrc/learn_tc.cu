@@ -276,7 +276,7 @@ __device__ __forceinline__ float4 ldg_stream(const float* p) {   // volatile: is
 }
 __device__ __forceinline__ float4 ldg_plain(const float* p) {    // coherent (the same kernel writes these arrays), issue order kept
     float4 v;
-    asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
 __device__ __forceinline__ void sts4(uint32_t a, const float4& v) {

@@ -87,20 +87,37 @@ class PeerExchange:
             return self
         N, lib = self.N, self.grp.lib
         handle, off = (C.c_ubyte * 64)(), C.c_uint64()
+
+        def agree(err):         # every rank learns about any rank's failure, so all raise together (no one is left in a collective)
+            errs = [None] * self.world
+            dist.all_gather_object(errs, err, group=group)
+            bad = [f"rank {r}: {e}" for r, e in enumerate(errs) if e]
+            if bad:
+                self.close()
+                raise N.NativeError("peer-memory exchange could not be set up (" + "; ".join(bad) + ")")
         with torch.cuda.device(self.grp.device):
-            N.check(lib.dmdqn_ipc_export(self.buf.data_ptr(), handle, C.byref(off)))
+            err, mine = None, None
+            try:
+                N.check(lib.dmdqn_ipc_export(self.buf.data_ptr(), handle, C.byref(off)))
+                mine = (bytes(handle), int(off.value))
+            except Exception as exc:
+                err = str(exc)
+            agree(err)
             everyone = [None] * self.world
-            dist.all_gather_object(everyone, (bytes(handle), int(off.value)), group=group)
+            dist.all_gather_object(everyone, mine, group=group)
             self.ptrs = []
-            for p, (h, o) in enumerate(everyone):
-                if p == self.rank:
-                    self.ptrs.append(self.buf.data_ptr())
-                    continue
-                out = C.c_void_p()
-                N.check(lib.dmdqn_ipc_open((C.c_ubyte * 64).from_buffer_copy(h), o, C.byref(out)))
-                self.ptrs.append(int(out.value))
-                self._opened.append((int(out.value), o))
-            dist.barrier(group=group)       # nobody signals into a buffer its owner has not zeroed yet
+            try:
+                for p, (h, o) in enumerate(everyone):
+                    if p == self.rank:
+                        self.ptrs.append(self.buf.data_ptr())
+                        continue
+                    out = C.c_void_p()
+                    N.check(lib.dmdqn_ipc_open((C.c_ubyte * 64).from_buffer_copy(h), o, C.byref(out)))
+                    self.ptrs.append(int(out.value))
+                    self._opened.append((int(out.value), o))
+            except Exception as exc:
+                err = str(exc)
+            agree(err)                      # also the barrier: nobody signals into a buffer its owner has not zeroed yet
         return self
 
     @staticmethod

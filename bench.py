@@ -323,6 +323,39 @@ def block_act(args, rank, world, local):
             **out}
 
 
+def block_cfg2(args, rank, world, local, K, W):
+    """BASELINE cfg2: 16 agents (4x4 grid), batch 64 on one GPU -- a launch/latency-bound shape (each kernel runs one short item per
+    CTA on 16-48 of the 148 SMs).  Measured twice: the plain dmdqn_learn call per step, and the step captured once as a CUDA graph
+    (AgentGroup.capture_learn) and replayed.  Every rank runs its own copy; rank 0's numbers are reported."""
+    from dmdqn_b200.group import AgentGroup
+    w = WORKLOADS["cfg2"]
+    grp = AgentGroup(w["agents"], agent_cfg(w, args.precision), D, A, seed=77)
+    synth_fill(grp, seed=5)
+    n, b = grp.n_agents, grp.batch_size
+    draws = grp.draw_words((K + W, n, b))
+    ms_plain = time_learn(grp, draws, K, W, world)
+    replay, dbuf = grp.capture_learn()
+    stream = torch.cuda.current_stream()
+    for i in range(W):
+        dbuf.copy_(draws[i]); replay()
+    _barrier(world)
+    e0, e1 = _events(2)
+    e0.record(stream)
+    for i in range(K):
+        dbuf.copy_(draws[W + i]); replay()
+    e1.record(stream)
+    _barrier(world)
+    ms_graph = e0.elapsed_time(e1)
+    stage_ms = stage_times(grp, draws[W:], min(K, 20))
+    grp.check_errors()
+    del grp, draws
+    torch.cuda.empty_cache()
+    return {"workload": workload_name("cfg2"), "value": n * K / (ms_graph / 1e3), "unit": "agent-updates/s", "ms_per_step": ms_graph / K,
+            "how": "one CUDA-graph replay per step (sample, K3, K4a, K4b captured once; the draws buffer refilled before each replay)",
+            "plain_calls": {"value": n * K / (ms_plain / 1e3), "ms_per_step": ms_plain / K}, "steps": K,
+            "kernels_ms_rank0": stage_ms}
+
+
 def block_strong_cfg3(args, rank, world, local, K, W):
     """BASELINE cfg3 'then sharded 2/4/8': 256 agents in TOTAL, split by contiguous agent range over the ranks
     (parallel.shard_range), no collective.  value = 256 agents x steps / max-over-ranks time."""
@@ -534,10 +567,12 @@ def run_ours(args):
     # ---- the other configurations north_star names --------------------------------------------
     blocks = {}
     want = set(args.blocks.split(",")) if args.blocks not in ("all", "none") else (
-        {"act", "strong_cfg3", "cfg4", "cfg5"} if args.blocks == "all" else set())
+        {"act", "cfg2", "strong_cfg3", "cfg4", "cfg5"} if args.blocks == "all" else set())
     bk, bw = max(3, min(K, args.block_steps)), 3
     if "act" in want:
         extra["act"] = block_act(args, rank, world, local)
+    if "cfg2" in want:
+        blocks["cfg2"] = block_cfg2(args, rank, world, local, bk, bw)
     if "strong_cfg3" in want:
         blocks["strong_cfg3"] = block_strong_cfg3(args, rank, world, local, bk, bw)
     if "cfg4" in want:
@@ -673,7 +708,7 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--blocks", default="all", help="all | none | comma list of act,strong_cfg3,cfg4,cfg5")
+    ap.add_argument("--blocks", default="all", help="all | none | comma list of act,cfg2,strong_cfg3,cfg4,cfg5")
     ap.add_argument("--block-steps", type=int, default=30)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()

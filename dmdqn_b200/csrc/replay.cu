@@ -175,7 +175,11 @@ sample_kernel(dmdqn_dims d, dmdqn_hparams hp, dmdqn_replay rp, int32_t* __restri
 }
 
 // ---------------------------------------------------------------- gather ----------------
-// One warp per sampled transition: 2 x obs_stride floats in (whole 128-byte lines), dense out.
+// One warp per sampled transition.  The ring rows are obs_stride floats (whole 128-byte lines, 16-byte aligned), so the
+// read side is one 16-byte load per lane and tensor (24 of the 32 lanes at obs_stride = 96); the dense output rows are
+// obs_dim = 89 floats, i.e. not 16-byte aligned from row to row, so the write side stays 4-byte but fully coalesced:
+// the pieces are exchanged through shuffles so that lane l writes columns l, l + 32, l + 64 (consecutive lanes ->
+// consecutive addresses, whole 128-byte segments).
 __global__ void __launch_bounds__(128)
 gather_kernel(dmdqn_dims d, dmdqn_replay rp, const int32_t* __restrict__ rows, const float* __restrict__ r_hat,
               const int32_t* __restrict__ act_b, const float* __restrict__ done_b,
@@ -190,9 +194,24 @@ gather_kernel(dmdqn_dims d, dmdqn_replay rp, const int32_t* __restrict__ rows, c
     if (active_out && (r % d.batch) == 0 && lane == 0) active_out[g] = active[g];
     if (!active[g]) return;
     const size_t src = (size_t)rows[r] * d.obs_stride;
-    for (int c = lane; c < d.obs_dim; c += 32) {
-        states[r * d.obs_dim + c] = rp.obs[src + c];
-        next_states[r * d.obs_dim + c] = rp.next_obs[src + c];
+    const int q = d.obs_stride >> 2;                               // 16-byte pieces per row (<= 32: obs_stride <= 128)
+    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), n4 = s4;
+    if (lane < q) {
+        s4 = __ldg(reinterpret_cast<const float4*>(rp.obs + src) + lane);
+        n4 = __ldg(reinterpret_cast<const float4*>(rp.next_obs + src) + lane);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {                                   // column c = 32 k + lane lives in piece c / 4 = 8 k + lane / 4, component lane % 4
+        const int c = 32 * k + lane, from = 8 * k + (lane >> 2);
+        const float sx = __shfl_sync(0xffffffffu, s4.x, from), sy = __shfl_sync(0xffffffffu, s4.y, from);
+        const float sz = __shfl_sync(0xffffffffu, s4.z, from), sw = __shfl_sync(0xffffffffu, s4.w, from);
+        const float nx = __shfl_sync(0xffffffffu, n4.x, from), ny = __shfl_sync(0xffffffffu, n4.y, from);
+        const float nz = __shfl_sync(0xffffffffu, n4.z, from), nw = __shfl_sync(0xffffffffu, n4.w, from);
+        const int comp = lane & 3;
+        if (c < d.obs_dim) {
+            states[r * d.obs_dim + c] = comp == 0 ? sx : comp == 1 ? sy : comp == 2 ? sz : sw;
+            next_states[r * d.obs_dim + c] = comp == 0 ? nx : comp == 1 ? ny : comp == 2 ? nz : nw;
+        }
     }
     if (lane == 0) {
         actions[r] = act_b[r];

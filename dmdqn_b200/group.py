@@ -384,6 +384,37 @@ class AgentGroup:
         self.learn_step_host += self.active_host(mask).astype(np.int64)
         return self.metrics
 
+    @_on_device
+    def capture_learn(self, sample_mode: str | None = None):
+        """The learn step as a CUDA graph (sample -> K3 -> K4a -> K4b captured once, replayed with one launch): what a
+        small grid wants, where the four launches cost as much as the kernels (BASELINE cfg2: 16 agents, B = 64).
+        Returns ``(replay, draws)``: refill ``draws`` (int32 [n_nets, B] on the device: uniform words, or logical indices
+        in 'indices' mode) and call ``replay()`` -> metrics[G,8] (device, no host sync).  The library keeps no state, so the
+        graph is just the four kernels with their arguments; the step counters live on the device as always."""
+        hp = self._hp_for(sample_mode)
+        draws = self.draw_words((self.n_nets, self.batch_size)).contiguous()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+
+        def launch(stream_ptr, advance_host):
+            N.check(self.lib.dmdqn_learn(C.byref(self.dims), C.byref(hp), C.byref(self.replay), C.byref(self.nets),
+                                         _ptr(draws), None, _ptr(self.metrics), _ptr(self.workspace),
+                                         self.workspace.numel(), stream_ptr))
+            if advance_host:
+                self.learn_step_host += self.active_host().astype(np.int64)
+        with torch.cuda.stream(side):           # warm-up outside the capture: per-device launch attributes are set here
+            launch(side.cuda_stream, True)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            launch(torch.cuda.current_stream(self.device).cuda_stream, False)
+
+        def replay() -> torch.Tensor:
+            graph.replay()
+            self.learn_step_host += self.active_host().astype(np.int64)
+            return self.metrics
+        return replay, draws
+
     # ------------------------------------------------------------------ host-buffer step ----
     def make_step_block(self):
         """Pinned host block + device mirror for ``step_host``: typed views ``host[name]`` / ``dev[name]`` for

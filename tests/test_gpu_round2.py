@@ -638,3 +638,26 @@ def test_fused_peer_step_ranks_in_one_process_match_the_summed_gradient(world):
             for name in ("theta", "theta_tgt", "adam_m", "adam_v"):
                 assert torch.equal(getattr(ranks[r], name), getattr(ranks[0], name)), f"step {it}: replica {r} {name} diverged"
                 assert torch.equal(getattr(ranks[r], name), getattr(first, name)), f"step {it}: rank {r} {name} != summed-gradient reference"
+
+
+def test_captured_learn_graph_equals_plain_learn():
+    """AgentGroup.capture_learn: the CUDA-graph replay of a learn step gives the same bits as the plain call (cfg2 shape)."""
+    cfg = {"nn_layers": [256, 256], "replay_buffer_size": 300, "batch_size": 64, "precision": "tf32x3"}
+    a, b = _group(16, cfg, seed=9), _group(16, cfg, seed=9)
+    for g in (a, b):
+        _fill(g, None, np.random.default_rng(2), 300)
+    replay, draws = b.capture_learn()
+    # the warm-up inside capture_learn took one learn step on b with its own draws: do the same step on a
+    ma = a.learn(draws.clone())
+    rng = np.random.default_rng(8)
+    for it in range(4):
+        w = torch.as_tensor(rng.integers(0, 2**32, (16, 64), dtype=np.uint64).astype(np.uint32).view(np.int32)).to(a.device)
+        draws.copy_(w)
+        mb = replay().clone()
+        ma = a.learn(w).clone()
+        torch.cuda.synchronize()
+        assert torch.equal(ma, mb), f"step {it}: metrics differ"
+        for name in ("theta", "theta_tgt", "adam_m", "adam_v"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), f"step {it}: {name} differs"
+    assert np.array_equal(a.learn_step_host, b.learn_step_host)
+    assert torch.equal(a.learn_step, b.learn_step)

@@ -337,36 +337,44 @@ __device__ __forceinline__ bool tma_wait_gemm(uint32_t sbase, uint32_t& seen, ui
 //          one full phase early succeeds at once).
 // ------------------------------------------------------------------------------------------
 template <int PASSES>
-__device__ __forceinline__ bool conv_fwd(uint32_t sbase, int K, int tc, Ring& r, bool ok) {
+__device__ __forceinline__ bool conv_fwd(uint32_t sbase, int K, int grp, int t, Ring& r, bool ok) {
+    // Two groups of two warps, group g converts the chunks with (chunk count) % 2 == g into stage g: each group has a whole
+    // MMA chunk time (two chunks' worth) for its wait -> read -> split -> write -> arrive chain instead of one.
     const uint32_t bars = sbase + Fwd::BARS;
-    const int k0 = tc >> 6, n = (tc & 63) << 2;               // piece p = tc + 128 i: k-row tc / 64 + 2 i, columns 4 (tc % 64) .. + 3
-    for (int c = 0; c < (K >> 3); ++c) {
-        const uint32_t rs = r.f % NRAW, ru = r.f / NRAW, s = r.f % NSF, u = r.f / NSF;
+    const int k0 = t >> 6, n = (t & 63) << 2;                 // t = 0..63: piece p = t + 64 i: k-row i, columns 4 t .. + 3
+    const int nchunks = K >> 3;
+    for (int c = 0; c < nchunks; ++c) {
+        const uint32_t f = r.f + (uint32_t)c;
+        if ((int)(f % NSF) != grp) continue;                  // group g owns stage g
+        const uint32_t rs = f % NRAW, ru = f / NRAW, s = f % NSF, u = f / NSF;
         if (ok) ok = mbar_wait(bars + Bar::RAW_FULL + 8 * rs, ru & 1);                // the raw chunk has landed
-        float4 x[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) x[i] = lds4(sbase + Fwd::WB + rs * RAW_F + (uint32_t)(tc + 128 * i) * 16u);
-        // Generic-proxy reads of the slot must be ordered before the async-proxy (TMA) write that refills it: without this
-        // fence ptxas issues the arrive right behind the four LDS and ~1 % of the tiles saw a partly refilled chunk under load
-        // (tools/dbg_k3_repeat.py reproduces it in seconds).
-        fence_async_smem();
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) mbar_arrive(bars + Bar::RAW_EMPTY + 8 * rs);
         if (u && ok) ok = mbar_wait(bars + Bar::EMPTY_F + 8 * s, (u - 1) & 1);        // the MMAs of the stage's previous chunk have retired
-        const uint32_t st = sbase + Fwd::STG + s * STG_F;
+        const uint32_t st = sbase + Fwd::STG + s * STG_F, raw = sbase + Fwd::WB + rs * RAW_F;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float4 hi, lo;
-            split4<PASSES>(x[i], hi, lo);
-            const uint32_t o = st + off_mn(H, k0 + 2 * i, n);
-            sts4(o, hi);
-            if (PASSES == 3) sts4(o + RAW_F, lo);
+        for (int half = 0; half < 2; ++half) {
+            float4 x[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x[i] = lds4(raw + (uint32_t)(t + 64 * (4 * half + i)) * 16u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float4 hi, lo;
+                split4<PASSES>(x[i], hi, lo);
+                const uint32_t o = st + off_mn(H, k0 + 4 * half + i, n);
+                sts4(o, hi);
+                if (PASSES == 3) sts4(o + RAW_F, lo);
+            }
         }
+        // Generic-proxy reads of the raw slot must be ordered before the async-proxy (TMA) write that refills it, and the
+        // stage writes before the MMA's reads: one proxy fence serves both (without it ~1 % of the tiles saw a partly refilled
+        // chunk under load; tools/dbg_k3_repeat.py reproduces that in seconds).
         fence_async_smem();
         __syncwarp();
-        if ((threadIdx.x & 31) == 0) mbar_arrive(bars + Bar::CONV_F + 8 * s);
-        ++r.f;
+        if ((threadIdx.x & 31) == 0) {
+            mbar_arrive(bars + Bar::RAW_EMPTY + 8 * rs);
+            mbar_arrive(bars + Bar::CONV_F + 8 * s);
+        }
     }
+    r.f += (uint32_t)nchunks;
     return ok;
 }
 template <int PASSES>
@@ -625,10 +633,10 @@ __device__ __forceinline__ uint32_t tc_prologue(uint32_t sbase) {
     if (threadIdx.x == 0) {
         for (int b = 0; b < NRAW; ++b) {
             mbar_init(bars + Bar::RAW_FULL + 8 * b, 1);           // one arrive.expect_tx + the bytes of the chunk
-            mbar_init(bars + Bar::RAW_EMPTY + 8 * b, CONV_WARPS); // one arrival per converter warp
+            mbar_init(bars + Bar::RAW_EMPTY + 8 * b, CONV_GROUP_WARPS); // one arrival per warp of the converter group that read it
         }
         for (int b = 0; b < NSF; ++b) {
-            mbar_init(bars + Bar::CONV_F + 8 * b, CONV_WARPS);    // one arrival per converter warp
+            mbar_init(bars + Bar::CONV_F + 8 * b, CONV_GROUP_WARPS);    // one arrival per warp of the stage's converter group
             mbar_init(bars + Bar::EMPTY_F + 8 * b, 1);            // one tcgen05.commit
         }
         for (int b = 0; b < NSB; ++b) {
@@ -702,10 +710,10 @@ __global__ void __launch_bounds__(NT_F, 1) tc_target_kernel(const TcArgs A) {
         }
         __syncwarp();
       } else if (warp < W_CONV + CONV_WARPS) {   // converters (the last two warps only fill the warpgroup)
-        const int tc = threadIdx.x - W_CONV * 32;
+        const int tc = threadIdx.x - W_CONV * 32, cg = (warp - W_CONV) / CONV_GROUP_WARPS, t = tc % (CONV_GROUP_WARPS * 32);
         for (int q = k3_next(A, blockIdx.x, n_items); q < n_items; q = k3_next(A, q + gridDim.x, n_items)) {
-            ok = conv_fwd<PASSES>(sbase, Dp, tc, ring, ok);
-            ok = conv_fwd<PASSES>(sbase, H, tc, ring, ok);
+            ok = conv_fwd<PASSES>(sbase, Dp, cg, t, ring, ok);
+            ok = conv_fwd<PASSES>(sbase, H, cg, t, ring, ok);
         }
         if (!ok && tc == 0) atomicExch(A.error, 33);
       }
@@ -811,8 +819,8 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A, cons
       } else if (warp < W_CONV + CONV_WARPS) {   // converters (the last two warps only fill the warpgroup)
         const int tc = threadIdx.x - W_CONV * 32, cg = (warp - W_CONV) / CONV_GROUP_WARPS, t = tc % (CONV_GROUP_WARPS * 32);
         for (int q = k4_next(A, blockIdx.x, n_items); q < n_items; q = k4_next(A, q + gridDim.x, n_items)) {
-            ok = conv_fwd<PASSES>(sbase, Dp, tc, ring, ok);
-            ok = conv_fwd<PASSES>(sbase, H, tc, ring, ok);
+            ok = conv_fwd<PASSES>(sbase, Dp, cg, t, ring, ok);
+            ok = conv_fwd<PASSES>(sbase, H, cg, t, ring, ok);
             ok = conv_bwd<PASSES>(sbase, cg, t, ring, ok);
         }
         if (!ok && tc == 0) atomicExch(A.error, 34);

@@ -38,7 +38,7 @@ constexpr int BM = 128;         // batch rows per CTA (UMMA M)
 constexpr int EW = 16;          // gather / epilogue warps of K3 / K4a
 constexpr int NT = EW * 32;     // 512 threads
 constexpr int W_MMA = EW, W_TMA = EW + 1, W_CONV = EW + 2;   // warps 18..21: two converter groups of two warps; 22, 23 idle
-constexpr int CONV_WARPS = 4, CONV_GROUP_WARPS = 2;          // d.W^T: two groups of two warps, one per in-place stage
+constexpr int CONV_WARPS = 6, CONV_GROUP_WARPS = 2;          // d.W^T: two groups of two warps, one per in-place stage
 constexpr int NT_F = (EW + 8) * 32;   // 768 threads per K3 / K4a CTA: six warpgroups (setmaxnreg is per warpgroup)
 // Register split (setmaxnreg works per warpgroup, inside the pool the CTA was launched with: 768 x 80): the MMA / TMA
 // warpgroup and the converter warpgroup shrink to 32 and release 2 x 128 x 48 registers, which is exactly what the
@@ -241,7 +241,7 @@ struct Fwd {
     static constexpr uint32_t XLO = 3 * ATOM;                 // X lo (K <= 96) inside R
     static constexpr uint32_t WB = 8 * ATOM;                  // 80 KB of weight buffers: x.W: 6 raw slots of 8 KB (TMA targets) + 2 stages of
                                                               // 16 KB (hi | lo); d.W^T: 2 in-place stages of 32 KB over the first 64 KB
-    static constexpr uint32_t STG = WB + 6 * 8192;            // the two x.W stages
+    static constexpr uint32_t STG = WB + 4 * 8192;            // the three x.W stages
     static constexpr uint32_t BIAS1 = WB + 81920;             // b1[256]
     static constexpr uint32_t BIAS2 = BIAS1 + 1024;           // b2[256]
     static constexpr uint32_t W3S = BIAS2 + 1024;             // W3[256][4]
@@ -252,13 +252,13 @@ struct Fwd {
 };
 // Barrier block (byte offsets from Fwd::BARS).
 struct Bar {
-    static constexpr uint32_t RAW_FULL = 0, RAW_EMPTY = 48;              // x.W raw ring: 6 slots (TMA landed / converters have read it)
-    static constexpr uint32_t CONV_F = 96, EMPTY_F = 112;                // x.W stage ring: 2 stages (converted / MMAs retired)
+    static constexpr uint32_t RAW_FULL = 0, RAW_EMPTY = 32;              // x.W raw ring: 4 slots (TMA landed / converters have read it)
+    static constexpr uint32_t CONV_F = 64, EMPTY_F = 88;                 // x.W stage ring: 3 stages (converted / MMAs retired)
     static constexpr uint32_t TMA_B = 128, CONV_B = 144, EMPTY_B = 160;  // d.W^T ring: 2 in-place stages (same shared memory)
     static constexpr uint32_t AREADY = 176, DONE = 184;                  // A operand published (16 warps) / GEMM retired (1 commit)
     static constexpr uint32_t TMEM = 192;                                // TMEM base address (written by tcgen05.alloc)
 };
-constexpr int NRAW = 6, NSF = 2, NSB = 2;                     // raw slots / stages of the x.W pipe, stages of the d.W^T ring
+constexpr int NRAW = 4, NSF = 3, NSB = 2;                     // raw slots / stages of the x.W pipe, stages of the d.W^T ring
 constexpr uint32_t STG_F = 16384, RAW_F = 8192;               // x.W   stage: hi 8 KB | lo 8 KB   (8 k-rows x 256 columns)
 constexpr uint32_t STG_B = 32768, RAW_B = 16384;              // d.W^T stage: hi 16 KB | lo 16 KB (256 rows x 16 k-columns)
 
@@ -347,6 +347,10 @@ __device__ __forceinline__ bool conv_fwd(uint32_t sbase, int K, int grp, int t, 
         const uint32_t f = r.f + (uint32_t)c;
         if ((int)(f % NSF) != grp) continue;                  // group g owns stage g
         const uint32_t rs = f % NRAW, ru = f / NRAW, s = f % NSF, u = f / NSF;
+        // A raw slot is read by different groups from use to use (4 slots, 3 groups), and a parity wait cannot tell "two phases
+        // ahead" from "done": a group that ran ahead would take the slot's PREVIOUS chunk for its own.  So it first waits until
+        // that previous use has been read (by whichever group) -- after that the slot's FULL barrier is exactly one phase behind.
+        if (ru && ok) ok = mbar_wait(bars + Bar::RAW_EMPTY + 8 * rs, (ru - 1) & 1);
         if (ok) ok = mbar_wait(bars + Bar::RAW_FULL + 8 * rs, ru & 1);                // the raw chunk has landed
         if (u && ok) ok = mbar_wait(bars + Bar::EMPTY_F + 8 * s, (u - 1) & 1);        // the MMAs of the stage's previous chunk have retired
         const uint32_t st = sbase + Fwd::STG + s * STG_F, raw = sbase + Fwd::WB + rs * RAW_F;

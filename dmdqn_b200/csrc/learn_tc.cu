@@ -53,7 +53,7 @@ constexpr unsigned long long WAIT_LIMIT_NS = 2000000000ull;   // a wrong descrip
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 1 = SWIZZLE_128B_BASE32B (the only MN-major layout for tf32)
+// layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B, 1 = SWIZZLE_128B_BASE32B (the only MN-major layout for tf32)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16 |
            (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32 | (uint64_t)1 << 46 | (uint64_t)layout << 61;
@@ -254,13 +254,13 @@ struct Fwd {
 struct Bar {
     static constexpr uint32_t RAW_FULL = 0, RAW_EMPTY = 32;              // x.W raw ring: 4 slots (TMA landed / converters have read it)
     static constexpr uint32_t CONV_F = 64, EMPTY_F = 88;                 // x.W stage ring: 3 stages (converted / MMAs retired)
-    static constexpr uint32_t TMA_B = 128, CONV_B = 144, EMPTY_B = 160;  // d.W^T ring: 2 in-place stages (same shared memory)
-    static constexpr uint32_t AREADY = 176, DONE = 184;                  // A operand published (16 warps) / GEMM retired (1 commit)
-    static constexpr uint32_t TMEM = 192;                                // TMEM base address (written by tcgen05.alloc)
+    static constexpr uint32_t TMA_B = 112, CONV_B = 152, EMPTY_B = 192;  // d.W^T ring: 5 in-place stages (same shared memory)
+    static constexpr uint32_t AREADY = 232, DONE = 240;                  // A operand published (16 warps) / GEMM retired (1 commit)
+    static constexpr uint32_t TMEM = 248;                                // TMEM base address (written by tcgen05.alloc)
 };
-constexpr int NRAW = 4, NSF = 3, NSB = 2;                     // raw slots / stages of the x.W pipe, stages of the d.W^T ring
+constexpr int NRAW = 4, NSF = 3, NSB = 5;                     // raw slots / stages of the x.W pipe, stages of the d.W^T ring
 constexpr uint32_t STG_F = 16384, RAW_F = 8192;               // x.W   stage: hi 8 KB | lo 8 KB   (8 k-rows x 256 columns)
-constexpr uint32_t STG_B = 32768, RAW_B = 16384;              // d.W^T stage: hi 16 KB | lo 16 KB (256 rows x 16 k-columns)
+constexpr uint32_t STG_B = 16384, RAW_B = 8192;               // d.W^T stage: hi 8 KB | lo 8 KB   (256 rows x 8 k-columns, one k-step)
 
 // Chunk / GEMM counters.  Every role walks the same sequence of items, GEMMs and chunks, so each keeps its own copy:
 // f / b = chunks that have gone through the x.W / d.W^T ring so far (stage = count % stages, use = count / stages,
@@ -304,14 +304,15 @@ __device__ __forceinline__ bool tma_fwd(uint32_t sbase, const float* __restrict_
     }
     return ok;
 }
-// d.W^T: box {16 k-columns, 256 rows, network g} of W2 seen as a rank-3 tensor -> 256 rows of 64 B, dense
+// d.W^T: box {8 k-columns, 256 rows, network g} of W2 seen as a rank-3 tensor -> 256 rows of 32 B with the 32-byte swizzle of
+// the UMMA K-major SW32 layout, straight into the hi half of a stage (five stages of 16 KB: one k-step each)
 __device__ __forceinline__ bool tma_bwd(uint32_t sbase, const CUtensorMap* tm, int g, Ring& r, bool ok) {
     const uint32_t bars = sbase + Fwd::BARS;
-    for (int c = 0; c < H / 16; ++c) {
+    for (int c = 0; c < H / 8; ++c) {
         const uint32_t s = r.b % NSB, u = r.b / NSB;
         if (u && ok) ok = mbar_wait(bars + Bar::EMPTY_B + 8 * s, (u - 1) & 1);
         mbar_expect_tx(bars + Bar::TMA_B + 8 * s, RAW_B);
-        tma_load_3d(sbase + Fwd::WB + s * STG_B, tm, c * 16, 0, g, bars + Bar::TMA_B + 8 * s);      // in place: the hi half of the stage
+        tma_load_3d(sbase + Fwd::WB + s * STG_B, tm, c * 8, 0, g, bars + Bar::TMA_B + 8 * s);       // in place: the hi half of the stage
         ++r.b;
     }
     return ok;
@@ -383,54 +384,55 @@ __device__ __forceinline__ bool conv_fwd(uint32_t sbase, int K, int grp, int t, 
 }
 template <int PASSES>
 __device__ __forceinline__ bool conv_bwd(uint32_t sbase, int grp, int t, Ring& r, bool ok) {
+    // In place: the chunk landed in the hi half of its stage already swizzled (TMA SWIZZLE_32B == UMMA K-major SW32), so a
+    // thread reads a 16-byte piece, leaves its hi part at the same address and puts the lo part 8 KB further.  Chunk c of the
+    // ring goes to group c % 3; stages (5) and groups (3) do not line up, hence the same guard as in conv_fwd: wait until the
+    // stage's previous chunk has been converted (by whichever group) before trusting the parity of its TMA barrier.
     const uint32_t bars = sbase + Fwd::BARS;
-    for (int c = 0; c < H / 16; ++c) {
+    constexpr int NGRP = CONV_WARPS / CONV_GROUP_WARPS;
+    for (int c = 0; c < H / 8; ++c) {
         const uint32_t b = r.b + (uint32_t)c;
-        if ((int)(b % NSB) != grp) continue;                  // group g owns stage g
+        if ((int)(b % NGRP) != grp) continue;
         const uint32_t s = b % NSB, u = b / NSB;
         const uint32_t st = sbase + Fwd::WB + s * STG_B;
+        if (u && ok) ok = mbar_wait(bars + Bar::CONV_B + 8 * s, (u - 1) & 1);
         if (ok) ok = mbar_wait(bars + Bar::TMA_B + 8 * s, u & 1);
-        // piece p = t + 64 j: row p / 4 = t / 4 + 16 j, 16-byte piece t % 4 of its 64-byte row.  The swizzle permutes the four
-        // pieces of a row among themselves, and those sit on four neighbouring lanes: a warp barrier is all it needs.
 #pragma unroll
-        for (int rnd = 0; rnd < 4; ++rnd) {
+        for (int half = 0; half < 2; ++half) {
             float4 x[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) x[i] = lds4(st + (uint32_t)(t + 64 * (4 * rnd + i)) * 16u);
-            __syncwarp();
+            for (int i = 0; i < 4; ++i) x[i] = lds4(st + (uint32_t)(t + 64 * (4 * half + i)) * 16u);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int row = (t >> 2) + 16 * (4 * rnd + i), pc = t & 3;
                 float4 hi, lo;
                 split4<PASSES>(x[i], hi, lo);
-                const uint32_t o = st + (uint32_t)row * 64u + (uint32_t)((pc ^ ((row >> 1) & 3)) << 4);   // off_k64
-                sts4(o, hi);
-                if (PASSES == 3) sts4(o + RAW_B, lo);
+                const uint32_t o = st + (uint32_t)(t + 64 * (4 * half + i)) * 16u;
+                if (PASSES == 3) { sts4(o, hi); sts4(o + RAW_B, lo); }      // (one pass: the tensor core truncates the raw words itself)
             }
         }
         fence_async_smem();
         __syncwarp();
         if ((threadIdx.x & 31) == 0) mbar_arrive(bars + Bar::CONV_B + 8 * s);
     }
-    r.b += (uint32_t)(H / 16);
+    r.b += (uint32_t)(H / 8);
     return ok;
 }
 
 // ------------------------------------------------------------------------------------------
 // MMA lane (lane 0 of warp W_MMA): D[128 x 256] (TMEM columns 0..255) = A[128 x K] * op(W), fp32 via PASSES MMAs.
 //   A hi: shared memory, K-major SW128 at a_hi; A lo: shared memory (a_lo_smem != 0) or TMEM columns.
-//   BT = false: x.W, stages MN-major, one k-step per chunk;  BT = true: d.W^T, stages K-major SW64, two k-steps per chunk.
+//   BT = false: x.W, stages MN-major;  BT = true: d.W^T, stages K-major SW32.  One k-step (8 k) per chunk either way.
 // ------------------------------------------------------------------------------------------
 template <int PASSES, bool BT>
 __device__ __forceinline__ bool mma_gemm(uint32_t sbase, uint32_t tmem, uint32_t a_hi, uint32_t a_lo_smem, uint32_t a_lo_tmem,
                                          int K, Ring& r, bool ok) {
     const uint32_t bars = sbase + Fwd::BARS;
-    constexpr int KCX = BT ? 16 : 8;
+    constexpr int KCX = 8;
     constexpr uint32_t idesc = make_idesc(false, !BT);
     // Descriptors differ only in their 14-bit start-address field: build each once, then add (bytes >> 4).
     const uint64_t a_hi0 = make_desc(a_hi, 16, 1024, 2);
     const uint64_t a_lo0 = make_desc(a_lo_smem, 16, 1024, 2);
-    const uint64_t b0 = BT ? make_desc(sbase + Fwd::WB, 16, 512, 4) : make_desc(sbase + Fwd::STG, 512, 4096, 1);
+    const uint64_t b0 = BT ? make_desc(sbase + Fwd::WB, 16, 256, 6) : make_desc(sbase + Fwd::STG, 512, 4096, 1);
     if (ok) ok = mbar_wait(bars + Bar::AREADY, r.gemms & 1);      // all 16 epilogue warps have published the A operand
     tc_fence_after();
     const int nchunks = K / KCX;
@@ -443,7 +445,7 @@ __device__ __forceinline__ bool mma_gemm(uint32_t sbase, uint32_t tmem, uint32_t
         for (int ks = 0; ks < KCX / 8; ++ks) {
             const int kg = c * KCX + ks * 8;
             const uint32_t a_off = ((uint32_t)(kg >> 5) * ATOM + (uint32_t)((kg & 31) >> 3) * 32) >> 4;
-            const uint32_t b_off = (s * (BT ? STG_B : STG_F) + (BT ? ks * 32u : 0u)) >> 4;
+            const uint32_t b_off = (s * (BT ? STG_B : STG_F)) >> 4;
             const uint64_t a_hi_d = a_hi0 + a_off;
             const uint64_t b_hi = b0 + b_off, b_lo = b0 + b_off + ((BT ? RAW_B : RAW_F) >> 4);
             uint32_t acc = (c | ks) ? 1u : 0u;
@@ -1545,7 +1547,7 @@ int encode_map3(CUtensorMap* out, const float* base, cuuint64_t d0, cuuint64_t d
 }
 int make_w2_tensor_map(const TcArgs& A, CUtensorMap* out) {
     return encode_map3(out, A.nets.theta + A.L.w2, H, H, A.d.n_nets, (cuuint64_t)H * sizeof(float),
-                       (cuuint64_t)A.L.stride * sizeof(float), 16, H, CU_TENSOR_MAP_SWIZZLE_NONE);
+                       (cuuint64_t)A.L.stride * sizeof(float), 8, H, CU_TENSOR_MAP_SWIZZLE_32B);
 }
 // K4b's K-major operands: the transposed scratch [n_nets][H features][B batch] as {B, H, n_nets}, box = {16 batch columns,
 // `rows` features}, landing with the 64-byte swizzle of the UMMA K-major SW64 layout (16-byte piece ^= (row / 2) % 4).

@@ -291,12 +291,19 @@ __device__ __forceinline__ float4 lds4(uint32_t a) {
 // ------------------------------------------------------------------------------------------
 // TMA producer (lane 0 of warp W_TMA).
 // ------------------------------------------------------------------------------------------
-// x.W: W is [K][256] row-major; chunk c = rows 8c .. 8c+7 = 8 KB contiguous -> a raw slot, as it lies.  Six slots deep:
-// under load an L2 read takes ~2 000 cycles and the tensor pipe wants a chunk every ~470.
-__device__ __forceinline__ bool tma_fwd(uint32_t sbase, const float* __restrict__ W, int K, Ring& r, bool ok) {
+// x.W: W is [K][256] row-major; chunk c = rows 8c .. 8c+7 = 8 KB contiguous -> a raw slot, as it lies.  Four slots deep;
+// under load a DRAM read takes ~2 000 cycles and the tensor pipe wants a chunk every ~410, which four slots cannot cover,
+// so every chunk is also requested into L2 PF chunks ahead of its copy (of this matrix, then of `next`: the matrix
+// the ring streams after this one), which turns the copies into L2 hits.
+constexpr int PF = 6;
+__device__ __forceinline__ bool tma_fwd(uint32_t sbase, const float* __restrict__ W, int K, Ring& r, bool ok,
+                                        const float* __restrict__ next) {
     const uint32_t bars = sbase + Fwd::BARS;
-    for (int c = 0; c < (K >> 3); ++c) {
+    const int nchunks = K >> 3;
+    for (int c = 0; c < nchunks; ++c) {
         const uint32_t s = r.f % NRAW, u = r.f / NRAW;
+        if (c + PF < nchunks) l2_prefetch(W + (size_t)(c + PF) * 8 * H, RAW_F);
+        else if (next) l2_prefetch(next + (size_t)(c + PF - nchunks) * 8 * H, RAW_F);
         if (u && ok) ok = mbar_wait(bars + Bar::RAW_EMPTY + 8 * s, (u - 1) & 1);      // the converters have read the previous chunk of this slot
         mbar_expect_tx(bars + Bar::RAW_FULL + 8 * s, RAW_F);
         bulk_g2s(sbase + Fwd::WB + s * RAW_F, W + (size_t)c * 8 * H, RAW_F, bars + Bar::RAW_FULL + 8 * s);
@@ -706,11 +713,14 @@ __global__ void __launch_bounds__(NT_F, 1) tc_target_kernel(const TcArgs A) {
         __syncwarp();
       } else if (warp == W_TMA) {
         if ((threadIdx.x & 31) == 0) {
-            for (int q = k3_next(A, blockIdx.x, n_items); q < n_items; q = k3_next(A, q + gridDim.x, n_items)) {
+            for (int q = k3_next(A, blockIdx.x, n_items); q < n_items;) {
                 const int g = (q >> 1) / A.tiles;
                 const float* P = ((q & 1) ? A.nets.theta_tgt : A.nets.theta) + (size_t)g * A.L.stride;
-                ok = tma_fwd(sbase, P + A.L.w1, Dp, ring, ok);
-                ok = tma_fwd(sbase, P + A.L.w2, H, ring, ok);
+                const int qn = k3_next(A, q + gridDim.x, n_items);
+                const float* Pn = qn < n_items ? ((qn & 1) ? A.nets.theta_tgt : A.nets.theta) + (size_t)((qn >> 1) / A.tiles) * A.L.stride + A.L.w1 : nullptr;
+                ok = tma_fwd(sbase, P + A.L.w1, Dp, ring, ok, P + A.L.w2);
+                ok = tma_fwd(sbase, P + A.L.w2, H, ring, ok, Pn);
+                q = qn;
             }
             if (!ok) atomicExch(A.error, 23);
         }
@@ -812,8 +822,10 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A, cons
             for (int q = k4_next(A, blockIdx.x, n_items); q < n_items; q = k4_next(A, q + gridDim.x, n_items)) {
                 const int g = q / A.tiles;
                 const float* P = A.nets.theta + (size_t)g * A.L.stride;
-                ok = tma_fwd(sbase, P + A.L.w1, Dp, ring, ok);
-                ok = tma_fwd(sbase, P + A.L.w2, H, ring, ok);
+                const int qn = k4_next(A, q + gridDim.x, n_items);
+                const float* Pn = qn < n_items ? A.nets.theta + (size_t)(qn / A.tiles) * A.L.stride + A.L.w1 : nullptr;
+                ok = tma_fwd(sbase, P + A.L.w1, Dp, ring, ok, P + A.L.w2);
+                ok = tma_fwd(sbase, P + A.L.w2, H, ring, ok, Pn);
                 ok = tma_wait_gemm(sbase, seen, gemm + 1, ok);       // the d.W^T stages alias the x.W stages: layer 2 must have retired
                 ok = tma_bwd(sbase, &tmap_w2, g, ring, ok);
                 ok = tma_wait_gemm(sbase, seen, gemm + 2, ok);       // ... and the backward GEMM before the next item's W1 chunks

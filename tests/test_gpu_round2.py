@@ -661,3 +661,38 @@ def test_captured_learn_graph_equals_plain_learn():
             assert torch.equal(getattr(a, name), getattr(b, name)), f"step {it}: {name} differs"
     assert np.array_equal(a.learn_step_host, b.learn_step_host)
     assert torch.equal(a.learn_step, b.learn_step)
+
+
+@pytest.mark.parametrize("n,batch,cap,reps", [(150, 64, 80, 12), (300, 128, 160, 6)])
+def test_tcgen05_forward_kernels_are_bit_stable_run_to_run(n, batch, cap, reps):
+    """Race detector for the persistent warp-specialised K3 / K4a (several items per CTA, TMA ring + converter groups + MMA lane
+    coupled by mbarriers): the same inputs re-run `reps` times must give the same BITS every time, and agree with the FFMA kernels.
+    Both races found while building these kernels (a missing proxy fence before the TMA refill of a raw slot; a converter group
+    taking a slot's previous chunk for its own through mbarrier parity aliasing) corrupted ~1 % of the tiles under load and
+    showed up here within a few repetitions, while single-shot parity tests passed."""
+    import ctypes as C
+    cfg = {"nn_layers": [256, 256], "replay_buffer_size": cap, "batch_size": batch}
+    ref, tc = _group(n, dict(cfg, precision="fp32"), seed=4), _group(n, dict(cfg, precision="tf32x3"), seed=4)
+    for g in (ref, tc):
+        _fill(g, None, np.random.default_rng(6), cap + 3)
+    d = tc.draw_words((n, batch))
+
+    def stages(grp, mask):
+        from dmdqn_b200 import _native as N
+        N.check(grp.lib.dmdqn_learn_stages(C.byref(grp.dims), C.byref(grp.hp), C.byref(grp.replay), C.byref(grp.nets), d.data_ptr(), None,
+                                           grp.metrics.data_ptr(), grp.workspace.data_ptr(), grp.workspace.numel(), mask,
+                                           torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        v = grp.debug_views()
+        assert int(v["tc_error"][0]) == 0
+        return {k: v[k].clone() for k in ("q_next", "tq_all", "q_all", "y", "dh1")}
+    stages(ref, 1); stages(tc, 1)
+    want = stages(ref, 2 | 4)
+    first = stages(tc, 2 | 4)
+    for k in ("q_next", "tq_all", "q_all"):
+        close(first[k].cpu().numpy(), want[k].cpu().numpy(), rtol=RTOL, what=f"tcgen05 vs FFMA {k}")
+    for rep in range(reps):
+        again = stages(tc, 2 | 4)
+        for k, v in again.items():
+            same = torch.equal(v, first[k])
+            assert same, f"repetition {rep}: {k} differs from the first run in networks {torch.nonzero((v != first[k]).flatten(1).any(1)).flatten().tolist()[:8]}"

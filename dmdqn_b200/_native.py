@@ -112,7 +112,7 @@ def lib() -> C.CDLL:
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)  # AttributeError if the .so does not export it
             fn.restype, fn.argtypes = res, args
-        if handle.dmdqn_abi_version() != 1:
+        if handle.dmdqn_abi_version() != 2:      # 2: + dmdqn_allreduce_adam, dmdqn_ipc_* (round 2)
             raise NativeError("libdmdqn_b200.so ABI version mismatch: rebuild")
         _lib = handle
     return _lib

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define DMDQN_ABI_VERSION 1
+#define DMDQN_ABI_VERSION 2
 
 #define DMDQN_OK            0
 #define DMDQN_ERR_ARG      -1   /* bad dims / null pointer / unsupported size          */

@@ -247,7 +247,7 @@ int dmdqn_learn_grads(const dmdqn_dims* dims, const dmdqn_hparams* hp, const dmd
     rc = launch_sample(*dims, *hp, *replay, *nets, draws, learn_mask, 1, (char*)workspace, w, (cudaStream_t)stream);
     if (rc) return rc;
     return launch_learn(*dims, *hp, *replay, *nets, metrics_out, (char*)workspace, w,
-                        DMDQN_STAGE_TARGET | DMDQN_STAGE_ONLINE | DMDQN_STAGE_WGRAD, grads_out, global_batch, nullptr,
+                        DMDQN_STAGE_SAMPLE | DMDQN_STAGE_TARGET | DMDQN_STAGE_ONLINE | DMDQN_STAGE_WGRAD, grads_out, global_batch, nullptr,
                         (cudaStream_t)stream);
 }
 

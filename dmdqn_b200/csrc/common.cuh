@@ -70,6 +70,8 @@ struct Workspace {
     size_t part_b3;                   // [n_nets][T][4]
     size_t part_w3;                   // [n_nets][T][H][4]
     size_t part_b2, part_b1;          // [n_nets][T][H]
+    size_t sync;                      // tcgen05 path, int32: [0] K4b work counter, [1..3] spare, [4 ..] k4a_done[n_nets], then
+                                      // k3_done[n_nets][T]; zeroed by the sample kernel (dataflow flags between the learn kernels)
     size_t total;
     int tiles;
 };
@@ -105,6 +107,7 @@ inline Workspace make_workspace(const dmdqn_dims& d) {
     w.part_w3 = take(nt * d.hidden * 4 * 4);
     w.part_b2 = take(nt * d.hidden * 4);
     w.part_b1 = take(nt * d.hidden * 4);
+    w.sync = take((4 + (size_t)d.n_nets + nt) * 4);
     w.total = off;
     return w;
 }

@@ -203,7 +203,30 @@ struct TcArgs {
     float* w3_copy;               // [n_nets][H][4]
     float *y, *gcoef, *q_all, *q_next, *tq_all, *h1, *dh1, *dh2, *part_loss, *part_b3, *part_w3, *part_b2, *metrics, *grads;
     int* error;
+    // Dataflow between the learn kernels of one dmdqn_learn call (`chain`: the sample kernel of the same call has reset the
+    // flags): K4a / K4b are programmatic dependent launches whose CTAs start on SMs the previous kernel has left and wait
+    // per (network, tile) / per network instead of for the whole previous grid.
+    int chain, tiles_ws;
+    int *sched, *k4a_done, *k3_done;      // K4b work counter | K4a items finished per network | K3 items finished per (network, tile)
 };
+
+// Release / acquire on a global flag (gpu scope).  The producer calls flag_release after a CTA-wide barrier that follows
+// its last global store of the item; the consumer's bounded spin ends in an error flag, never in a hung GPU.
+__device__ __forceinline__ void flag_release_add(int* f) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(f) : "memory");
+}
+__device__ __forceinline__ bool flag_acquire_ge(const int* f, int want) {
+    // bounded by an iteration count (one register) rather than by the global timer: 2^23 polls of >= 256 ns are > 2 s
+    for (int i = 0; i < (1 << 23); ++i) {
+        int v;
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if (v >= want) return true;
+        __nanosleep(256);
+    }
+    return false;
+}
+__device__ __forceinline__ unsigned smid_() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // Phase stamps (build with -DTC_TIMING, tools/phase_timing.sh): a few threads print clock64 deltas.
 #ifdef TC_TIMING
@@ -698,14 +721,21 @@ __global__ void __launch_bounds__(NT_F, 1) tc_target_kernel(const TcArgs A) {
     const int warp = threadIdx.x >> 5;
     KT_BEGIN;
     const uint32_t tmem = tc_prologue(sbase);
+    if (A.chain) pdl_launch_dependents();      // K4a's CTAs may take an SM as soon as this kernel's CTA has left it
     Ring ring;
     bool ok = true;
     if (warp >= EW) {
         regs_dec<REGS_AUX>();          // one instruction for both auxiliary warpgroups (.aligned)
       if (warp == W_MMA) {
         if ((threadIdx.x & 31) == 0) {
+            // This lane also publishes the PREVIOUS item's outputs (release of the per-tile flag): it has just seen every
+            // epilogue warp arrive for this item's layer 1 -- an arrival that follows that warp's last store of the previous
+            // item -- and it is idle until the layer-1 epilogue is done, so the fence costs the epilogue warps nothing.
+            int prev = -1;
             for (int q = k3_next(A, blockIdx.x, n_items); q < n_items; q = k3_next(A, q + gridDim.x, n_items)) {
                 ok = mma_gemm<PASSES, false>(sbase, tmem, sbase + Fwd::R, sbase + Fwd::XLO, 0, Dp, ring, ok);
+                if (prev >= 0) flag_release_add(A.k3_done + (size_t)((prev >> 1) / A.tiles) * A.tiles_ws + (prev >> 1) % A.tiles);
+                prev = q;
                 ok = mma_gemm<PASSES, false>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, H, ring, ok);
             }
             if (!ok) atomicExch(A.error, 13);
@@ -742,6 +772,7 @@ __global__ void __launch_bounds__(NT_F, 1) tc_target_kernel(const TcArgs A) {
             const int g = (q >> 1) / A.tiles, rt = (q >> 1) % A.tiles;
             xg.begin(A.rp.next_obs, A.rows + (size_t)g * B, rt * BM, B, Dp);
         }
+        int q_last = -1;                                       // the last item is published here, the others by the MMA lane
         while (q < n_items) {
             const int item = q >> 1, pass = q & 1;            // 0: online(s')  1: target(s')
             const int g = item / A.tiles, rt = item % A.tiles, r0 = rt * BM;
@@ -776,8 +807,11 @@ __global__ void __launch_bounds__(NT_F, 1) tc_target_kernel(const TcArgs A) {
                 float* out = (pass == 0 ? A.q_next : A.tq_all) + ((size_t)g * B + gr) * 4;
                 *reinterpret_cast<float4*>(out) = make_float4(qv[0], qv[1], qv[2], qv[3]);
             }
+            q_last = q;
             q = qn;
         }
+        epi_sync();
+        if (q_last >= 0 && threadIdx.x == 0) flag_release_add(A.k3_done + (size_t)((q_last >> 1) / A.tiles) * A.tiles_ws + (q_last >> 1) % A.tiles);
         if (!ok && threadIdx.x == 0) atomicExch(A.error, 3);
         KT_END("K3");
     }
@@ -802,14 +836,18 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A, cons
     const int warp = threadIdx.x >> 5;
     KT_BEGIN;
     const uint32_t tmem = tc_prologue(sbase);
+    if (A.chain) pdl_launch_dependents();      // K4b's CTAs may take an SM as soon as this kernel's CTA has left it
     Ring ring;
     bool ok = true;
     if (warp >= EW) {
         regs_dec<REGS_AUX>();          // one instruction for both auxiliary warpgroups (.aligned)
       if (warp == W_MMA) {
         if ((threadIdx.x & 31) == 0) {
+            int prev = -1;                                     // as in K3: the previous item is published from this lane's idle window
             for (int q = k4_next(A, blockIdx.x, n_items); q < n_items; q = k4_next(A, q + gridDim.x, n_items)) {
                 ok = mma_gemm<PASSES, false>(sbase, tmem, sbase + Fwd::R, sbase + Fwd::XLO, 0, Dp, ring, ok);
+                if (prev >= 0) flag_release_add(A.k4a_done + prev / A.tiles);
+                prev = q;
                 ok = mma_gemm<PASSES, false>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, H, ring, ok);
                 ok = mma_gemm<PASSES, true>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, H, ring, ok);
             }
@@ -821,6 +859,8 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A, cons
             uint32_t seen = 0, gemm = 0;
             for (int q = k4_next(A, blockIdx.x, n_items); q < n_items; q = k4_next(A, q + gridDim.x, n_items)) {
                 const int g = q / A.tiles;
+                // K3 may still be running on other SMs: both halves of this tile's TD-target inputs must have been published
+                if (A.chain && ok) ok = flag_acquire_ge(A.k3_done + (size_t)g * A.tiles_ws + q % A.tiles, 2);
                 const float* P = A.nets.theta + (size_t)g * A.L.stride;
                 const int qn = k4_next(A, q + gridDim.x, n_items);
                 const float* Pn = qn < n_items ? A.nets.theta + (size_t)(qn / A.tiles) * A.L.stride + A.L.w1 : nullptr;
@@ -849,6 +889,7 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A, cons
         XGather<PASSES> xg;
         int q = k4_next(A, blockIdx.x, n_items);
         if (q < n_items) xg.begin(A.rp.obs, A.rows + (size_t)(q / A.tiles) * B, (q % A.tiles) * BM, B, Dp);
+        int q_last = -1;                                       // the last item is published here, the others by the MMA lane
         while (q < n_items) {
             const int g = q / A.tiles, rt = q % A.tiles, r0 = rt * BM;
             const size_t sb = (size_t)g * B;
@@ -860,11 +901,18 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A, cons
             KT_FIRST();
             load_small_params(sbase, P, A.L);
             xg.store(sbase);
+            a_ready(sbase);
+            epi_sync();        // biases / head weights visible to every epilogue thread
+            TS();
+            ok = wait_gemm(sbase, ring, ok);
+            TS();
             // TD target of this row from the two halves of K3 (reference :342-347), ties -> lowest index
+            // (in a chain the TMA lane has waited for K3's flag of this tile before it sent the first weight chunk of the
+            // item, so by the time the layer-1 GEMM has retired both halves are in L2; the loads bypass L1)
             float yi = 0.f;
             if (valid) {
-                const float4 qo = *reinterpret_cast<const float4*>(A.q_next + (sb + gr) * 4);
-                const float4 qt = *reinterpret_cast<const float4*>(A.tq_all + (sb + gr) * 4);
+                const float4 qo = ldg_plain(A.q_next + (sb + gr) * 4);
+                const float4 qt = ldg_plain(A.tq_all + (sb + gr) * 4);
                 const float q_on[4] = {qo.x, qo.y, qo.z, qo.w}, q_tg[4] = {qt.x, qt.y, qt.z, qt.w};
                 float bmax = q_on[0], tq = q_tg[0], tmax = q_tg[0];
 #pragma unroll
@@ -878,11 +926,6 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A, cons
                 yi = A.r_hat[sb + gr] + (A.gamma * (1.0f - A.done_b[sb + gr])) * tq;
                 if (e.part == 0) A.y[sb + gr] = yi;
             }
-            a_ready(sbase);
-            epi_sync();        // biases / head weights visible to every epilogue thread
-            TS();
-            ok = wait_gemm(sbase, ring, ok);
-            TS();
             uint32_t mask1[2], mask2[2];
             epi_hidden<PASSES>(sbase, tmem, e, Fwd::BIAS1, valid ? A.h1 + sb * H + gr : nullptr, B, mask1);
             a_ready(sbase);
@@ -1032,8 +1075,11 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A, cons
             }
             TS();
             TS_PRINT("K4a store L1 epi1 L2 epi2 loss+dW3 dh2 bwdGEMM dh1store");
+            q_last = q;
             q = qn;
         }
+        epi_sync();
+        if (q_last >= 0 && threadIdx.x == 0) flag_release_add(A.k4a_done + q_last / A.tiles);
         if (!ok && threadIdx.x == 0) atomicExch(A.error, 4);
         KT_END("K4a");
     }
@@ -1093,7 +1139,9 @@ struct Wg {     // persistent wgrad kernel, one CTA per SM
     static constexpr uint32_t W3T = TILES + 8 * 32 * TLD * 4; // W3^T [2 item parities][4 actions][256] floats
     static constexpr uint32_t BARS = W3T + 2 * 4 * H * 4;
     static constexpr uint32_t FULL = 0, CONV = 24, EMPTY = 48, ACC_FULL = 72, ACC_FREE = 88, TMEM = 104;   // byte offsets from BARS
-    static constexpr uint32_t TOTAL = BARS + 128;
+    static constexpr int NQ = 8;                              // item queue: the TMA warp is never more than ~4 items ahead of the epilogue
+    static constexpr uint32_t QFULL = 112, QITEM = QFULL + 8 * NQ;   // NQ mbarriers (item published) | NQ item numbers
+    static constexpr uint32_t TOTAL = BARS + 256;
     static constexpr int EPI_WARPS = 8, CONV_WARPS = 8;       // warps 0-7 / 8-15; warp 16: MMA lane, warp 17: TMA, 18-19 fill the warpgroup
     static constexpr int NCONV = CONV_WARPS * 32;
     static constexpr int NTW = 20 * 32;                       // five warpgroups
@@ -1107,6 +1155,32 @@ __device__ __forceinline__ void conv_sync() { asm volatile("bar.sync 1, 256;" ::
 __device__ __forceinline__ void wg_item(int q, int G, int& g, int& t) {
     if (q < 2 * G) { g = q >> 1; t = q & 1; }
     else { g = q - 2 * G; t = 2; }
+}
+
+// The item order is a QUEUE, not a static walk: the TMA warp draws item numbers from a global counter (reset by the sample
+// kernel, or by a memset when the stage is launched on its own) and publishes them through shared memory; the other roles
+// pop them in the same order.  A CTA that starts early (K4b is a programmatic dependent launch of K4a: its CTAs take over
+// the SMs K4a's last partial wave leaves idle) or draws the short dW1 items simply draws more, so the kernel ends within
+// one item on every SM.  Only items of active networks are published; -1 ends the walk.  No "slot free" barrier is needed:
+// publishing item n comes after the TMA warp has issued every chunk of item n - 1, which needs the MMA lane inside item
+// >= n - 4 (three stages, >= 1 chunk per item), which needs the epilogue to have released item n - 6: every role has
+// popped item n - 8 long before its slot is reused.
+__device__ __forceinline__ int wg_pop(uint32_t bars, int& nq, bool& ok) {
+    const uint32_t slot = (uint32_t)nq & (Wg::NQ - 1);
+    int q = -1;
+    if ((threadIdx.x & 31) == 0) {
+        if (ok) ok = mbar_wait(bars + Wg::QFULL + 8 * slot, (uint32_t)(nq >> 3) & 1u);
+        if (ok) asm volatile("ld.shared.s32 %0, [%1];" : "=r"(q) : "r"(bars + Wg::QITEM + 4 * slot));
+    }
+    ++nq;
+    q = __shfl_sync(0xffffffffu, q, 0);
+    if (q < 0) ok = __shfl_sync(0xffffffffu, (int)ok, 0) != 0;
+    return q;
+}
+__device__ __forceinline__ float ldcg_f(const float* p) {        // L2 loads: data another kernel's CTAs may have written while this CTA was resident
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
 }
 
 // dW tile: D[128 x 256] = A^T-operand * D-operand over K = batch, Adam in the epilogue.
@@ -1151,6 +1225,7 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A, co
             mbar_init(bars + Wg::ACC_FULL + 8 * b, 1);                // one tcgen05.commit
             mbar_init(bars + Wg::ACC_FREE + 8 * b, Wg::EPI_WARPS);    // one arrival per epilogue warp
         }
+        for (int b = 0; b < Wg::NQ; ++b) mbar_init(bars + Wg::QFULL + 8 * b, 1);   // one arrival: the TMA warp's lane 0
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -1168,13 +1243,15 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A, co
         regs_dec<Wg::REGS_AUX>();
         if (warp == Wg::EPI_WARPS + Wg::CONV_WARPS) {
             // ------------------------------------------------------------------ MMA lane -------------------
-            if (lane == 0) {
+            {
                 uint32_t used = 0;
-                int n = 0;
-                for (int q = blockIdx.x; q < n_items; q += gridDim.x) {
+                int n = 0, nq = 0;
+                for (;;) {
+                    const int q = wg_pop(bars, nq, ok);
+                    if (q < 0) break;
+                    if (lane != 0) continue;
                     int g, t;
                     wg_item(q, G, g, t);
-                    if (!A.active[g]) continue;
                     const bool is_w2 = t < 2;
                     const uint32_t acc_buf = (uint32_t)(n & 1);
                     const uint32_t d_tmem = tmem + acc_buf * 256u;
@@ -1214,16 +1291,40 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A, co
                     }
                     ++n;
                 }
-                if (!ok) atomicExch(A.error, 15);
+                if (!ok && lane == 0) atomicExch(A.error, 15);
             }
             __syncwarp();
         } else if (warp == Wg::EPI_WARPS + Wg::CONV_WARPS + 1) {
             // ------------------------------------------------------------------ TMA producer ---------------
             uint32_t used = 0;
-            for (int q = blockIdx.x; q < n_items; q += gridDim.x) {
+            int nq = 0;
+            for (;;) {
+                int q = 0;
+                if (lane == 0) q = atomicAdd(A.sched, 1);
+                q = __shfl_sync(0xffffffffu, q, 0);
+                if (q >= n_items || !ok) break;
                 int g, t;
                 wg_item(q, G, g, t);
-                if (!A.active[g]) continue;
+                if (!A.active[g]) {                                   // nothing to compute: only the metrics row is cleared
+                    if (t == 2 && lane < DMDQN_METRICS_STRIDE && A.metrics) A.metrics[g * DMDQN_METRICS_STRIDE + lane] = 0.f;
+                    continue;
+                }
+                if (A.chain) {
+                    // every K4a item of this network has published its scratch (h1^T, dh1^T, masks, (g, action), partials);
+                    // the tensor-map / bulk reads below are async-proxy reads of data written through the generic proxy
+                    int fine = 1;
+                    if (lane == 0) {
+                        fine = flag_acquire_ge(A.k4a_done + g, A.tiles) ? 1 : 0;
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                    }
+                    ok = __shfl_sync(0xffffffffu, fine, 0) != 0;
+                    if (!ok) break;
+                }
+                if (lane == 0) {
+                    asm volatile("st.shared.s32 [%0], %1;" ::"r"(bars + Wg::QITEM + 4 * ((uint32_t)nq & (Wg::NQ - 1))), "r"(q) : "memory");
+                    mbar_arrive(bars + Wg::QFULL + 8 * ((uint32_t)nq & (Wg::NQ - 1)));
+                }
+                ++nq;
                 const size_t sb = (size_t)g * B;
                 int32_t rid = 0;
                 if (t == 2 && lane < KC && lane < B) rid = __ldg(A.rows + sb + lane);
@@ -1254,6 +1355,16 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A, co
                     ++used;
                 }
             }
+            if (lane == 0) {                                          // end of the walk
+                asm volatile("st.shared.s32 [%0], %1;" ::"r"(bars + Wg::QITEM + 4 * ((uint32_t)nq & (Wg::NQ - 1))), "r"(-1) : "memory");
+                mbar_arrive(bars + Wg::QFULL + 8 * ((uint32_t)nq & (Wg::NQ - 1)));
+                // the last CTA to make its final draw leaves the counter at zero for the next launch (a stage launched on its
+                // own has no sample kernel in front of it to do that)
+                if (atomicAdd(A.sched + 1, 1) == (int)gridDim.x - 1) {
+                    atomicExch(A.sched + 1, 0);
+                    atomicExch(A.sched, 0);
+                }
+            }
             if (!ok && lane == 0) atomicExch(A.error, 25);
         }
     } else if (warp >= Wg::EPI_WARPS) {
@@ -1273,22 +1384,18 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A, co
             put(o, lo_off, x);
         };
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        // W3 (as K4a saw it) of the first dW2 item; the next item's copy is fetched while this one is converted
-        float4 w3n = z4;
-        {
-            int g, t;
-            for (int q = blockIdx.x; q < n_items; q += gridDim.x) {
-                wg_item(q, G, g, t);
-                if (A.active[g] && t < 2) { w3n = __ldg(reinterpret_cast<const float4*>(A.w3_copy + (size_t)g * H * 4) + tc); break; }
-            }
-        }
+        int nq = 0;
         WG_TS_DECL;
-        for (int q = blockIdx.x; q < n_items; q += gridDim.x) {
+        for (;;) {
+            const int q = wg_pop(bars, nq, ok);
+            if (q < 0) break;
             int g, t;
             wg_item(q, G, g, t);
-            if (!A.active[g]) continue;
             WG_TS();
             if (t < 2) {
+                // W3 as K4a saw it (the items are drawn dynamically, so it is fetched at the start of the item: an L2 hit that
+                // elapses next to the first chunk's TMA)
+                const float4 w3n = ldg_plain(A.w3_copy + (size_t)g * H * 4 + tc * 4);
                 // ---- dW2: A in place; B = dh2 rebuilt, staged MN-major ([k][n], n contiguous): thread = (k-row bu of the chunk,
                 // 16 columns n = 128 hh + 32 i + 4 l7 + 0..3, i = 0..3), so one (g, action) pair and four mask words serve 16
                 // values, W3^T comes from shared memory as four conflict-free 16-byte loads, every store is a 16-byte piece.
@@ -1299,14 +1406,6 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A, co
                 asm volatile("st.shared.f32 [%0], %1;" ::"r"(w3t + (uint32_t)(2 * H + tc) * 4), "f"(w3n.z) : "memory");
                 asm volatile("st.shared.f32 [%0], %1;" ::"r"(w3t + (uint32_t)(3 * H + tc) * 4), "f"(w3n.w) : "memory");
                 conv_sync();      // every item: a warp two items ahead would overwrite the buffer a slower warp still reads
-                {                 // prefetch W3 of this CTA's next dW2 item
-                    int g2, t2;
-                    for (int q2 = q + gridDim.x; q2 < n_items; q2 += gridDim.x) {
-                        wg_item(q2, G, g2, t2);
-                        if (t2 >= 2) break;
-                        if (A.active[g2]) { w3n = __ldg(reinterpret_cast<const float4*>(A.w3_copy + (size_t)g2 * H * 4) + tc); break; }
-                    }
-                }
                 const int mshift = l7 << 2;
                 const uint32_t w3t_thr = w3t + (uint32_t)(128 * hh + 4 * l7) * 4;
                 const uint32_t b_dst = 2 * Wg::A_BYTES + off_mn(H, bu, 128 * hh + 4 * l7);   // piece i: + i atoms of 512 B
@@ -1380,15 +1479,16 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A, co
         const uint32_t lane_addr = (uint32_t)((ew & 3) * 32) << 16;
         float* tile = reinterpret_cast<float*>(__cvta_shared_to_generic((size_t)(sbase + Wg::TILES))) + ew * (32 * Wg::TLD);
         const int rsub = lane >> 3, c4 = (lane & 7) << 2;
-        int n = 0;
+        int n = 0, nq = 0;
         WG_TS_DECL;
-        for (int q = blockIdx.x; q < n_items; q += gridDim.x) {
+#ifdef TC_TIMING
+        const long long wg_t0 = clock64();
+#endif
+        for (;;) {
+            const int q = wg_pop(bars, nq, ok);
+            if (q < 0) break;
             int g, t;
             wg_item(q, G, g, t);
-            if (!A.active[g]) {
-                if (t == 2 && et < DMDQN_METRICS_STRIDE && A.metrics) A.metrics[g * DMDQN_METRICS_STRIDE + et] = 0.f;
-                continue;
-            }
             // A bounded mbarrier wait that expired (here or in K3 / K4a of this step) means the accumulators are garbage:
             // leave theta / m / v alone and report it through the learned flag instead of applying the update.
             const int err_code = *reinterpret_cast<volatile int*>(A.error);
@@ -1414,23 +1514,23 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A, co
                 const size_t p0 = (size_t)g * A.tiles;
                 float s2 = 0.f, w[4] = {0.f, 0.f, 0.f, 0.f};
                 for (int r = 0; r < A.tiles; ++r) {
-                    s2 += A.part_b2[(p0 + r) * H + et];
-                    const float4 pw = reinterpret_cast<const float4*>(A.part_w3 + (p0 + r) * H * 4)[et];
+                    s2 += ldcg_f(A.part_b2 + (p0 + r) * H + et);
+                    const float4 pw = ldg_plain(A.part_w3 + ((p0 + r) * H + et) * 4);
                     w[0] += pw.x; w[1] += pw.y; w[2] += pw.z; w[3] += pw.w;
                 }
                 upd(A.L.b2 + et, s2);
                 for (int a = 0; a < 4; ++a) upd(A.L.w3 + (int64_t)et * 4 + a, w[a]);
                 if (et < 4) {
                     float s3 = 0.f;
-                    for (int r = 0; r < A.tiles; ++r) s3 += A.part_b3[(p0 + r) * 4 + et];
+                    for (int r = 0; r < A.tiles; ++r) s3 += ldcg_f(A.part_b3 + (p0 + r) * 4 + et);
                     upd(A.L.b3 + et, s3);
                 }
                 if (et == 0 && A.metrics) {
                     double ls = 0, qs = 0, qq = 0, hist[4] = {0, 0, 0, 0};
                     for (int r = 0; r < A.tiles; ++r) {
                         const float* pl = A.part_loss + (p0 + r) * 8;
-                        ls += pl[0]; qs += pl[1]; qq += pl[2];
-                        for (int a = 0; a < 4; ++a) hist[a] += pl[3 + a];
+                        ls += ldcg_f(pl); qs += ldcg_f(pl + 1); qq += ldcg_f(pl + 2);
+                        for (int a = 0; a < 4; ++a) hist[a] += ldcg_f(pl + 3 + a);
                     }
                     const double cnt = (double)B * A.d.n_actions, mean = qs / cnt, var = fmax(qq / cnt - mean * mean, 0.0);
                     float* m = A.metrics + g * DMDQN_METRICS_STRIDE;
@@ -1519,6 +1619,9 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A, co
         }
         WG_TS();
         WG_TS_PRINT("K4b epilogue (wait, adam)*", et == 0);
+#ifdef TC_TIMING
+        if (et == 0) printf("K4bsum cta %d sm %d items %d cycles %lld\n", blockIdx.x, (int)smid_(), n, clock64() - wg_t0);
+#endif
         if (!ok && lane == 0) atomicExch(A.error, 6);
     }
     tc_fence_before();
@@ -1578,6 +1681,16 @@ int launch_tc(const TcArgs& A, int stages, cudaStream_t s) {
     if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void*>(tc_online_kernel<PASSES>), smem_f, cfg_o)) return rc;
     if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void*>(tc_wgrad_kernel<PASSES>), smem_w, cfg_w)) return rc;
     const int items = A.d.n_nets * A.tiles;                       // persistent: one CTA per SM walks its items
+    // In a chain (sample + K3 + K4a + K4b issued by one call) K4a and K4b are programmatic dependent launches: their CTAs
+    // are scheduled as soon as every CTA of the previous kernel is resident, take over SMs as that kernel's CTAs leave, and
+    // order themselves behind the data they need with the per-tile / per-network flags.  Every CTA of the producer is
+    // resident (or finished) before a consumer CTA exists, so a waiting consumer can never starve its producer.
+    cudaLaunchAttribute pdl[1];
+    pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.stream = s;
+    cfg.attrs = pdl;
     if (stages & DMDQN_STAGE_TARGET) {
         tc_target_kernel<PASSES><<<2 * items < n_sm ? 2 * items : n_sm, NT_F, smem_f, s>>>(A);
         DMDQN_CUDA(cudaGetLastError());
@@ -1585,16 +1698,22 @@ int launch_tc(const TcArgs& A, int stages, cudaStream_t s) {
     if (stages & DMDQN_STAGE_ONLINE) {
         CUtensorMap tmap;
         if (int rc = make_w2_tensor_map(A, &tmap)) return rc;
-        tc_online_kernel<PASSES><<<items < n_sm ? items : n_sm, NT_F, smem_f, s>>>(A, tmap);
-        DMDQN_CUDA(cudaGetLastError());
+        cfg.gridDim = dim3(items < n_sm ? items : n_sm);
+        cfg.blockDim = dim3(NT_F);
+        cfg.dynamicSmemBytes = smem_f;
+        cfg.numAttrs = A.chain ? 1 : 0;
+        DMDQN_CUDA(cudaLaunchKernelEx(&cfg, tc_online_kernel<PASSES>, A, tmap));
     }
     if (stages & DMDQN_STAGE_WGRAD) {
         const int items = A.d.n_nets * 3;
         CUtensorMap tmap_h1, tmap_dh1;
         if (int rc = make_scratch_tensor_map(A, A.h1, BM, &tmap_h1)) return rc;
         if (int rc = make_scratch_tensor_map(A, A.dh1, H, &tmap_dh1)) return rc;
-        tc_wgrad_kernel<PASSES><<<items < n_sm ? items : n_sm, Wg::NTW, smem_w, s>>>(A, tmap_h1, tmap_dh1);
-        DMDQN_CUDA(cudaGetLastError());
+        cfg.gridDim = dim3(items < n_sm ? items : n_sm);
+        cfg.blockDim = dim3(Wg::NTW);
+        cfg.dynamicSmemBytes = smem_w;
+        cfg.numAttrs = A.chain ? 1 : 0;
+        DMDQN_CUDA(cudaLaunchKernelEx(&cfg, tc_wgrad_kernel<PASSES>, A, tmap_h1, tmap_dh1));
     }
     return DMDQN_OK;
 }
@@ -1647,6 +1766,12 @@ int launch_learn_tc(const dmdqn_dims& d, const dmdqn_hparams& hp, const dmdqn_re
     A.metrics = metrics;
     A.grads = grads;
     A.error = reinterpret_cast<int*>(ws + w.tc_error);
+    const int all = DMDQN_STAGE_SAMPLE | DMDQN_STAGE_TARGET | DMDQN_STAGE_ONLINE | DMDQN_STAGE_WGRAD;
+    A.chain = (stages & all) == all ? 1 : 0;      // the sample kernel of this call has just reset the flags
+    A.tiles_ws = w.tiles;
+    A.sched = reinterpret_cast<int*>(ws + w.sync);
+    A.k4a_done = A.sched + 4;
+    A.k3_done = A.k4a_done + d.n_nets;
     return hp.precision == DMDQN_PRECISION_TF32 ? launch_tc<1>(A, stages, s) : launch_tc<3>(A, stages, s);
 }
 

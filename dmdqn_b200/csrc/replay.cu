@@ -67,7 +67,7 @@ sample_kernel(dmdqn_dims d, dmdqn_hparams hp, dmdqn_replay rp, int32_t* __restri
               const uint32_t* __restrict__ draws, const uint8_t* __restrict__ learn_mask, int advance,
               int32_t* __restrict__ rows, float* __restrict__ r_hat, int32_t* __restrict__ act_b,
               float* __restrict__ done_b, int32_t* __restrict__ active, int32_t* __restrict__ step_t,
-              float4* __restrict__ adam_sc) {
+              float4* __restrict__ adam_sc, int32_t* __restrict__ sync, int tiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int B = d.batch, Bp = (B + 1) & ~1;
     int* js = reinterpret_cast<int*>(smem_raw);
@@ -77,6 +77,11 @@ sample_kernel(dmdqn_dims d, dmdqn_hparams hp, dmdqn_replay rp, int32_t* __restri
     __shared__ double stat[2];
     const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const bool shared_net = d.n_nets == 1 && d.n_agents > 1;
+    // dataflow flags of the tcgen05 learn kernels (learn_tc.cu): this launch is ordered after every kernel of the previous
+    // step, so it is the one place where they can be reset without a race
+    if (tid < 4 && g == 0) sync[tid] = 0;
+    if (tid == 4) sync[4 + g] = 0;
+    if (tid >= 32 && tid < 32 + tiles) sync[4 + d.n_nets + g * tiles + (tid - 32)] = 0;
 
     // Population: this agent's ring, or (shared parameters) all rings of this GPU, which the
     // host keeps equally filled, concatenated agent-major.
@@ -242,7 +247,7 @@ int launch_sample(const dmdqn_dims& d, const dmdqn_hparams& hp, const dmdqn_repl
         reinterpret_cast<int32_t*>(ws + w.rows), reinterpret_cast<float*>(ws + w.r_hat),
         reinterpret_cast<int32_t*>(ws + w.act_b), reinterpret_cast<float*>(ws + w.done_b),
         reinterpret_cast<int32_t*>(ws + w.active), reinterpret_cast<int32_t*>(ws + w.step_t),
-        reinterpret_cast<float4*>(ws + w.adam_sc));
+        reinterpret_cast<float4*>(ws + w.adam_sc), reinterpret_cast<int32_t*>(ws + w.sync), w.tiles);
     DMDQN_CUDA(cudaGetLastError());
     return DMDQN_OK;
 }

@@ -238,12 +238,12 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 #define TS() do { if (tsi_ < 16) ts_[tsi_++] = clock64(); } while (0)
 #define TS_D(i) (i < tsi_ ? ts_[i] - ts_[i - 1] : 0LL)
 #define TS_PRINT(name) do { if (TC_TIMING > 1 && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 77 || blockIdx.x == gridDim.x - 1)) \
-        printf("%s cta %d: %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld | total %lld\n", name, blockIdx.x, TS_D(1), TS_D(2), TS_D(3), \
-               TS_D(4), TS_D(5), TS_D(6), TS_D(7), TS_D(8), TS_D(9), TS_D(10), ts_[tsi_ - 1] - ts_[0]); tsi_ = 0; } while (0)
+        printf("%s cta %d: %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld | total %lld\n", name, blockIdx.x, TS_D(1), TS_D(2), TS_D(3), \
+               TS_D(4), TS_D(5), TS_D(6), TS_D(7), TS_D(8), TS_D(9), TS_D(10), TS_D(11), TS_D(12), ts_[tsi_ - 1] - ts_[0]); tsi_ = 0; } while (0)
 #define WG_TS_DECL long long wts_[20]; int wtsi_ = 0
 #define WG_TS() do { if (wtsi_ < 20) wts_[wtsi_++] = clock64(); } while (0)
 #define WG_D(i) ((i) < wtsi_ ? wts_[i] - wts_[(i) - 1] : 0LL)
-#define WG_TS_PRINT(name, cond) do { if ((cond) && (blockIdx.x == 0 || blockIdx.x == 100)) \
+#define WG_TS_PRINT(name, cond) do { if (TC_TIMING > 1 && (cond) && (blockIdx.x == 0 || blockIdx.x == 100)) \
         printf("%s cta %d: %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld\n", name, blockIdx.x, WG_D(1), WG_D(2), WG_D(3), WG_D(4), \
                WG_D(5), WG_D(6), WG_D(7), WG_D(8), WG_D(9), WG_D(10), WG_D(11), WG_D(12), WG_D(13), WG_D(14)); } while (0)
 #else
@@ -721,7 +721,10 @@ __global__ void __launch_bounds__(NT_F, 1) tc_target_kernel(const TcArgs A) {
     const int warp = threadIdx.x >> 5;
     KT_BEGIN;
     const uint32_t tmem = tc_prologue(sbase);
-    if (A.chain) pdl_launch_dependents();      // K4a's CTAs may take an SM as soon as this kernel's CTA has left it
+    if (A.chain) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");   // the sample kernel (this launch may have started under its tail) is complete
+        pdl_launch_dependents();               // K4a's CTAs may take an SM as soon as this kernel's CTA has left it
+    }
     Ring ring;
     bool ok = true;
     if (warp >= EW) {
@@ -906,9 +909,14 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A, cons
             TS();
             ok = wait_gemm(sbase, ring, ok);
             TS();
+            uint32_t mask1[2], mask2[2];
+            epi_hidden<PASSES>(sbase, tmem, e, Fwd::BIAS1, valid ? A.h1 + sb * H + gr : nullptr, B, mask1);
+            a_ready(sbase);
+            TS();
             // TD target of this row from the two halves of K3 (reference :342-347), ties -> lowest index
-            // (in a chain the TMA lane has waited for K3's flag of this tile before it sent the first weight chunk of the
-            // item, so by the time the layer-1 GEMM has retired both halves are in L2; the loads bypass L1)
+            // Computed while the layer-2 GEMM runs (the epilogue warps have nothing else to do).  In a chain the TMA lane has waited
+            // for K3's flag of this tile before it sent the first weight chunk of the item, so both halves have long been in L2
+            // (the loads bypass L1).
             float yi = 0.f;
             if (valid) {
                 const float4 qo = ldg_plain(A.q_next + (sb + gr) * 4);
@@ -926,10 +934,7 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A, cons
                 yi = A.r_hat[sb + gr] + (A.gamma * (1.0f - A.done_b[sb + gr])) * tq;
                 if (e.part == 0) A.y[sb + gr] = yi;
             }
-            uint32_t mask1[2], mask2[2];
-            epi_hidden<PASSES>(sbase, tmem, e, Fwd::BIAS1, valid ? A.h1 + sb * H + gr : nullptr, B, mask1);
-            a_ready(sbase);
-            TS();
+            const int ai_pre = valid ? A.act_b[sb + gr] : 0;
             ok = wait_gemm(sbase, ring, ok);
             TS();
             float qv[4];
@@ -940,7 +945,7 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A, cons
             float gi = 0.f, term = 0.f;
             int ai = 0;
             if (valid) {
-                ai = A.act_b[sb + gr];
+                ai = ai_pre;
                 const float qa = ai == 0 ? qv[0] : ai == 1 ? qv[1] : ai == 2 ? qv[2] : qv[3];
                 const float err = qa - yi;
                 if (A.loss == DMDQN_LOSS_MSE) {
@@ -983,6 +988,7 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A, cons
                     for (int v = 0; v < 11; ++v) rowf[7 * BM + (threadIdx.x >> 5) * 11 + v] = red[v];
             }
             epi_sync();
+            TS();
             if (threadIdx.x < 11) {
                 const float* wp = rowf + 7 * BM + threadIdx.x;
                 const float tot = ((wp[0] + wp[11]) + wp[22]) + wp[33];
@@ -990,39 +996,67 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A, cons
                 if (threadIdx.x < 7) A.part_loss[pt * 8 + threadIdx.x] = tot;      // loss, q sum, q^2 sum, action histogram
                 else A.part_b3[pt * 4 + (threadIdx.x - 7)] = tot;
             }
-            {   // dW3[j][a] = sum_i h2[i][j] g_i [a_i = a] and db2[j] = sum_i dh2[i][j] over this tile's rows: thread = (column j,
-                // row half), rows read back in order from the h2 tile left in R by epi_head; lower half + upper half
-                const int j = threadIdx.x & (H - 1), rh = threadIdx.x >> 8;
-                const float4 w3 = lds4(sbase + Fwd::W3S + (uint32_t)j * 16);
-                float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, s2 = 0.f;
-                // h2 column j of the tile: K-major SW128, the 16-byte piece index is xor-ed with row % 8
-                const uint32_t hcol = sbase + Fwd::R + (uint32_t)(j >> 5) * ATOM + (uint32_t)((j & 3) << 2);
-                const uint32_t jq = (uint32_t)((j & 31) >> 2);
-                const uint32_t gsel = sbase + Fwd::ROWF + BM * 4;
-#pragma unroll 1
-                for (int i0 = rh * (BM / 2); i0 < (rh + 1) * (BM / 2); i0 += 8) {
+            {   // dW3[j][a] = sum_i h2[i][j] g_i [a_i = a] and db2[j] = sum_i dh2[i][j] over this tile's rows, read back from the h2
+                // tile epi_head left in R.  Thread = (four adjacent columns, 16 rows): warp w covers the 32 columns of block
+                // w % 8 and the row half w / 8, lane = (column quad, row group).  One 16-byte load brings four columns of a row
+                // (they are one swizzled piece of the K-major tile), one broadcast load the row's g * onehot(action): two
+                // shared-memory loads per four elements (the previous column-per-thread loop needed eight and was bound by
+                // them).  The four row groups of a warp are combined by a fixed xor butterfly, the two row halves through QP.
+                const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+                const int j0 = ((w & 7) * 8 + (l & 7)) * 4, rh = w >> 3, rg = l >> 3;
+                float4 w3c[4];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int i = i0 + u;
-                        float h;
-                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(h) : "r"(hcol + (uint32_t)i * 128u + ((jq ^ (uint32_t)u) << 4)));
-                        const float4 gs = lds4(gsel + (uint32_t)i * 16u);
-                        d0 = fmaf(h, gs.x, d0); d1 = fmaf(h, gs.y, d1); d2 = fmaf(h, gs.z, d2); d3 = fmaf(h, gs.w, d3);
-                        const float gw = fmaf(gs.w, w3.w, fmaf(gs.z, w3.z, fmaf(gs.y, w3.y, gs.x * w3.x)));   // = g * W3[j][a]: the other terms are exact zeros
-                        s2 += h > 0.f ? gw : 0.f;
+                for (int c = 0; c < 4; ++c) w3c[c] = lds4(sbase + Fwd::W3S + (uint32_t)(j0 + c) * 16);
+                float d[4][4], s2[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { d[c][0] = d[c][1] = d[c][2] = d[c][3] = 0.f; s2[c] = 0.f; }
+                const uint32_t hrow = sbase + Fwd::R + (uint32_t)(j0 >> 5) * ATOM;
+                const uint32_t piece = (uint32_t)((j0 & 31) >> 2);
+                const uint32_t gsel = sbase + Fwd::ROWF + BM * 4;
+                const int i_begin = rh * (BM / 2) + rg * 16;
+#pragma unroll 4
+                for (int u = 0; u < 16; ++u) {
+                    const int i = i_begin + u;
+                    const float4 h4 = lds4(hrow + (uint32_t)i * 128u + ((piece ^ (uint32_t)(i & 7)) << 4));
+                    const float4 gs = lds4(gsel + (uint32_t)i * 16u);
+                    const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        d[c][0] = fmaf(hv[c], gs.x, d[c][0]); d[c][1] = fmaf(hv[c], gs.y, d[c][1]);
+                        d[c][2] = fmaf(hv[c], gs.z, d[c][2]); d[c][3] = fmaf(hv[c], gs.w, d[c][3]);
+                        const float gw = fmaf(gs.w, w3c[c].w, fmaf(gs.z, w3c[c].z, fmaf(gs.y, w3c[c].y, gs.x * w3c[c].x)));   // = g * W3[j][a]: the other terms are exact zeros
+                        s2[c] += hv[c] > 0.f ? gw : 0.f;
                     }
                 }
+#pragma unroll
+                for (int o = 8; o <= 16; o <<= 1) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) d[c][a] += __shfl_xor_sync(0xffffffffu, d[c][a], o);
+                        s2[c] += __shfl_xor_sync(0xffffffffu, s2[c], o);
+                    }
+                }
+                TS();
                 float* up = sf + Fwd::QP / 4;                     // [256][8] floats: partials of the upper row half
-                if (rh == 1) {
-                    reinterpret_cast<float4*>(up)[j * 2] = make_float4(d0, d1, d2, d3);
-                    up[j * 8 + 4] = s2;
+                if (rh == 1 && rg == 0) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        reinterpret_cast<float4*>(up)[(j0 + c) * 2] = make_float4(d[c][0], d[c][1], d[c][2], d[c][3]);
+                        up[(j0 + c) * 8 + 4] = s2[c];
+                    }
                 }
                 epi_sync();
-                if (rh == 0) {
-                    const float4 u4 = reinterpret_cast<const float4*>(up)[j * 2];
+                if (rh == 0 && rg == 0) {
                     const size_t pt = (size_t)g * A.tiles + rt;
-                    reinterpret_cast<float4*>(A.part_w3 + pt * H * 4)[j] = make_float4(d0 + u4.x, d1 + u4.y, d2 + u4.z, d3 + u4.w);
-                    A.part_b2[pt * H + j] = s2 + up[j * 8 + 4];
+                    float sb2[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float4 u4 = reinterpret_cast<const float4*>(up)[(j0 + c) * 2];
+                        reinterpret_cast<float4*>(A.part_w3 + pt * H * 4)[j0 + c] = make_float4(d[c][0] + u4.x, d[c][1] + u4.y, d[c][2] + u4.z, d[c][3] + u4.w);
+                        sb2[c] = s2[c] + up[(j0 + c) * 8 + 4];
+                    }
+                    *reinterpret_cast<float4*>(A.part_b2 + pt * H + j0) = make_float4(sb2[0], sb2[1], sb2[2], sb2[3]);
                 }
             }
             epi_sync();          // R is rewritten with dh2 below
@@ -1074,7 +1108,7 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A, cons
                 }
             }
             TS();
-            TS_PRINT("K4a store L1 epi1 L2 epi2 loss+dW3 dh2 bwdGEMM dh1store");
+            TS_PRINT("K4a store L1 epi1 L2 epi2 loss dW3loop dW3out dh2 bwdGEMM dh1store");
             q_last = q;
             q = qn;
         }
@@ -1483,6 +1517,7 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A, co
         WG_TS_DECL;
 #ifdef TC_TIMING
         const long long wg_t0 = clock64();
+        unsigned long long wg_g0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(wg_g0));
 #endif
         for (;;) {
             const int q = wg_pop(bars, nq, ok);
@@ -1620,7 +1655,8 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A, co
         WG_TS();
         WG_TS_PRINT("K4b epilogue (wait, adam)*", et == 0);
 #ifdef TC_TIMING
-        if (et == 0) printf("K4bsum cta %d sm %d items %d cycles %lld\n", blockIdx.x, (int)smid_(), n, clock64() - wg_t0);
+        if (et == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+            printf("K4bsum cta %d sm %d items %d cycles %lld chain %d t0 %llu t1 %llu\n", blockIdx.x, (int)smid_(), n, clock64() - wg_t0, A.chain, wg_g0, gt); }
 #endif
         if (!ok && lane == 0) atomicExch(A.error, 6);
     }
@@ -1692,8 +1728,11 @@ int launch_tc(const TcArgs& A, int stages, cudaStream_t s) {
     cfg.stream = s;
     cfg.attrs = pdl;
     if (stages & DMDQN_STAGE_TARGET) {
-        tc_target_kernel<PASSES><<<2 * items < n_sm ? 2 * items : n_sm, NT_F, smem_f, s>>>(A);
-        DMDQN_CUDA(cudaGetLastError());
+        cfg.gridDim = dim3(2 * items < n_sm ? 2 * items : n_sm);
+        cfg.blockDim = dim3(NT_F);
+        cfg.dynamicSmemBytes = smem_f;
+        cfg.numAttrs = A.chain ? 1 : 0;         // in a chain: launched under the tail of the sample kernel (griddepcontrol.wait inside)
+        DMDQN_CUDA(cudaLaunchKernelEx(&cfg, tc_target_kernel<PASSES>, A));
     }
     if (stages & DMDQN_STAGE_ONLINE) {
         CUtensorMap tmap;

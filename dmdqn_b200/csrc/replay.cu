@@ -79,6 +79,9 @@ sample_kernel(dmdqn_dims d, dmdqn_hparams hp, dmdqn_replay rp, int32_t* __restri
     const bool shared_net = d.n_nets == 1 && d.n_agents > 1;
     // dataflow flags of the tcgen05 learn kernels (learn_tc.cu): this launch is ordered after every kernel of the previous
     // step, so it is the one place where they can be reset without a race
+    // K3 of the same call is a programmatic dependent launch: its CTAs may set up (barriers, TMEM) while this grid runs; they
+    // read nothing of this kernel's before their griddepcontrol.wait, which returns when this grid has completed
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid < 4 && g == 0) sync[tid] = 0;
     if (tid == 4) sync[4 + g] = 0;
     if (tid >= 32 && tid < 32 + tiles) sync[4 + d.n_nets + g * tiles + (tid - 32)] = 0;

@@ -47,6 +47,85 @@ __global__ void __launch_bounds__(256, 1) tile_rmw(float* th, float* am, float* 
         }
     }
 }
+// 16 warps: row quarter w & 3, column quarter w >> 2 (64 floats); LPR lanes per row segment, NB row groups per batch
+template <int LPR, int NB>
+__global__ void __launch_bounds__(512, 1) tile_rmw16(float* th, float* am, float* av, int n_tiles) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rq = warp & 3, quarter = warp >> 2;
+    constexpr int RPI = 32 / LPR;
+    const int rsub = lane / LPR, c4 = (lane % LPR) * 4;
+    constexpr int COLS = LPR * 4;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const size_t base = (size_t)t * 128 * 256 + (size_t)(rq * 32) * 256 + quarter * 64;
+        for (int cb = 0; cb < 64 / COLS; ++cb) {
+            for (int r0 = 0; r0 < 32; r0 += RPI * NB) {
+                float4 t4[NB], m4[NB], v4[NB];
+                size_t off[NB];
+#pragma unroll
+                for (int u = 0; u < NB; ++u) {
+                    off[u] = base + (size_t)(r0 + u * RPI + rsub) * 256 + cb * COLS + c4;
+                    t4[u] = ldcg(th + off[u]); m4[u] = ldcg(am + off[u]); v4[u] = ldcg(av + off[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < NB; ++u) {
+                    upd(t4[u], m4[u], v4[u]);
+                    *reinterpret_cast<float4*>(th + off[u]) = t4[u];
+                    *reinterpret_cast<float4*>(am + off[u]) = m4[u];
+                    *reinterpret_cast<float4*>(av + off[u]) = v4[u];
+                }
+            }
+        }
+    }
+}
+// The same walk with K4b's real per-element work: gradient from a per-warp shared-memory tile (written as a "TMEM row" per
+// lane, read back as 16-byte row pieces, like the epilogue's transpose) and the real Adam arithmetic (MUFU sqrt + divide).
+__device__ __forceinline__ void adam_real(float g, float& th, float& m, float& v) {
+    m = m + (g - m) * 0.1f;
+    v = v + (g * g - v) * 0.001f;
+    float sq;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(v));
+    th = th - __fdividef(m * 5e-4f, sq + 1e-7f);
+}
+template <int WARPS, int LPR, int NB, int CW>   // CW = columns of a block (32 or 16); a warp owns 256 / (WARPS / 4) columns
+__global__ void __launch_bounds__(WARPS * 32, 1) tile_real(float* th, float* am, float* av, int n_tiles) {
+    constexpr int TLD = CW + 4;
+    extern __shared__ __align__(16) float tiles_dyn[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rq = warp & 3, part = warp >> 2;
+    constexpr int WCOLS = 256 / (WARPS / 4);
+    constexpr int RPI = 32 / LPR;
+    static_assert(LPR * 4 == CW, "a row segment is one block wide");
+    const int rsub = lane / LPR, c4 = (lane % LPR) * 4;
+    float* tile = tiles_dyn + warp * 32 * TLD;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const size_t base = (size_t)t * 128 * 256 + (size_t)(rq * 32) * 256 + part * WCOLS;
+        for (int cb = 0; cb < WCOLS / CW; ++cb) {
+#pragma unroll
+            for (int j = 0; j < CW; j += 4)      // "accumulator row" of this lane -> tile
+                *reinterpret_cast<float4*>(tile + lane * TLD + j) = make_float4(1e-3f * j, 2e-3f, 3e-3f, 1e-3f * lane);
+            __syncwarp();
+            for (int r0 = 0; r0 < 32; r0 += RPI * NB) {
+                float4 t4[NB], m4[NB], v4[NB];
+                size_t off[NB];
+#pragma unroll
+                for (int u = 0; u < NB; ++u) {
+                    off[u] = base + (size_t)(r0 + u * RPI + rsub) * 256 + cb * CW + c4;
+                    t4[u] = ldcg(th + off[u]); m4[u] = ldcg(am + off[u]); v4[u] = ldcg(av + off[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < NB; ++u) {
+                    const float4 g = *reinterpret_cast<const float4*>(tile + (r0 + u * RPI + rsub) * TLD + c4);
+                    adam_real(g.x, t4[u].x, m4[u].x, v4[u].x); adam_real(g.y, t4[u].y, m4[u].y, v4[u].y);
+                    adam_real(g.z, t4[u].z, m4[u].z, v4[u].z); adam_real(g.w, t4[u].w, m4[u].w, v4[u].w);
+                    *reinterpret_cast<float4*>(th + off[u]) = t4[u];
+                    *reinterpret_cast<float4*>(am + off[u]) = m4[u];
+                    *reinterpret_cast<float4*>(av + off[u]) = v4[u];
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
 __global__ void stream_rmw(float* th, float* am, float* av, size_t n4) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         float4 t = ldcg(th + 4 * i), m = ldcg(am + 4 * i), v = ldcg(av + 4 * i);
@@ -78,6 +157,15 @@ int main() {
     rep("tiles, 2 rows x 256 B per instr, batch 8", timeit([&] { tile_rmw<16, 8><<<148, 256>>>(th, am, av, n_tiles); }));
     rep("tiles, 1 row x 512 B per instr, batch 8", timeit([&] { tile_rmw<32, 8><<<148, 256>>>(th, am, av, n_tiles); }));
     rep("tiles, 1 row x 512 B per instr, batch 16", timeit([&] { tile_rmw<32, 16><<<148, 256>>>(th, am, av, n_tiles); }));
+    rep("16 warps, 8 rows x 64 B per instr, batch 4", timeit([&] { tile_rmw16<4, 4><<<148, 512>>>(th, am, av, n_tiles); }));
+    rep("16 warps, 4 rows x 128 B per instr, batch 4", timeit([&] { tile_rmw16<8, 4><<<148, 512>>>(th, am, av, n_tiles); }));
+    rep("16 warps, 4 rows x 128 B per instr, batch 8", timeit([&] { tile_rmw16<8, 8><<<148, 512>>>(th, am, av, n_tiles); }));
+    rep("16 warps, 2 rows x 256 B per instr, batch 4", timeit([&] { tile_rmw16<16, 4><<<148, 512>>>(th, am, av, n_tiles); }));
+    rep("REAL math+tile,  8 warps, 4 x 128 B, batch 8", timeit([&] { cudaFuncSetAttribute(tile_real<8, 8, 8, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 36864); tile_real<8, 8, 8, 32><<<148, 256, 36864>>>(th, am, av, n_tiles); }));
+    rep("REAL math+tile, 16 warps, 4 x 128 B, batch 4", timeit([&] { cudaFuncSetAttribute(tile_real<16, 8, 4, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 73728); tile_real<16, 8, 4, 32><<<148, 512, 73728>>>(th, am, av, n_tiles); }));
+    rep("REAL math+tile, 16 warps, 4 x 128 B, batch 8", timeit([&] { cudaFuncSetAttribute(tile_real<16, 8, 8, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 73728); tile_real<16, 8, 8, 32><<<148, 512, 73728>>>(th, am, av, n_tiles); }));
+    rep("REAL math+tile, 16 warps, 8 x 64 B, batch 4", timeit([&] { cudaFuncSetAttribute(tile_real<16, 4, 4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 40960); tile_real<16, 4, 4, 16><<<148, 512, 40960>>>(th, am, av, n_tiles); }));
+    rep("REAL math+tile, 12 warps, 4 x 128 B, batch 8", timeit([&] { cudaFuncSetAttribute(tile_real<12, 8, 8, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 55296); tile_real<12, 8, 8, 32><<<148, 384, 55296>>>(th, am, av, n_tiles); }));
     CK(cudaDeviceSynchronize());
     return 0;
 }

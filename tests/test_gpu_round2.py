@@ -696,3 +696,55 @@ def test_tcgen05_forward_kernels_are_bit_stable_run_to_run(n, batch, cap, reps):
         for k, v in again.items():
             same = torch.equal(v, first[k])
             assert same, f"repetition {rep}: {k} differs from the first run in networks {torch.nonzero((v != first[k]).flatten(1).any(1)).flatten().tolist()[:8]}"
+
+
+@pytest.mark.parametrize("n,batch,cap", [(300, 128, 160), (40, 64, 80), (20, 256, 300)])
+def test_chained_learn_equals_stage_by_stage_learn(n, batch, cap):
+    """dmdqn_learn issues sample + K3 + K4a + K4b as ONE chain: K3 starts under the sample kernel's tail, K4a / K4b are
+    programmatic dependent launches that take over SMs while the previous kernel is still running and order themselves behind
+    per-tile / per-network release-acquire flags, and K4b draws its items from a global work counter.  None of that may change
+    a bit: the same steps issued one stage per call (plain stream order, no flags consulted) must give identical parameters,
+    Adam moments, targets and metrics -- with several items per CTA (300 networks on 148 SMs), with fewer items than SMs, and
+    with a different subset of networks masked out of every step."""
+    import ctypes as C
+    from dmdqn_b200 import _native as N
+    cfg = {"nn_layers": [256, 256], "replay_buffer_size": cap, "batch_size": batch, "precision": "tf32x3",
+           "target_update_frequency": 3}
+    a, b = _group(n, cfg, seed=21), _group(n, cfg, seed=21)
+    for g in (a, b):
+        _fill(g, None, np.random.default_rng(5), cap + 2)
+    rng = np.random.default_rng(17)
+    for it in range(6):
+        w = torch.as_tensor(rng.integers(0, 2**32, (n, batch), dtype=np.uint64).astype(np.uint32).view(np.int32)).to(a.device)
+        mask = torch.as_tensor((rng.random(n) < (0.8 if it % 2 else 1.0)).astype(np.uint8)).to(a.device)
+        ma = a.learn(w, mask=mask).clone()
+        for stage in (1, 2, 4, 8):
+            N.check(b.lib.dmdqn_learn_stages(C.byref(b.dims), C.byref(b.hp), C.byref(b.replay), C.byref(b.nets), w.data_ptr(),
+                                             mask.data_ptr(), b.metrics.data_ptr(), b.workspace.data_ptr(), b.workspace.numel(),
+                                             stage, torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        assert int(a.debug_views()["tc_error"][0]) == 0 and int(b.debug_views()["tc_error"][0]) == 0
+        assert torch.equal(ma, b.metrics), f"step {it}: metrics differ"
+        for name in ("theta", "theta_tgt", "adam_m", "adam_v"):
+            x, y = getattr(a, name), getattr(b, name)
+            assert torch.equal(x, y), f"step {it}: {name} differs in networks {torch.nonzero((x != y).flatten(1).any(1)).flatten().tolist()[:8]}"
+        assert torch.equal(a.learn_step, b.learn_step)
+    # the chain must also be repeatable, and must neither hang nor change a bit when OTHER work occupies part of the GPU
+    # (a consumer CTA only exists once every producer CTA is resident or done, whatever else is running): the same six steps
+    # again on a fresh group, with matrix products streaming on a second stream
+    c = _group(n, cfg, seed=21)
+    _fill(c, None, np.random.default_rng(5), cap + 2)
+    rng = np.random.default_rng(17)
+    side = torch.cuda.Stream()
+    x = torch.randn(4096, 4096, device=a.device)
+    for it in range(6):
+        w = torch.as_tensor(rng.integers(0, 2**32, (n, batch), dtype=np.uint64).astype(np.uint32).view(np.int32)).to(a.device)
+        mask = torch.as_tensor((rng.random(n) < (0.8 if it % 2 else 1.0)).astype(np.uint8)).to(a.device)
+        with torch.cuda.stream(side):
+            for _ in range(4):
+                x = (x @ x).clamp_(-1.0, 1.0)
+        c.learn(w, mask=mask)
+    torch.cuda.synchronize()
+    assert int(c.debug_views()["tc_error"][0]) == 0
+    for name in ("theta", "theta_tgt", "adam_m", "adam_v"):
+        assert torch.equal(getattr(a, name), getattr(c, name)), f"second run: {name} differs"

@@ -221,7 +221,8 @@ def test_act_q_values_and_greedy_actions(h, n):
     close(q.cpu().numpy(), q_ref, what="Q(s)")
     top2 = np.sort(q_ref, axis=1)[:, -2:]
     gap_ok = (top2[:, 1] - top2[:, 0]) > 1e-4 * np.abs(q_ref).max()
-    assert gap_ok.mean() > 0.95                                        # near-ties are the rare exception
+    print(f"greedy-action parity H={h}: {int((~gap_ok).sum())} of {n} rows excluded as near-ties (top-2 gap <= 1e-4 max|Q|)")
+    assert (~gap_ok).sum() <= max(1, n // 50)                          # near-ties are the rare exception
     assert np.array_equal(actions.cpu().numpy()[gap_ok], q_ref.argmax(1)[gap_ok])
     # epsilon mask with supplied draws: bit-exact decisions and random actions
     eps = rng.choice([0.0, 0.3, 1.0], n)
@@ -289,6 +290,8 @@ def _learn_case(h, n, batch, cap, steps, loss="mse", tau=None, freq=3, double_dq
         # a near-tie in argmax_a online(s') may legitimately flip: exclude those rows (counted)
         qn = np.sort(out["q_next"], axis=2)
         tie = (qn[..., -1] - qn[..., -2]) < rtol * np.abs(out["q_next"]).max()
+        if tie.any():
+            print(f"step {step}: {int(tie.sum())} of {tie.size} TD-target rows excluded as argmax near-ties")
         assert tie.mean() < 0.01 * (rtol / RTOL)
         close(dbg["q_next"], out["q_next"], rtol=rtol, what=f"step {step} online Q(s')")
         close(dbg["tq_all"], out["tq_all"], rtol=rtol, what=f"step {step} target Q(s')")

@@ -222,13 +222,18 @@ int dmdqn_gather(const dmdqn_dims* dims, const dmdqn_replay* replay, const void*
  * Replaces DQNAgent.learn / replay (src/agents/dqn_agent.py:328-380,428-434):
  * sample, target-net forward + online argmax + TD target, online forward, MSE/Huber,
  * backward, Adam, hard/Polyak target sync.
- *   metrics_out device float[n_nets][DMDQN_METRICS_STRIDE]. */
+ *   metrics_out device float[n_nets][DMDQN_METRICS_STRIDE].
+ * On the tcgen05 path the four kernels of one call form a dataflow chain (programmatic dependent launches:
+ * K3 starts under the sample kernel's tail, K4a / K4b take over SMs while the previous kernel is still running
+ * and wait on per-tile / per-network flags in the workspace, which the sample kernel resets).  Results are
+ * bit-identical to the stage-by-stage form below; the workspace must not be shared by two calls in flight. */
 int dmdqn_learn(const dmdqn_dims* dims, const dmdqn_hparams* hp, const dmdqn_replay* replay,
                 const dmdqn_nets* nets, const void* draws, const uint8_t* learn_mask,
                 float* metrics_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* The same step, one stage per call, so a caller can bracket each kernel with CUDA events
- * (bench.py roofline): stages is a bit mask of DMDQN_STAGE_*; all four in order == dmdqn_learn. */
+ * (bench.py roofline): stages is a bit mask of DMDQN_STAGE_*; all four in order == dmdqn_learn (same bits;
+ * kernels of different calls are ordered by the stream alone, only a call with all four stages is chained). */
 #define DMDQN_STAGE_SAMPLE 1   /* K1b */
 #define DMDQN_STAGE_TARGET 2   /* K3  */
 #define DMDQN_STAGE_ONLINE 4   /* K4a */

@@ -92,23 +92,28 @@ sample_kernel(dmdqn_dims d, dmdqn_hparams hp, dmdqn_replay rp, int32_t* __restri
     const int size0 = (int)(nw0 < d.capacity ? nw0 : d.capacity);
     const long long pop = shared_net ? (long long)size0 * d.n_agents : size0;
     const bool on = (learn_mask == nullptr || learn_mask[g]) && pop >= B;  // dqn_agent.py:61-62
+    int t_step = 0;
     if (tid == 0) {
         active[g] = on ? 1 : 0;
         int t = learn_step[g];
         if (on && advance) learn_step[g] = ++t;    // dqn_agent.py:359
         step_t[g] = t;
-        if (on) {
-            // Adam scalars of this step, once per network instead of once per thread of K4b:
-            // alpha_t = lr * sqrt(1 - b2^t) / (1 - b1^t) in float64, then rounded (oracle/dqn.py adam_scalars)
-            const double bc1 = 1.0 - pow(hp.beta1, (double)t), bc2 = 1.0 - pow(hp.beta2, (double)t);
-            const int freq = hp.target_update_frequency > 0 ? hp.target_update_frequency : 1;
-            const int sync = hp.tau >= 0.0 ? 2 : (t % freq == 0 ? 1 : 0);          // counter already incremented (:359,376)
-            adam_sc[g] = make_float4((float)(hp.learning_rate * sqrt(bc2) / bc1),
-                                     (float)(hp.adam_form == DMDQN_ADAM_KERAS ? hp.adam_eps : hp.adam_eps * sqrt(bc2)),
-                                     __int_as_float(sync), 0.f);
-        }
+        t_step = t;
     }
     if (!on) return;
+    // Adam scalars of this step, once per network instead of once per thread of K4b: alpha_t = lr * sqrt(1 - b2^t) / (1 - b1^t)
+    // in float64, then rounded (oracle/dqn.py adam_scalars).  Two double-precision pow() calls (~2 us) by ONE thread: thread 0
+    // runs them while the other warps are still in their index scan (warp 0's is the shortest), not in front of a barrier
+    // every thread waits at.
+    auto adam_scalars = [&]() {
+        const int t = t_step;
+        const double bc1 = 1.0 - pow(hp.beta1, (double)t), bc2 = 1.0 - pow(hp.beta2, (double)t);
+        const int freq = hp.target_update_frequency > 0 ? hp.target_update_frequency : 1;
+        const int sync_mode = hp.tau >= 0.0 ? 2 : (t % freq == 0 ? 1 : 0);          // counter already incremented (:359,376)
+        adam_sc[g] = make_float4((float)(hp.learning_rate * sqrt(bc2) / bc1),
+                                 (float)(hp.adam_form == DMDQN_ADAM_KERAS ? hp.adam_eps : hp.adam_eps * sqrt(bc2)),
+                                 __int_as_float(sync_mode), 0.f);
+    };
 
     if (hp.sample_mode == DMDQN_SAMPLE_FISHER_YATES) {
         const int n = (int)pop;
@@ -129,6 +134,7 @@ sample_kernel(dmdqn_dims d, dmdqn_hparams hp, dmdqn_replay rp, int32_t* __restri
             }
             if (i < B) { pt[i] = ptk; words[i] = pj; }
         }
+        if (tid == 0) adam_scalars();
         __syncthreads();
         for (int i = tid; i < B; i += kSampleThreads) {    // words[i] is read and rewritten by its own thread only
             int k = words[i];
@@ -141,11 +147,13 @@ sample_kernel(dmdqn_dims d, dmdqn_hparams hp, dmdqn_replay rp, int32_t* __restri
         }
     } else if (hp.sample_mode == DMDQN_SAMPLE_REPLACEMENT) {
         for (int i = tid; i < B; i += kSampleThreads) words[i] = (int)__umulhi(draws[(size_t)g * B + i], (unsigned)pop);
+        if (tid == 0) adam_scalars();
     } else {                                            // explicit logical indices, clamped
         for (int i = tid; i < B; i += kSampleThreads) {
             const int v = (int)draws[(size_t)g * B + i];
             words[i] = v < 0 ? 0 : (v >= pop ? (int)pop - 1 : v);
         }
+        if (tid == 0) adam_scalars();
     }
     __syncthreads();
 

@@ -748,3 +748,41 @@ def test_chained_learn_equals_stage_by_stage_learn(n, batch, cap):
     assert int(c.debug_views()["tc_error"][0]) == 0
     for name in ("theta", "theta_tgt", "adam_m", "adam_v"):
         assert torch.equal(getattr(a, name), getattr(c, name)), f"second run: {name} differs"
+
+
+def test_fractional_observations_meet_the_fp32_bar():
+    """Every other learn test feeds integer-valued observations (queue counts, one-hots, -1 padding), whose tf32 split has an
+    empty lo half: the A_lo * B_hi term of layer 1 is then all zeros and a kernel that dropped it would still pass them.  Half
+    of the networks here hold integers + a fraction that needs the lo half; both halves must meet the fp32 bar against the
+    FFMA kernels (a missing lo term costs ~1e-4 relative).  (Skipping that MMA for all-integer tiles was measured: 1.6 us of
+    500 -- layer 1 is bound by the weight feed, not by the tensor pipe -- and not kept.)"""
+    import ctypes as C
+    from dmdqn_b200 import _native as N
+    n, batch, cap = 64, 128, 160
+    cfg = {"nn_layers": [256, 256], "replay_buffer_size": cap, "batch_size": batch}
+    ref, tc = _group(n, dict(cfg, precision="fp32"), seed=4), _group(n, dict(cfg, precision="tf32x3"), seed=4)
+    rng = np.random.default_rng(23)
+    frac = np.zeros((n, 1), np.float32); frac[n // 2:] = 1.0
+    for _ in range(cap + 3):
+        s = rng.integers(-1, 20, (n, 89)).astype(np.float32) + frac * rng.random((n, 89)).astype(np.float32)
+        s2 = rng.integers(-1, 20, (n, 89)).astype(np.float32) + frac * rng.random((n, 89)).astype(np.float32)
+        a = rng.integers(0, 4, n).astype(np.int32)
+        r = -0.3 * rng.integers(0, 200, n) - 0.7 * rng.integers(0, 5000, n)
+        dn = rng.random(n) < 0.1
+        for g in (ref, tc):
+            g.push(s, a, r, s2, dn)
+    d = tc.draw_words((n, batch))
+
+    def stages(grp, mask):
+        N.check(grp.lib.dmdqn_learn_stages(C.byref(grp.dims), C.byref(grp.hp), C.byref(grp.replay), C.byref(grp.nets), d.data_ptr(), None,
+                                           grp.metrics.data_ptr(), grp.workspace.data_ptr(), grp.workspace.numel(), mask,
+                                           torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        v = grp.debug_views()
+        assert int(v["tc_error"][0]) == 0
+        return {k: v[k].clone().cpu().numpy() for k in ("q_next", "tq_all", "q_all", "y")}
+    stages(ref, 1); stages(tc, 1)
+    want, got = stages(ref, 2 | 4), stages(tc, 2 | 4)
+    for half, sl in (("integer observations", slice(0, n // 2)), ("fractional observations", slice(n // 2, n))):
+        for k in ("q_next", "tq_all", "q_all"):
+            close(got[k][sl], want[k][sl], rtol=RTOL, what=f"{half}: tcgen05 vs FFMA {k}")

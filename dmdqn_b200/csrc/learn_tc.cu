@@ -116,6 +116,10 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
                  "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, int c4, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst),
+                 "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar) : "memory");
+}
 template <int N> __device__ __forceinline__ void regs_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void regs_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }    // the 16 gather / epilogue warps of K3 / K4a
@@ -319,6 +323,26 @@ __device__ __forceinline__ float4 lds4(uint32_t a) {
 // so every chunk is also requested into L2 PF chunks ahead of its copy (of this matrix, then of `next`: the matrix
 // the ring streams after this one), which turns the copies into L2 hits.
 constexpr int PF = 6;
+// x.W IN PLACE (the ring both directions share): W seen through a rank-5 tensor map {32 columns, 4 k-rows, 8 column blocks,
+// K / 4 k-groups, network} with box {32, 4, 8, 2, 1} and the 32-byte-atom 128-byte swizzle -- one box is a chunk of 8 k-rows x 256
+// columns landing as [k / 4][column / 32][k % 4][128 B] with the 32-byte piece xor-ed by k % 4: the UMMA MN-major
+// "128B_BASE32B" layout itself.  The converters then split it where it lies (hi stays, lo 8 KB further), exactly as they do
+// for d.W^T: no raw slots, five stages deep instead of three, one barrier hop less per chunk.
+__device__ __forceinline__ bool tma_fwd_map(uint32_t sbase, const CUtensorMap* tm, int g, const float* __restrict__ W, int K, Ring& r,
+                                            bool ok, const float* __restrict__ next) {
+    const uint32_t bars = sbase + Fwd::BARS;
+    const int nchunks = K >> 3;
+    for (int c = 0; c < nchunks; ++c) {
+        const uint32_t s = r.b % NSB, u = r.b / NSB;
+        if (c + PF < nchunks) l2_prefetch(W + (size_t)(c + PF) * 8 * H, RAW_F);
+        else if (next) l2_prefetch(next + (size_t)(c + PF - nchunks) * 8 * H, RAW_F);
+        if (u && ok) ok = mbar_wait(bars + Bar::EMPTY_B + 8 * s, (u - 1) & 1);
+        mbar_expect_tx(bars + Bar::TMA_B + 8 * s, RAW_B);
+        tma_load_5d(sbase + Fwd::WB + s * STG_B, tm, 0, 0, 0, 2 * c, g, bars + Bar::TMA_B + 8 * s);
+        ++r.b;
+    }
+    return ok;
+}
 __device__ __forceinline__ bool tma_fwd(uint32_t sbase, const float* __restrict__ W, int K, Ring& r, bool ok,
                                         const float* __restrict__ next) {
     const uint32_t bars = sbase + Fwd::BARS;
@@ -413,14 +437,14 @@ __device__ __forceinline__ bool conv_fwd(uint32_t sbase, int K, int grp, int t, 
     return ok;
 }
 template <int PASSES>
-__device__ __forceinline__ bool conv_bwd(uint32_t sbase, int grp, int t, Ring& r, bool ok) {
+__device__ __forceinline__ bool conv_bwd(uint32_t sbase, int grp, int t, Ring& r, bool ok, int nchunks = H / 8) {
     // In place: the chunk landed in the hi half of its stage already swizzled (TMA SWIZZLE_32B == UMMA K-major SW32), so a
     // thread reads a 16-byte piece, leaves its hi part at the same address and puts the lo part 8 KB further.  Chunk c of the
     // ring goes to group c % 3; stages (5) and groups (3) do not line up, hence the same guard as in conv_fwd: wait until the
     // stage's previous chunk has been converted (by whichever group) before trusting the parity of its TMA barrier.
     const uint32_t bars = sbase + Fwd::BARS;
     constexpr int NGRP = CONV_WARPS / CONV_GROUP_WARPS;
-    for (int c = 0; c < H / 8; ++c) {
+    for (int c = 0; c < nchunks; ++c) {
         const uint32_t b = r.b + (uint32_t)c;
         if ((int)(b % NGRP) != grp) continue;
         const uint32_t s = b % NSB, u = b / NSB;
@@ -444,7 +468,7 @@ __device__ __forceinline__ bool conv_bwd(uint32_t sbase, int grp, int t, Ring& r
         __syncwarp();
         if ((threadIdx.x & 31) == 0) mbar_arrive(bars + Bar::CONV_B + 8 * s);
     }
-    r.b += (uint32_t)(H / 8);
+    r.b += (uint32_t)nchunks;
     return ok;
 }
 
@@ -453,16 +477,23 @@ __device__ __forceinline__ bool conv_bwd(uint32_t sbase, int grp, int t, Ring& r
 //   A hi: shared memory, K-major SW128 at a_hi; A lo: shared memory (a_lo_smem != 0) or TMEM columns.
 //   BT = false: x.W, stages MN-major;  BT = true: d.W^T, stages K-major SW32.  One k-step (8 k) per chunk either way.
 // ------------------------------------------------------------------------------------------
-template <int PASSES, bool BT>
+#ifdef FWD_RAW_RING
+constexpr bool kOneRing = false;
+#else
+constexpr bool kOneRing = true;     // x.W chunks travel through the in-place ring too (tma_fwd_map)
+#endif
+template <int PASSES, bool BT_>
 __device__ __forceinline__ bool mma_gemm(uint32_t sbase, uint32_t tmem, uint32_t a_hi, uint32_t a_lo_smem, uint32_t a_lo_tmem,
                                          int K, Ring& r, bool ok) {
     const uint32_t bars = sbase + Fwd::BARS;
     constexpr int KCX = 8;
-    constexpr uint32_t idesc = make_idesc(false, !BT);
+    constexpr uint32_t idesc = make_idesc(false, !BT_);
+    constexpr bool BT = BT_ || kOneRing;            // which ring (barriers, stage geometry, counter); BT_ alone picks the layout
     // Descriptors differ only in their 14-bit start-address field: build each once, then add (bytes >> 4).
     const uint64_t a_hi0 = make_desc(a_hi, 16, 1024, 2);
     const uint64_t a_lo0 = make_desc(a_lo_smem, 16, 1024, 2);
-    const uint64_t b0 = BT ? make_desc(sbase + Fwd::WB, 16, 256, 6) : make_desc(sbase + Fwd::STG, 512, 4096, 1);
+    const uint64_t b0 = BT_ ? make_desc(sbase + Fwd::WB, 16, 256, 6)
+                            : make_desc(sbase + (kOneRing ? Fwd::WB : Fwd::STG), 512, 4096, 1);
     if (ok) ok = mbar_wait(bars + Bar::AREADY, r.gemms & 1);      // all 16 epilogue warps have published the A operand
     tc_fence_after();
     const int nchunks = K / KCX;
@@ -713,7 +744,10 @@ __device__ __forceinline__ int k3_next(const TcArgs& A, int q, int n_items) {
 }
 
 template <int PASSES>
-__global__ void __launch_bounds__(NT_F, 1) tc_target_kernel(const TcArgs A) {
+__global__ void __launch_bounds__(NT_F, 1) tc_target_kernel(const TcArgs A, const __grid_constant__ CUtensorMap tm_w1,
+                                                            const __grid_constant__ CUtensorMap tm_w2,
+                                                            const __grid_constant__ CUtensorMap tm_w1t,
+                                                            const __grid_constant__ CUtensorMap tm_w2t) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int B = A.d.batch, Dp = A.d.obs_stride;
@@ -751,8 +785,13 @@ __global__ void __launch_bounds__(NT_F, 1) tc_target_kernel(const TcArgs A) {
                 const float* P = ((q & 1) ? A.nets.theta_tgt : A.nets.theta) + (size_t)g * A.L.stride;
                 const int qn = k3_next(A, q + gridDim.x, n_items);
                 const float* Pn = qn < n_items ? ((qn & 1) ? A.nets.theta_tgt : A.nets.theta) + (size_t)((qn >> 1) / A.tiles) * A.L.stride + A.L.w1 : nullptr;
-                ok = tma_fwd(sbase, P + A.L.w1, Dp, ring, ok, P + A.L.w2);
-                ok = tma_fwd(sbase, P + A.L.w2, H, ring, ok, Pn);
+                if (kOneRing) {
+                    ok = tma_fwd_map(sbase, (q & 1) ? &tm_w1t : &tm_w1, g, P + A.L.w1, Dp, ring, ok, P + A.L.w2);
+                    ok = tma_fwd_map(sbase, (q & 1) ? &tm_w2t : &tm_w2, g, P + A.L.w2, H, ring, ok, Pn);
+                } else {
+                    ok = tma_fwd(sbase, P + A.L.w1, Dp, ring, ok, P + A.L.w2);
+                    ok = tma_fwd(sbase, P + A.L.w2, H, ring, ok, Pn);
+                }
                 q = qn;
             }
             if (!ok) atomicExch(A.error, 23);
@@ -761,8 +800,13 @@ __global__ void __launch_bounds__(NT_F, 1) tc_target_kernel(const TcArgs A) {
       } else if (warp < W_CONV + CONV_WARPS) {   // converters (the last two warps only fill the warpgroup)
         const int tc = threadIdx.x - W_CONV * 32, cg = (warp - W_CONV) / CONV_GROUP_WARPS, t = tc % (CONV_GROUP_WARPS * 32);
         for (int q = k3_next(A, blockIdx.x, n_items); q < n_items; q = k3_next(A, q + gridDim.x, n_items)) {
-            ok = conv_fwd<PASSES>(sbase, Dp, cg, t, ring, ok);
-            ok = conv_fwd<PASSES>(sbase, H, cg, t, ring, ok);
+            if (kOneRing) {
+                ok = conv_bwd<PASSES>(sbase, cg, t, ring, ok, Dp / 8);
+                ok = conv_bwd<PASSES>(sbase, cg, t, ring, ok, H / 8);
+            } else {
+                ok = conv_fwd<PASSES>(sbase, Dp, cg, t, ring, ok);
+                ok = conv_fwd<PASSES>(sbase, H, cg, t, ring, ok);
+            }
         }
         if (!ok && tc == 0) atomicExch(A.error, 33);
       }
@@ -830,7 +874,9 @@ __device__ __forceinline__ int k4_next(const TcArgs& A, int q, int n_items) {
 }
 
 template <int PASSES>
-__global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A, const __grid_constant__ CUtensorMap tmap_w2) {
+__global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A, const __grid_constant__ CUtensorMap tmap_w2,
+                                                            const __grid_constant__ CUtensorMap tm_w1,
+                                                            const __grid_constant__ CUtensorMap tm_w2) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     float* sf = reinterpret_cast<float*>(__cvta_shared_to_generic((size_t)sbase));
@@ -867,11 +913,17 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A, cons
                 const float* P = A.nets.theta + (size_t)g * A.L.stride;
                 const int qn = k4_next(A, q + gridDim.x, n_items);
                 const float* Pn = qn < n_items ? A.nets.theta + (size_t)(qn / A.tiles) * A.L.stride + A.L.w1 : nullptr;
-                ok = tma_fwd(sbase, P + A.L.w1, Dp, ring, ok, P + A.L.w2);
-                ok = tma_fwd(sbase, P + A.L.w2, H, ring, ok, Pn);
-                ok = tma_wait_gemm(sbase, seen, gemm + 1, ok);       // the d.W^T stages alias the x.W stages: layer 2 must have retired
-                ok = tma_bwd(sbase, &tmap_w2, g, ring, ok);
-                ok = tma_wait_gemm(sbase, seen, gemm + 2, ok);       // ... and the backward GEMM before the next item's W1 chunks
+                if (kOneRing) {       // one ring for all three GEMMs: a stage is reused as soon as its MMAs have retired, whatever GEMM they belong to
+                    ok = tma_fwd_map(sbase, &tm_w1, g, P + A.L.w1, Dp, ring, ok, P + A.L.w2);
+                    ok = tma_fwd_map(sbase, &tm_w2, g, P + A.L.w2, H, ring, ok, Pn);
+                    ok = tma_bwd(sbase, &tmap_w2, g, ring, ok);
+                } else {
+                    ok = tma_fwd(sbase, P + A.L.w1, Dp, ring, ok, P + A.L.w2);
+                    ok = tma_fwd(sbase, P + A.L.w2, H, ring, ok, Pn);
+                    ok = tma_wait_gemm(sbase, seen, gemm + 1, ok);       // the d.W^T stages alias the x.W stages: layer 2 must have retired
+                    ok = tma_bwd(sbase, &tmap_w2, g, ring, ok);
+                    ok = tma_wait_gemm(sbase, seen, gemm + 2, ok);       // ... and the backward GEMM before the next item's W1 chunks
+                }
                 gemm += 3;
             }
             if (!ok) atomicExch(A.error, 24);
@@ -880,8 +932,13 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A, cons
       } else if (warp < W_CONV + CONV_WARPS) {   // converters (the last two warps only fill the warpgroup)
         const int tc = threadIdx.x - W_CONV * 32, cg = (warp - W_CONV) / CONV_GROUP_WARPS, t = tc % (CONV_GROUP_WARPS * 32);
         for (int q = k4_next(A, blockIdx.x, n_items); q < n_items; q = k4_next(A, q + gridDim.x, n_items)) {
-            ok = conv_fwd<PASSES>(sbase, Dp, cg, t, ring, ok);
-            ok = conv_fwd<PASSES>(sbase, H, cg, t, ring, ok);
+            if (kOneRing) {
+                ok = conv_bwd<PASSES>(sbase, cg, t, ring, ok, Dp / 8);
+                ok = conv_bwd<PASSES>(sbase, cg, t, ring, ok, H / 8);
+            } else {
+                ok = conv_fwd<PASSES>(sbase, Dp, cg, t, ring, ok);
+                ok = conv_fwd<PASSES>(sbase, H, cg, t, ring, ok);
+            }
             ok = conv_bwd<PASSES>(sbase, cg, t, ring, ok);
         }
         if (!ok && tc == 0) atomicExch(A.error, 34);
@@ -1703,6 +1760,32 @@ int encode_map3(CUtensorMap* out, const float* base, cuuint64_t d0, cuuint64_t d
     }
     return DMDQN_OK;
 }
+// x.W chunks in the UMMA MN-major layout straight from TMA (tma_fwd_map): the [K][256] matrix at float offset `woff` of every
+// network's parameter block as {32 columns, 4 k-rows, 8 column blocks, K / 4 k-groups, network}.
+int make_fwd_tensor_map(const TcArgs& A, const float* theta, int64_t woff, int K, CUtensorMap* out) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        DMDQN_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !fn) {
+            set_error("cuTensorMapEncodeTiled is not available from this driver");
+            return DMDQN_ERR_CUDA;
+        }
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    const cuuint64_t dims[5] = {32, 4, (cuuint64_t)(H / 32), (cuuint64_t)(K / 4), (cuuint64_t)A.d.n_nets};
+    const cuuint64_t strides[4] = {(cuuint64_t)H * 4, 128, (cuuint64_t)H * 16, (cuuint64_t)A.L.stride * 4};
+    const cuuint32_t box[5] = {32, 4, (cuuint32_t)(H / 32), 2, 1}, estr[5] = {1, 1, 1, 1, 1};
+    const CUresult rc = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(theta + woff), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (x.W map) failed with CUresult %d", (int)rc);
+        return DMDQN_ERR_CUDA;
+    }
+    return DMDQN_OK;
+}
 int make_w2_tensor_map(const TcArgs& A, CUtensorMap* out) {
     return encode_map3(out, A.nets.theta + A.L.w2, H, H, A.d.n_nets, (cuuint64_t)H * sizeof(float),
                        (cuuint64_t)A.L.stride * sizeof(float), 8, H, CU_TENSOR_MAP_SWIZZLE_32B);
@@ -1739,7 +1822,12 @@ int launch_tc(const TcArgs& A, int stages, cudaStream_t s) {
         cfg.blockDim = dim3(NT_F);
         cfg.dynamicSmemBytes = smem_f;
         cfg.numAttrs = A.chain ? 1 : 0;         // in a chain: launched under the tail of the sample kernel (griddepcontrol.wait inside)
-        DMDQN_CUDA(cudaLaunchKernelEx(&cfg, tc_target_kernel<PASSES>, A));
+        CUtensorMap m1, m2, m1t, m2t;
+        if (int rc = make_fwd_tensor_map(A, A.nets.theta, A.L.w1, A.d.obs_stride, &m1)) return rc;
+        if (int rc = make_fwd_tensor_map(A, A.nets.theta, A.L.w2, H, &m2)) return rc;
+        if (int rc = make_fwd_tensor_map(A, A.nets.theta_tgt, A.L.w1, A.d.obs_stride, &m1t)) return rc;
+        if (int rc = make_fwd_tensor_map(A, A.nets.theta_tgt, A.L.w2, H, &m2t)) return rc;
+        DMDQN_CUDA(cudaLaunchKernelEx(&cfg, tc_target_kernel<PASSES>, A, m1, m2, m1t, m2t));
     }
     if (stages & DMDQN_STAGE_ONLINE) {
         CUtensorMap tmap;
@@ -1748,7 +1836,10 @@ int launch_tc(const TcArgs& A, int stages, cudaStream_t s) {
         cfg.blockDim = dim3(NT_F);
         cfg.dynamicSmemBytes = smem_f;
         cfg.numAttrs = A.chain ? 1 : 0;
-        DMDQN_CUDA(cudaLaunchKernelEx(&cfg, tc_online_kernel<PASSES>, A, tmap));
+        CUtensorMap m1, m2;
+        if (int rc = make_fwd_tensor_map(A, A.nets.theta, A.L.w1, A.d.obs_stride, &m1)) return rc;
+        if (int rc = make_fwd_tensor_map(A, A.nets.theta, A.L.w2, H, &m2)) return rc;
+        DMDQN_CUDA(cudaLaunchKernelEx(&cfg, tc_online_kernel<PASSES>, A, tmap, m1, m2));
     }
     if (stages & DMDQN_STAGE_WGRAD) {
         const int items = A.d.n_nets * 3;

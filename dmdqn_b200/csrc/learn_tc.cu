@@ -18,14 +18,16 @@
 //               swizzle), lo part to TMEM columns 256..511 (A-from-TMEM MMA) -- 128 KB each, so all 512 TMEM
 //               columns are used: 256 accumulator + 256 operand;
 //   warp 16     lane 0 issues every tcgen05.mma and commits stages / GEMMs to mbarriers;
-//   warp 17     lane 0 is the TMA producer: raw fp32 weight chunks travel global -> shared memory with
-//               cp.async.bulk (x.W: contiguous 8 x 256 rows) and cp.async.bulk.tensor (d.W^T: a 16-column box of
-//               all 256 rows of W2 through a tensor map), completion on the stage's mbarrier (expect_tx);
-//   warps 18-21 converters: turn a landed raw chunk IN PLACE into the hi | lo halves of the stage in the UMMA
-//               canonical layout (MN-major "128B_BASE32B" for x.W, K-major 64-byte swizzle for d.W^T), then hand
-//               the stage to the MMA lane.  Nobody holds weights in registers across a latency any more, and the
-//               epilogue warps never touch a weight.
-// Stage ring: tma_full (TMA landed) -> conv_full (converted) -> empty (tcgen05.commit: MMAs retired).
+//   warp 17     lane 0 is the TMA producer: every weight chunk (8 k x 256 weights, raw fp32) travels global -> shared memory
+//               through a tensor map that lands it IN the UMMA canonical layout of its GEMM -- x.W: rank-5 view {32 columns,
+//               4 k-rows, 8 column blocks, K / 4 k-groups, network}, box {32, 4, 8, 2, 1}, SWIZZLE_128B_ATOM_32B = the MN-major
+//               "128B_BASE32B" layout; d.W^T: box {8 k-columns, 256 rows}, SWIZZLE_32B = K-major SW32 -- straight into the hi half
+//               of a stage, completion on the stage's mbarrier (expect_tx); each chunk is also requested into L2 six chunks ahead;
+//   warps 18-23 converters, three groups of two warps: split a landed chunk IN PLACE (a 16-byte piece is read, its tf32-rounded
+//               hi part stays at the same address, the lo part goes 8 KB further -- the layout is whatever TMA produced), then
+//               hand the stage to the MMA lane.  Nobody holds weights in registers across a latency, nobody transposes them in
+//               shared memory, and the epilogue warps never touch a weight.
+// One ring of five stages serves all GEMMs of a kernel: tma (landed) -> conv (split) -> empty (tcgen05.commit: MMAs retired).
 #include <cuda.h>
 #include "common.cuh"
 
@@ -37,8 +39,8 @@ constexpr int H = 256;          // hidden width served by this path
 constexpr int BM = 128;         // batch rows per CTA (UMMA M)
 constexpr int EW = 16;          // gather / epilogue warps of K3 / K4a
 constexpr int NT = EW * 32;     // 512 threads
-constexpr int W_MMA = EW, W_TMA = EW + 1, W_CONV = EW + 2;   // warps 18..21: two converter groups of two warps; 22, 23 idle
-constexpr int CONV_WARPS = 6, CONV_GROUP_WARPS = 2;          // d.W^T: two groups of two warps, one per in-place stage
+constexpr int W_MMA = EW, W_TMA = EW + 1, W_CONV = EW + 2;   // warps 18..23: three converter groups of two warps
+constexpr int CONV_WARPS = 6, CONV_GROUP_WARPS = 2;
 constexpr int NT_F = (EW + 8) * 32;   // 768 threads per K3 / K4a CTA: six warpgroups (setmaxnreg is per warpgroup)
 // Register split (setmaxnreg works per warpgroup, inside the pool the CTA was launched with: 768 x 80): the MMA / TMA
 // warpgroup and the converter warpgroup shrink to 32 and release 2 x 128 x 48 registers, which is exactly what the
@@ -266,9 +268,8 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 struct Fwd {
     static constexpr uint32_t R = 0;                          // 128 KB: X hi|lo during layer 1, then activation hi
     static constexpr uint32_t XLO = 3 * ATOM;                 // X lo (K <= 96) inside R
-    static constexpr uint32_t WB = 8 * ATOM;                  // 80 KB of weight buffers: x.W: 6 raw slots of 8 KB (TMA targets) + 2 stages of
-                                                              // 16 KB (hi | lo); d.W^T: 2 in-place stages of 32 KB over the first 64 KB
-    static constexpr uint32_t STG = WB + 4 * 8192;            // the three x.W stages
+    static constexpr uint32_t WB = 8 * ATOM;                  // 80 KB weight ring: five in-place stages of 16 KB (hi 8 KB | lo 8 KB), one k-step each,
+                                                              // shared by the x.W chunks (MN-major) and the d.W^T chunks (K-major SW32)
     static constexpr uint32_t BIAS1 = WB + 81920;             // b1[256]
     static constexpr uint32_t BIAS2 = BIAS1 + 1024;           // b2[256]
     static constexpr uint32_t W3S = BIAS2 + 1024;             // W3[256][4]
@@ -279,21 +280,18 @@ struct Fwd {
 };
 // Barrier block (byte offsets from Fwd::BARS).
 struct Bar {
-    static constexpr uint32_t RAW_FULL = 0, RAW_EMPTY = 32;              // x.W raw ring: 4 slots (TMA landed / converters have read it)
-    static constexpr uint32_t CONV_F = 64, EMPTY_F = 88;                 // x.W stage ring: 3 stages (converted / MMAs retired)
-    static constexpr uint32_t TMA_B = 112, CONV_B = 152, EMPTY_B = 192;  // d.W^T ring: 5 in-place stages (same shared memory)
+    static constexpr uint32_t TMA_B = 112, CONV_B = 152, EMPTY_B = 192;  // weight ring: TMA landed / converted / MMAs retired, per stage
     static constexpr uint32_t AREADY = 232, DONE = 240;                  // A operand published (16 warps) / GEMM retired (1 commit)
     static constexpr uint32_t TMEM = 248;                                // TMEM base address (written by tcgen05.alloc)
 };
-constexpr int NRAW = 4, NSF = 3, NSB = 5;                     // raw slots / stages of the x.W pipe, stages of the d.W^T ring
-constexpr uint32_t STG_F = 16384, RAW_F = 8192;               // x.W   stage: hi 8 KB | lo 8 KB   (8 k-rows x 256 columns)
-constexpr uint32_t STG_B = 16384, RAW_B = 8192;               // d.W^T stage: hi 8 KB | lo 8 KB   (256 rows x 8 k-columns, one k-step)
+constexpr int NSB = 5;                                        // stages of the weight ring (x.W and d.W^T chunks alike)
+constexpr uint32_t STG_B = 16384, RAW_B = 8192;               // a stage: hi 8 KB | lo 8 KB (8 k x 256 weights, one k-step)
 
 // Chunk / GEMM counters.  Every role walks the same sequence of items, GEMMs and chunks, so each keeps its own copy:
-// f / b = chunks that have gone through the x.W / d.W^T ring so far (stage = count % stages, use = count / stages,
+// b = chunks that have gone through the weight ring so far (stage = count % stages, use = count / stages,
 // mbarrier parity = use & 1), gemms = GEMMs retired (parity of AREADY / DONE).
 struct Ring {
-    uint32_t f = 0, b = 0, gemms = 0;
+    uint32_t b = 0, gemms = 0;
 };
 
 __device__ __forceinline__ float4 ldg_stream(const float* p) {   // volatile: issue order = program order
@@ -318,43 +316,27 @@ __device__ __forceinline__ float4 lds4(uint32_t a) {
 // ------------------------------------------------------------------------------------------
 // TMA producer (lane 0 of warp W_TMA).
 // ------------------------------------------------------------------------------------------
-// x.W: W is [K][256] row-major; chunk c = rows 8c .. 8c+7 = 8 KB contiguous -> a raw slot, as it lies.  Four slots deep;
-// under load a DRAM read takes ~2 000 cycles and the tensor pipe wants a chunk every ~410, which four slots cannot cover,
-// so every chunk is also requested into L2 PF chunks ahead of its copy (of this matrix, then of `next`: the matrix
-// the ring streams after this one), which turns the copies into L2 hits.
+// Under load a DRAM read takes ~2 000 cycles and the tensor pipe wants a chunk every ~470, which five stages cannot cover, so
+// every x.W chunk (rows 8c .. 8c+7 of W: 8 KB contiguous) is also requested into L2 PF chunks ahead of its copy (of this
+// matrix, then of `next`: the matrix the ring streams after this one), which turns the copies into L2 hits.
 constexpr int PF = 6;
 // x.W IN PLACE (the ring both directions share): W seen through a rank-5 tensor map {32 columns, 4 k-rows, 8 column blocks,
 // K / 4 k-groups, network} with box {32, 4, 8, 2, 1} and the 32-byte-atom 128-byte swizzle -- one box is a chunk of 8 k-rows x 256
 // columns landing as [k / 4][column / 32][k % 4][128 B] with the 32-byte piece xor-ed by k % 4: the UMMA MN-major
 // "128B_BASE32B" layout itself.  The converters then split it where it lies (hi stays, lo 8 KB further), exactly as they do
 // for d.W^T: no raw slots, five stages deep instead of three, one barrier hop less per chunk.
-__device__ __forceinline__ bool tma_fwd_map(uint32_t sbase, const CUtensorMap* tm, int g, const float* __restrict__ W, int K, Ring& r,
+__device__ __forceinline__ bool tma_fwd(uint32_t sbase, const CUtensorMap* tm, int g, const float* __restrict__ W, int K, Ring& r,
                                             bool ok, const float* __restrict__ next) {
     const uint32_t bars = sbase + Fwd::BARS;
     const int nchunks = K >> 3;
     for (int c = 0; c < nchunks; ++c) {
         const uint32_t s = r.b % NSB, u = r.b / NSB;
-        if (c + PF < nchunks) l2_prefetch(W + (size_t)(c + PF) * 8 * H, RAW_F);
-        else if (next) l2_prefetch(next + (size_t)(c + PF - nchunks) * 8 * H, RAW_F);
+        if (c + PF < nchunks) l2_prefetch(W + (size_t)(c + PF) * 8 * H, RAW_B);
+        else if (next) l2_prefetch(next + (size_t)(c + PF - nchunks) * 8 * H, RAW_B);
         if (u && ok) ok = mbar_wait(bars + Bar::EMPTY_B + 8 * s, (u - 1) & 1);
         mbar_expect_tx(bars + Bar::TMA_B + 8 * s, RAW_B);
         tma_load_5d(sbase + Fwd::WB + s * STG_B, tm, 0, 0, 0, 2 * c, g, bars + Bar::TMA_B + 8 * s);
         ++r.b;
-    }
-    return ok;
-}
-__device__ __forceinline__ bool tma_fwd(uint32_t sbase, const float* __restrict__ W, int K, Ring& r, bool ok,
-                                        const float* __restrict__ next) {
-    const uint32_t bars = sbase + Fwd::BARS;
-    const int nchunks = K >> 3;
-    for (int c = 0; c < nchunks; ++c) {
-        const uint32_t s = r.f % NRAW, u = r.f / NRAW;
-        if (c + PF < nchunks) l2_prefetch(W + (size_t)(c + PF) * 8 * H, RAW_F);
-        else if (next) l2_prefetch(next + (size_t)(c + PF - nchunks) * 8 * H, RAW_F);
-        if (u && ok) ok = mbar_wait(bars + Bar::RAW_EMPTY + 8 * s, (u - 1) & 1);      // the converters have read the previous chunk of this slot
-        mbar_expect_tx(bars + Bar::RAW_FULL + 8 * s, RAW_F);
-        bulk_g2s(sbase + Fwd::WB + s * RAW_F, W + (size_t)c * 8 * H, RAW_F, bars + Bar::RAW_FULL + 8 * s);
-        ++r.f;
     }
     return ok;
 }
@@ -371,77 +353,18 @@ __device__ __forceinline__ bool tma_bwd(uint32_t sbase, const CUtensorMap* tm, i
     }
     return ok;
 }
-// The TMA lane must have seen every phase of DONE before it waits for a later one (a parity wait cannot tell
-// "two phases ahead" from "not yet").
-__device__ __forceinline__ bool tma_wait_gemm(uint32_t sbase, uint32_t& seen, uint32_t upto, bool ok) {
-    while (seen <= upto) {
-        if (ok) ok = mbar_wait(sbase + Fwd::BARS + Bar::DONE, seen & 1);
-        ++seen;
-    }
-    return ok;
-}
-
 // ------------------------------------------------------------------------------------------
-// Converters (warps W_CONV .. W_CONV + 3, tc = 0..127): raw fp32 chunk -> hi | lo halves of a stage in the UMMA canonical layout.
-//   x.W:   all four warps take the chunk out of its raw slot (16 bytes x 4 per thread), free the slot for the TMA lane, and
-//          write the split pieces into one of the two stages (MN-major "128B_BASE32B") as soon as its MMAs have retired;
-//   d.W^T: the chunk was loaded straight into the hi half of its stage and is converted IN PLACE (K-major 64-byte swizzle;
-//          the swizzle permutes the four 16-byte pieces of a 64-byte row among themselves, and those sit on four
-//          neighbouring lanes, so a warp barrier between reading and writing is all it needs).  Two groups of two warps,
-//          group g owns stage g, so each group sees every phase of its stage's mbarriers in order (a parity wait that is
-//          one full phase early succeeds at once).
+// Converters (warps W_CONV .. W_CONV + 5): raw fp32 chunk -> hi | lo halves of its stage, in place.  Three groups of two warps;
+// chunk c of the ring goes to group c % 3, so each group has three chunk times for its wait -> read -> split -> write -> fence
+// -> arrive chain.
 // ------------------------------------------------------------------------------------------
 template <int PASSES>
-__device__ __forceinline__ bool conv_fwd(uint32_t sbase, int K, int grp, int t, Ring& r, bool ok) {
-    // Two groups of two warps, group g converts the chunks with (chunk count) % 2 == g into stage g: each group has a whole
-    // MMA chunk time (two chunks' worth) for its wait -> read -> split -> write -> arrive chain instead of one.
-    const uint32_t bars = sbase + Fwd::BARS;
-    const int k0 = t >> 6, n = (t & 63) << 2;                 // t = 0..63: piece p = t + 64 i: k-row i, columns 4 t .. + 3
-    const int nchunks = K >> 3;
-    for (int c = 0; c < nchunks; ++c) {
-        const uint32_t f = r.f + (uint32_t)c;
-        if ((int)(f % NSF) != grp) continue;                  // group g owns stage g
-        const uint32_t rs = f % NRAW, ru = f / NRAW, s = f % NSF, u = f / NSF;
-        // A raw slot is read by different groups from use to use (4 slots, 3 groups), and a parity wait cannot tell "two phases
-        // ahead" from "done": a group that ran ahead would take the slot's PREVIOUS chunk for its own.  So it first waits until
-        // that previous use has been read (by whichever group) -- after that the slot's FULL barrier is exactly one phase behind.
-        if (ru && ok) ok = mbar_wait(bars + Bar::RAW_EMPTY + 8 * rs, (ru - 1) & 1);
-        if (ok) ok = mbar_wait(bars + Bar::RAW_FULL + 8 * rs, ru & 1);                // the raw chunk has landed
-        if (u && ok) ok = mbar_wait(bars + Bar::EMPTY_F + 8 * s, (u - 1) & 1);        // the MMAs of the stage's previous chunk have retired
-        const uint32_t st = sbase + Fwd::STG + s * STG_F, raw = sbase + Fwd::WB + rs * RAW_F;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            float4 x[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) x[i] = lds4(raw + (uint32_t)(t + 64 * (4 * half + i)) * 16u);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float4 hi, lo;
-                split4<PASSES>(x[i], hi, lo);
-                const uint32_t o = st + off_mn(H, k0 + 4 * half + i, n);
-                sts4(o, hi);
-                if (PASSES == 3) sts4(o + RAW_F, lo);
-            }
-        }
-        // Generic-proxy reads of the raw slot must be ordered before the async-proxy (TMA) write that refills it, and the
-        // stage writes before the MMA's reads: one proxy fence serves both (without it ~1 % of the tiles saw a partly refilled
-        // chunk under load; tools/dbg_k3_repeat.py reproduces that in seconds).
-        fence_async_smem();
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) {
-            mbar_arrive(bars + Bar::RAW_EMPTY + 8 * rs);
-            mbar_arrive(bars + Bar::CONV_F + 8 * s);
-        }
-    }
-    r.f += (uint32_t)nchunks;
-    return ok;
-}
-template <int PASSES>
-__device__ __forceinline__ bool conv_bwd(uint32_t sbase, int grp, int t, Ring& r, bool ok, int nchunks = H / 8) {
-    // In place: the chunk landed in the hi half of its stage already swizzled (TMA SWIZZLE_32B == UMMA K-major SW32), so a
-    // thread reads a 16-byte piece, leaves its hi part at the same address and puts the lo part 8 KB further.  Chunk c of the
-    // ring goes to group c % 3; stages (5) and groups (3) do not line up, hence the same guard as in conv_fwd: wait until the
-    // stage's previous chunk has been converted (by whichever group) before trusting the parity of its TMA barrier.
+__device__ __forceinline__ bool conv_ring(uint32_t sbase, int grp, int t, Ring& r, bool ok, int nchunks = H / 8) {
+    // In place: the chunk landed in the hi half of its stage already in the UMMA layout (the tensor map's box order and swizzle
+    // are the layout), so a thread reads a 16-byte piece, leaves its hi part at the same address and puts the lo part 8 KB
+    // further.  Stages (5) and groups (3) do not line up, and an mbarrier parity wait cannot tell "two phases ahead" from
+    // "done": a group first waits until the stage's previous chunk has been converted (by whichever group) before it trusts
+    // the parity of the stage's TMA barrier.
     const uint32_t bars = sbase + Fwd::BARS;
     constexpr int NGRP = CONV_WARPS / CONV_GROUP_WARPS;
     for (int c = 0; c < nchunks; ++c) {
@@ -477,38 +400,30 @@ __device__ __forceinline__ bool conv_bwd(uint32_t sbase, int grp, int t, Ring& r
 //   A hi: shared memory, K-major SW128 at a_hi; A lo: shared memory (a_lo_smem != 0) or TMEM columns.
 //   BT = false: x.W, stages MN-major;  BT = true: d.W^T, stages K-major SW32.  One k-step (8 k) per chunk either way.
 // ------------------------------------------------------------------------------------------
-#ifdef FWD_RAW_RING
-constexpr bool kOneRing = false;
-#else
-constexpr bool kOneRing = true;     // x.W chunks travel through the in-place ring too (tma_fwd_map)
-#endif
-template <int PASSES, bool BT_>
+template <int PASSES, bool BT>
 __device__ __forceinline__ bool mma_gemm(uint32_t sbase, uint32_t tmem, uint32_t a_hi, uint32_t a_lo_smem, uint32_t a_lo_tmem,
                                          int K, Ring& r, bool ok) {
     const uint32_t bars = sbase + Fwd::BARS;
     constexpr int KCX = 8;
-    constexpr uint32_t idesc = make_idesc(false, !BT_);
-    constexpr bool BT = BT_ || kOneRing;            // which ring (barriers, stage geometry, counter); BT_ alone picks the layout
+    constexpr uint32_t idesc = make_idesc(false, !BT);
     // Descriptors differ only in their 14-bit start-address field: build each once, then add (bytes >> 4).
     const uint64_t a_hi0 = make_desc(a_hi, 16, 1024, 2);
     const uint64_t a_lo0 = make_desc(a_lo_smem, 16, 1024, 2);
-    const uint64_t b0 = BT_ ? make_desc(sbase + Fwd::WB, 16, 256, 6)
-                            : make_desc(sbase + (kOneRing ? Fwd::WB : Fwd::STG), 512, 4096, 1);
+    const uint64_t b0 = BT ? make_desc(sbase + Fwd::WB, 16, 256, 6) : make_desc(sbase + Fwd::WB, 512, 4096, 1);
     if (ok) ok = mbar_wait(bars + Bar::AREADY, r.gemms & 1);      // all 16 epilogue warps have published the A operand
     tc_fence_after();
     const int nchunks = K / KCX;
     for (int c = 0; c < nchunks; ++c) {
-        const uint32_t cnt = BT ? r.b : r.f;
-        const uint32_t s = cnt % (BT ? NSB : NSF), u = cnt / (BT ? NSB : NSF);
-        if (ok) ok = mbar_wait(bars + (BT ? Bar::CONV_B : Bar::CONV_F) + 8 * s, u & 1);   // the converters have finished chunk c
+        const uint32_t s = r.b % NSB, u = r.b / NSB;
+        if (ok) ok = mbar_wait(bars + Bar::CONV_B + 8 * s, u & 1);   // the converters have finished chunk c
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < KCX / 8; ++ks) {
             const int kg = c * KCX + ks * 8;
             const uint32_t a_off = ((uint32_t)(kg >> 5) * ATOM + (uint32_t)((kg & 31) >> 3) * 32) >> 4;
-            const uint32_t b_off = (s * (BT ? STG_B : STG_F)) >> 4;
+            const uint32_t b_off = (s * STG_B) >> 4;
             const uint64_t a_hi_d = a_hi0 + a_off;
-            const uint64_t b_hi = b0 + b_off, b_lo = b0 + b_off + ((BT ? RAW_B : RAW_F) >> 4);
+            const uint64_t b_hi = b0 + b_off, b_lo = b0 + b_off + (RAW_B >> 4);
             uint32_t acc = (c | ks) ? 1u : 0u;
             if (PASSES == 3) {                                // small terms first
                 if (a_lo_smem) mma_ss(tmem, a_lo0 + a_off, b_hi, idesc, acc);
@@ -518,8 +433,8 @@ __device__ __forceinline__ bool mma_gemm(uint32_t sbase, uint32_t tmem, uint32_t
             }
             mma_ss(tmem, a_hi_d, b_hi, idesc, acc);
         }
-        umma_commit(bars + (BT ? Bar::EMPTY_B : Bar::EMPTY_F) + 8 * s);   // the stage is free once these MMAs retire
-        if (BT) ++r.b; else ++r.f;
+        umma_commit(bars + Bar::EMPTY_B + 8 * s);   // the stage is free once these MMAs retire
+        ++r.b;
     }
     umma_commit(bars + Bar::DONE);
     r.gemms += 1;
@@ -698,14 +613,6 @@ __device__ __forceinline__ uint32_t tc_prologue(uint32_t sbase) {
     const int warp = threadIdx.x >> 5;
     const uint32_t bars = sbase + Fwd::BARS;
     if (threadIdx.x == 0) {
-        for (int b = 0; b < NRAW; ++b) {
-            mbar_init(bars + Bar::RAW_FULL + 8 * b, 1);           // one arrive.expect_tx + the bytes of the chunk
-            mbar_init(bars + Bar::RAW_EMPTY + 8 * b, CONV_GROUP_WARPS); // one arrival per warp of the converter group that read it
-        }
-        for (int b = 0; b < NSF; ++b) {
-            mbar_init(bars + Bar::CONV_F + 8 * b, CONV_GROUP_WARPS);    // one arrival per warp of the stage's converter group
-            mbar_init(bars + Bar::EMPTY_F + 8 * b, 1);            // one tcgen05.commit
-        }
         for (int b = 0; b < NSB; ++b) {
             mbar_init(bars + Bar::TMA_B + 8 * b, 1);
             mbar_init(bars + Bar::CONV_B + 8 * b, CONV_GROUP_WARPS);
@@ -785,13 +692,8 @@ __global__ void __launch_bounds__(NT_F, 1) tc_target_kernel(const TcArgs A, cons
                 const float* P = ((q & 1) ? A.nets.theta_tgt : A.nets.theta) + (size_t)g * A.L.stride;
                 const int qn = k3_next(A, q + gridDim.x, n_items);
                 const float* Pn = qn < n_items ? ((qn & 1) ? A.nets.theta_tgt : A.nets.theta) + (size_t)((qn >> 1) / A.tiles) * A.L.stride + A.L.w1 : nullptr;
-                if (kOneRing) {
-                    ok = tma_fwd_map(sbase, (q & 1) ? &tm_w1t : &tm_w1, g, P + A.L.w1, Dp, ring, ok, P + A.L.w2);
-                    ok = tma_fwd_map(sbase, (q & 1) ? &tm_w2t : &tm_w2, g, P + A.L.w2, H, ring, ok, Pn);
-                } else {
-                    ok = tma_fwd(sbase, P + A.L.w1, Dp, ring, ok, P + A.L.w2);
-                    ok = tma_fwd(sbase, P + A.L.w2, H, ring, ok, Pn);
-                }
+                ok = tma_fwd(sbase, (q & 1) ? &tm_w1t : &tm_w1, g, P + A.L.w1, Dp, ring, ok, P + A.L.w2);
+                ok = tma_fwd(sbase, (q & 1) ? &tm_w2t : &tm_w2, g, P + A.L.w2, H, ring, ok, Pn);
                 q = qn;
             }
             if (!ok) atomicExch(A.error, 23);
@@ -800,13 +702,8 @@ __global__ void __launch_bounds__(NT_F, 1) tc_target_kernel(const TcArgs A, cons
       } else if (warp < W_CONV + CONV_WARPS) {   // converters (the last two warps only fill the warpgroup)
         const int tc = threadIdx.x - W_CONV * 32, cg = (warp - W_CONV) / CONV_GROUP_WARPS, t = tc % (CONV_GROUP_WARPS * 32);
         for (int q = k3_next(A, blockIdx.x, n_items); q < n_items; q = k3_next(A, q + gridDim.x, n_items)) {
-            if (kOneRing) {
-                ok = conv_bwd<PASSES>(sbase, cg, t, ring, ok, Dp / 8);
-                ok = conv_bwd<PASSES>(sbase, cg, t, ring, ok, H / 8);
-            } else {
-                ok = conv_fwd<PASSES>(sbase, Dp, cg, t, ring, ok);
-                ok = conv_fwd<PASSES>(sbase, H, cg, t, ring, ok);
-            }
+            ok = conv_ring<PASSES>(sbase, cg, t, ring, ok, Dp / 8);
+            ok = conv_ring<PASSES>(sbase, cg, t, ring, ok, H / 8);
         }
         if (!ok && tc == 0) atomicExch(A.error, 33);
       }
@@ -905,7 +802,6 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A, cons
         __syncwarp();
       } else if (warp == W_TMA) {
         if ((threadIdx.x & 31) == 0) {
-            uint32_t seen = 0, gemm = 0;
             for (int q = k4_next(A, blockIdx.x, n_items); q < n_items; q = k4_next(A, q + gridDim.x, n_items)) {
                 const int g = q / A.tiles;
                 // K3 may still be running on other SMs: both halves of this tile's TD-target inputs must have been published
@@ -913,18 +809,10 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A, cons
                 const float* P = A.nets.theta + (size_t)g * A.L.stride;
                 const int qn = k4_next(A, q + gridDim.x, n_items);
                 const float* Pn = qn < n_items ? A.nets.theta + (size_t)(qn / A.tiles) * A.L.stride + A.L.w1 : nullptr;
-                if (kOneRing) {       // one ring for all three GEMMs: a stage is reused as soon as its MMAs have retired, whatever GEMM they belong to
-                    ok = tma_fwd_map(sbase, &tm_w1, g, P + A.L.w1, Dp, ring, ok, P + A.L.w2);
-                    ok = tma_fwd_map(sbase, &tm_w2, g, P + A.L.w2, H, ring, ok, Pn);
-                    ok = tma_bwd(sbase, &tmap_w2, g, ring, ok);
-                } else {
-                    ok = tma_fwd(sbase, P + A.L.w1, Dp, ring, ok, P + A.L.w2);
-                    ok = tma_fwd(sbase, P + A.L.w2, H, ring, ok, Pn);
-                    ok = tma_wait_gemm(sbase, seen, gemm + 1, ok);       // the d.W^T stages alias the x.W stages: layer 2 must have retired
-                    ok = tma_bwd(sbase, &tmap_w2, g, ring, ok);
-                    ok = tma_wait_gemm(sbase, seen, gemm + 2, ok);       // ... and the backward GEMM before the next item's W1 chunks
-                }
-                gemm += 3;
+                // one ring for all three GEMMs: a stage is reused as soon as its MMAs have retired, whatever GEMM they belong to
+                ok = tma_fwd(sbase, &tm_w1, g, P + A.L.w1, Dp, ring, ok, P + A.L.w2);
+                ok = tma_fwd(sbase, &tm_w2, g, P + A.L.w2, H, ring, ok, Pn);
+                ok = tma_bwd(sbase, &tmap_w2, g, ring, ok);
             }
             if (!ok) atomicExch(A.error, 24);
         }
@@ -932,14 +820,9 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A, cons
       } else if (warp < W_CONV + CONV_WARPS) {   // converters (the last two warps only fill the warpgroup)
         const int tc = threadIdx.x - W_CONV * 32, cg = (warp - W_CONV) / CONV_GROUP_WARPS, t = tc % (CONV_GROUP_WARPS * 32);
         for (int q = k4_next(A, blockIdx.x, n_items); q < n_items; q = k4_next(A, q + gridDim.x, n_items)) {
-            if (kOneRing) {
-                ok = conv_bwd<PASSES>(sbase, cg, t, ring, ok, Dp / 8);
-                ok = conv_bwd<PASSES>(sbase, cg, t, ring, ok, H / 8);
-            } else {
-                ok = conv_fwd<PASSES>(sbase, Dp, cg, t, ring, ok);
-                ok = conv_fwd<PASSES>(sbase, H, cg, t, ring, ok);
-            }
-            ok = conv_bwd<PASSES>(sbase, cg, t, ring, ok);
+            ok = conv_ring<PASSES>(sbase, cg, t, ring, ok, Dp / 8);
+            ok = conv_ring<PASSES>(sbase, cg, t, ring, ok, H / 8);
+            ok = conv_ring<PASSES>(sbase, cg, t, ring, ok, H / 8);
         }
         if (!ok && tc == 0) atomicExch(A.error, 34);
       }

@@ -470,8 +470,17 @@ struct XGather {
     float4 x[MAXP];
     uint32_t off[MAXP];
     int n;
+    float4 sp;                                                // this thread's share of the item's small parameters (b1 | b2 | W3)
 
-    __device__ __forceinline__ void begin(const float* __restrict__ ring, const int32_t* __restrict__ rows, int r0, int B, int Dp) {
+    // (P: the parameter block the item uses.  Its biases and head weights -- 6 KB that every epilogue reads from shared memory
+    // -- travel with the rows, one item ahead, instead of being fetched at the top of the item with the epilogue warps waiting.)
+    __device__ __forceinline__ void begin(const float* __restrict__ ring, const int32_t* __restrict__ rows, int r0, int B, int Dp,
+                                          const float* __restrict__ P, const Layout& L) {
+        {
+            const int j = threadIdx.x;
+            if (j < H) { sp.x = __ldg(P + L.b1 + j); sp.y = __ldg(P + L.b2 + j); }
+            else sp = __ldg(reinterpret_cast<const float4*>(P + L.w3) + (j - H));
+        }
         const int q = Dp >> 2;                                // 16-byte pieces per row
         n = BM * q / NT;
         const int dr = NT / q, dp = NT % q;
@@ -495,6 +504,12 @@ struct XGather {
         }
     }
     __device__ __forceinline__ void store(uint32_t sbase) {
+        {
+            float* s = reinterpret_cast<float*>(__cvta_shared_to_generic((size_t)sbase));
+            const int j = threadIdx.x;
+            if (j < H) { s[Fwd::BIAS1 / 4 + j] = sp.x; s[Fwd::BIAS2 / 4 + j] = sp.y; }
+            else reinterpret_cast<float4*>(s + Fwd::W3S / 4)[j - H] = sp;
+        }
 #pragma unroll
         for (int j = 0; j < MAXP; ++j) {
             if (j < n) {
@@ -596,17 +611,6 @@ __device__ __forceinline__ void epi_head(uint32_t sbase, uint32_t tmem, const Ep
     const float4 p0 = qp[e.row], p1 = qp[BM + e.row], p2 = qp[2 * BM + e.row], p3 = qp[3 * BM + e.row];
     q[0] = ((p0.x + p1.x) + (p2.x + p3.x)) + __ldg(b3 + 0); q[1] = ((p0.y + p1.y) + (p2.y + p3.y)) + __ldg(b3 + 1);
     q[2] = ((p0.z + p1.z) + (p2.z + p3.z)) + __ldg(b3 + 2); q[3] = ((p0.w + p1.w) + (p2.w + p3.w)) + __ldg(b3 + 3);
-}
-
-__device__ __forceinline__ void load_small_params(uint32_t sbase, const float* __restrict__ P, const Layout& L) {
-    float* s = reinterpret_cast<float*>(__cvta_shared_to_generic((size_t)sbase));
-    const int j = threadIdx.x;
-    if (j < H) {
-        s[Fwd::BIAS1 / 4 + j] = __ldg(P + L.b1 + j);
-        s[Fwd::BIAS2 / 4 + j] = __ldg(P + L.b2 + j);
-    } else {
-        reinterpret_cast<float4*>(s + Fwd::W3S / 4)[j - H] = __ldg(reinterpret_cast<const float4*>(P + L.w3) + (j - H));
-    }
 }
 
 __device__ __forceinline__ uint32_t tc_prologue(uint32_t sbase) {
@@ -714,7 +718,7 @@ __global__ void __launch_bounds__(NT_F, 1) tc_target_kernel(const TcArgs A, cons
         int q = k3_next(A, blockIdx.x, n_items);
         if (q < n_items) {
             const int g = (q >> 1) / A.tiles, rt = (q >> 1) % A.tiles;
-            xg.begin(A.rp.next_obs, A.rows + (size_t)g * B, rt * BM, B, Dp);
+            xg.begin(A.rp.next_obs, A.rows + (size_t)g * B, rt * BM, B, Dp, ((q & 1) ? A.nets.theta_tgt : A.nets.theta) + (size_t)g * A.L.stride, A.L);
         }
         int q_last = -1;                                       // the last item is published here, the others by the MMA lane
         while (q < n_items) {
@@ -724,8 +728,7 @@ __global__ void __launch_bounds__(NT_F, 1) tc_target_kernel(const TcArgs A, cons
             TS_DECL;
             TS();
             KT_FIRST();
-            load_small_params(sbase, P, A.L);
-            xg.store(sbase);
+            xg.store(sbase);          // observation rows and b1 | b2 | W3 of this item: requested one item ago
             a_ready(sbase);
             epi_sync();        // biases / head weights visible to every epilogue thread
             TS();
@@ -738,7 +741,8 @@ __global__ void __launch_bounds__(NT_F, 1) tc_target_kernel(const TcArgs A, cons
             const int qn = k3_next(A, q + gridDim.x, n_items);
             if (qn < n_items) {                                // the next tile's rows travel while layer 2 runs
                 const int gn = (qn >> 1) / A.tiles, rtn = (qn >> 1) % A.tiles;
-                xg.begin(A.rp.next_obs, A.rows + (size_t)gn * B, rtn * BM, B, Dp);
+                xg.begin(A.rp.next_obs, A.rows + (size_t)gn * B, rtn * BM, B, Dp,
+                         ((qn & 1) ? A.nets.theta_tgt : A.nets.theta) + (size_t)gn * A.L.stride, A.L);
             }
             ok = wait_gemm(sbase, ring, ok);
             TS();
@@ -831,7 +835,7 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A, cons
         const Epi e;
         XGather<PASSES> xg;
         int q = k4_next(A, blockIdx.x, n_items);
-        if (q < n_items) xg.begin(A.rp.obs, A.rows + (size_t)(q / A.tiles) * B, (q % A.tiles) * BM, B, Dp);
+        if (q < n_items) xg.begin(A.rp.obs, A.rows + (size_t)(q / A.tiles) * B, (q % A.tiles) * BM, B, Dp, A.nets.theta + (size_t)(q / A.tiles) * A.L.stride, A.L);
         int q_last = -1;                                       // the last item is published here, the others by the MMA lane
         while (q < n_items) {
             const int g = q / A.tiles, rt = q % A.tiles, r0 = rt * BM;
@@ -842,8 +846,7 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A, cons
             TS_DECL;
             TS();
             KT_FIRST();
-            load_small_params(sbase, P, A.L);
-            xg.store(sbase);
+            xg.store(sbase);          // observation rows and b1 | b2 | W3 of this item: requested one item ago
             a_ready(sbase);
             epi_sync();        // biases / head weights visible to every epilogue thread
             TS();
@@ -1032,7 +1035,7 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A, cons
             TS();
             const int qn = k4_next(A, q + gridDim.x, n_items);
             if (qn < n_items)                                     // the next tile's rows travel while the backward GEMM runs
-                xg.begin(A.rp.obs, A.rows + (size_t)(qn / A.tiles) * B, (qn % A.tiles) * BM, B, Dp);
+                xg.begin(A.rp.obs, A.rows + (size_t)(qn / A.tiles) * B, (qn % A.tiles) * BM, B, Dp, A.nets.theta + (size_t)(qn / A.tiles) * A.L.stride, A.L);
             // dh1 = (dh2 W2^T) * relu'(h1)
             ok = wait_gemm(sbase, ring, ok);
             TS();

@@ -451,6 +451,36 @@ class AgentGroup:
         self.learn_step_host += self.active_host().astype(np.int64)
         return sb["metrics_host"]
 
+    def capture_step_host(self, sb):
+        """``step_host`` as a CUDA graph: the H2D copy of the pinned block, push, the learn chain and the copy of the metrics
+        back to pinned host memory are captured once and replayed with ONE launch per step (the block and the metrics buffer
+        are the fixed addresses of ``sb``; refill ``sb["host"]`` before each replay).  Returns ``replay`` -> the pinned
+        metrics tensor; synchronise the stream before reading it.  Same results as ``step_host``, bit for bit."""
+        hp = self._hp_for(None)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+
+        def launch(stream_ptr):
+            N.check(self.lib.dmdqn_step_host(C.byref(self.dims), C.byref(hp), C.byref(self.replay), C.byref(self.nets),
+                                             C.byref(sb["desc"]), sb["host_block"].data_ptr(), sb["dev_block"].data_ptr(),
+                                             _ptr(self.metrics), sb["metrics_host"].data_ptr(), _ptr(self.workspace),
+                                             self.workspace.numel(), stream_ptr))
+        with torch.cuda.stream(side):           # warm-up outside the capture (per-device launch attributes): one real step
+            launch(side.cuda_stream)
+            self.n_written_host += 1
+            self.learn_step_host += self.active_host().astype(np.int64)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            launch(torch.cuda.current_stream(self.device).cuda_stream)
+
+        def replay() -> torch.Tensor:
+            graph.replay()
+            self.n_written_host += 1
+            self.learn_step_host += self.active_host().astype(np.int64)
+            return sb["metrics_host"]
+        return replay
+
     def check_errors(self) -> None:
         """Raise if a tcgen05 kernel reported an expired mbarrier wait since the last check (the kernels then skip
         the weight update instead of applying garbage; learned flag metrics[:, 7] < 0).  Reads one int from the

@@ -786,3 +786,38 @@ def test_fractional_observations_meet_the_fp32_bar():
     for half, sl in (("integer observations", slice(0, n // 2)), ("fractional observations", slice(n // 2, n))):
         for k in ("q_next", "tq_all", "q_all"):
             close(got[k][sl], want[k][sl], rtol=RTOL, what=f"{half}: tcgen05 vs FFMA {k}")
+
+
+def test_captured_step_host_equals_plain_step_host():
+    """AgentGroup.capture_step_host: H2D copy + push + learn chain + metrics D2H replayed as one CUDA graph gives the same bits
+    as the plain dmdqn_step_host call, step after step, with the host block refilled in between."""
+    cfg = {"nn_layers": [256, 256], "replay_buffer_size": 200, "batch_size": 64, "precision": "tf32x3"}
+    n = 24
+    a, b = _group(n, cfg, seed=5), _group(n, cfg, seed=5)
+    for g in (a, b):
+        _fill(g, None, np.random.default_rng(3), 200)
+    sa, sb_ = a.make_step_block(), b.make_step_block()
+    rng = np.random.default_rng(12)
+
+    def refill(blk):
+        h = blk["host"]
+        h["obs"].copy_(torch.as_tensor(obs)); h["next_obs"].copy_(torch.as_tensor(nxt)); h["act"].copy_(torch.as_tensor(act))
+        h["rew"].copy_(torch.as_tensor(rew)); h["done"].copy_(torch.as_tensor(dn)); h["draws"].copy_(torch.as_tensor(dr))
+    replay = None
+    for it in range(5):
+        obs = rng.integers(-1, 20, (n, 89)).astype(np.float32); nxt = rng.integers(-1, 20, (n, 89)).astype(np.float32)
+        act = rng.integers(0, 4, n).astype(np.int32); rew = -rng.random(n) * 100
+        dn = (rng.random(n) < 0.1).astype(np.uint8)
+        dr = rng.integers(0, 2**31, (n, 64)).astype(np.int32)
+        refill(sa); refill(sb_)
+        ma = a.step_host(sa)
+        if replay is None:
+            replay = b.capture_step_host(sb_)      # its warm-up IS this step (one real step on the side stream)
+            mb = sb_["metrics_host"]
+        else:
+            mb = replay()
+        torch.cuda.synchronize()
+        assert torch.equal(ma, mb), f"step {it}: metrics differ"
+        for name in ("theta", "theta_tgt", "adam_m", "adam_v", "obs", "rew_ring"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), f"step {it}: {name} differs"
+        assert np.array_equal(a.n_written_host, b.n_written_host) and np.array_equal(a.learn_step_host, b.learn_step_host)

@@ -35,6 +35,10 @@ timeit("step_host, sync every step", lambda: grp.step_host(sb), True)
 def full():
     m = grp.step_host(sb); stream.synchronize(); return float(m[0, 0])
 timeit("step_host, sync + read loss", full, False)
+replay = grp.capture_step_host(sb)
+def full_graph():
+    m = replay(); stream.synchronize(); return float(m[0, 0])
+timeit("step_host as ONE CUDA graph, sync + read loss", full_graph, False)
 dev = sb["dev_block"]; host = sb["host_block"]
 timeit("H2D copy of the block alone, sync every step", lambda: dev.copy_(host, non_blocking=True), True)
 t0 = time.perf_counter()

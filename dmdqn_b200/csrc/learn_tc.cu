@@ -183,10 +183,6 @@ __device__ __forceinline__ void split4(const float4& x, float4& hi, float4& lo) 
 __device__ __forceinline__ uint32_t off_k128(int rows, int r, int k) {
     return (uint32_t)((k >> 5) * rows * 128 + r * 128 + ((((k & 31) >> 2) ^ (r & 7)) << 4) + ((k & 3) << 2));
 }
-//   K-major, 64-byte swizzle: [k/16][row][64 B], piece index ^= (row / 2) % 4
-__device__ __forceinline__ uint32_t off_k64(int rows, int r, int k) {
-    return (uint32_t)((k >> 4) * rows * 64 + r * 64 + ((((k & 15) >> 2) ^ ((r >> 1) & 3)) << 4) + ((k & 3) << 2));
-}
 //   MN-major tf32 (128B_BASE32B): atoms of 4 k x 32 mn = 512 B, [k/4][mn/32][k%4][128 B], 32-byte piece ^= k % 4
 __device__ __forceinline__ uint32_t off_mn(int mn_total, int k, int mn) {
     return (uint32_t)((k >> 2) * (mn_total >> 5) * 512 + (mn >> 5) * 512 + (k & 3) * 128 +
@@ -231,7 +227,9 @@ __device__ __forceinline__ bool flag_acquire_ge(const int* f, int want) {
     }
     return false;
 }
+#ifdef TC_TIMING
 __device__ __forceinline__ unsigned smid_() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+#endif
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // Phase stamps (build with -DTC_TIMING, tools/phase_timing.sh): a few threads print clock64 deltas.

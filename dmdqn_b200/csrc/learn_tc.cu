@@ -29,6 +29,7 @@
 //               shared memory, and the epilogue warps never touch a weight.
 // One ring of five stages serves all GEMMs of a kernel: tma (landed) -> conv (split) -> empty (tcgen05.commit: MMAs retired).
 #include <cuda.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace dmdqn {
@@ -1619,8 +1620,18 @@ __global__ void __launch_bounds__(Wg::NTW, 1) tc_wgrad_kernel(const TcArgs A, co
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-int encode_map3(CUtensorMap* out, const float* base, cuuint64_t d0, cuuint64_t d1, cuuint64_t d2, cuuint64_t stride1_bytes,
-                cuuint64_t stride2_bytes, cuuint32_t box0, cuuint32_t box1, CUtensorMapSwizzle swz) {
+// One encoder for every tensor map of this file.  The library keeps no state, so the maps are built per launch -- nine per learn
+// step, ~1.3 us of host time each -- but a map is a pure function of (base address, shape, strides, box, swizzle): the last few
+// results are memoised per host thread, which takes ~10 us off the host side of a step for a caller that passes the same buffers
+// every step (the usual case) and changes nothing for one that does not.
+struct MapKey {
+    const void* base;
+    cuuint64_t dims[5], strides[4];
+    cuuint32_t box[5];
+    int rank, swz;
+};
+int encode_tiled(CUtensorMap* out, const float* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box,
+                 CUtensorMapSwizzle swz) {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -1632,43 +1643,42 @@ int encode_map3(CUtensorMap* out, const float* base, cuuint64_t d0, cuuint64_t d
         }
         encode = reinterpret_cast<EncodeTiledFn>(fn);
     }
-    const cuuint64_t dims[3] = {d0, d1, d2};
-    const cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
-    const cuuint32_t box[3] = {box0, box1, 1}, estr[3] = {1, 1, 1};
-    const CUresult rc = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    constexpr int kSlots = 32;
+    static thread_local MapKey keys[kSlots];
+    static thread_local CUtensorMap maps[kSlots];
+    static thread_local int used = 0, next = 0;
+    MapKey k = {};
+    k.base = base; k.rank = rank; k.swz = (int)swz;
+    for (int i = 0; i < rank; ++i) { k.dims[i] = dims[i]; k.box[i] = box[i]; }
+    for (int i = 0; i + 1 < rank; ++i) k.strides[i] = strides[i];
+    for (int i = 0; i < used; ++i)
+        if (memcmp(&keys[i], &k, sizeof(MapKey)) == 0) { *out = maps[i]; return DMDQN_OK; }
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUresult rc = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)rc);
+        set_error("cuTensorMapEncodeTiled (rank %d) failed with CUresult %d", rank, (int)rc);
         return DMDQN_ERR_CUDA;
     }
+    keys[next] = k; maps[next] = *out;
+    next = (next + 1) % kSlots;
+    if (used < kSlots) ++used;
     return DMDQN_OK;
 }
-// x.W chunks in the UMMA MN-major layout straight from TMA (tma_fwd_map): the [K][256] matrix at float offset `woff` of every
+int encode_map3(CUtensorMap* out, const float* base, cuuint64_t d0, cuuint64_t d1, cuuint64_t d2, cuuint64_t stride1_bytes,
+                cuuint64_t stride2_bytes, cuuint32_t box0, cuuint32_t box1, CUtensorMapSwizzle swz) {
+    const cuuint64_t dims[3] = {d0, d1, d2};
+    const cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+    const cuuint32_t box[3] = {box0, box1, 1};
+    return encode_tiled(out, base, 3, dims, strides, box, swz);
+}
+// x.W chunks in the UMMA MN-major layout straight from TMA (tma_fwd): the [K][256] matrix at float offset `woff` of every
 // network's parameter block as {32 columns, 4 k-rows, 8 column blocks, K / 4 k-groups, network}.
 int make_fwd_tensor_map(const TcArgs& A, const float* theta, int64_t woff, int K, CUtensorMap* out) {
-    static EncodeTiledFn encode = nullptr;
-    if (!encode) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        DMDQN_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-        if (qres != cudaDriverEntryPointSuccess || !fn) {
-            set_error("cuTensorMapEncodeTiled is not available from this driver");
-            return DMDQN_ERR_CUDA;
-        }
-        encode = reinterpret_cast<EncodeTiledFn>(fn);
-    }
     const cuuint64_t dims[5] = {32, 4, (cuuint64_t)(H / 32), (cuuint64_t)(K / 4), (cuuint64_t)A.d.n_nets};
     const cuuint64_t strides[4] = {(cuuint64_t)H * 4, 128, (cuuint64_t)H * 16, (cuuint64_t)A.L.stride * 4};
-    const cuuint32_t box[5] = {32, 4, (cuuint32_t)(H / 32), 2, 1}, estr[5] = {1, 1, 1, 1, 1};
-    const CUresult rc = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(theta + woff), dims, strides, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (rc != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled (x.W map) failed with CUresult %d", (int)rc);
-        return DMDQN_ERR_CUDA;
-    }
-    return DMDQN_OK;
+    const cuuint32_t box[5] = {32, 4, (cuuint32_t)(H / 32), 2, 1};
+    return encode_tiled(out, theta + woff, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
 }
 int make_w2_tensor_map(const TcArgs& A, CUtensorMap* out) {
     return encode_map3(out, A.nets.theta + A.L.w2, H, H, A.d.n_nets, (cuuint64_t)H * sizeof(float),

@@ -795,9 +795,11 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A, cons
             int prev = -1;                                     // as in K3: the previous item is published from this lane's idle window
             for (int q = k4_next(A, blockIdx.x, n_items); q < n_items; q = k4_next(A, q + gridDim.x, n_items)) {
                 ok = mma_gemm<PASSES, false>(sbase, tmem, sbase + Fwd::R, sbase + Fwd::XLO, 0, Dp, ring, ok);
+                ok = mma_gemm<PASSES, false>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, H, ring, ok);
+                // (the epilogue issues the second half of an item's dh1^T stores after it has published the NEXT item's layer-1
+                // operand, so the previous item is complete only once this item's LAYER-2 operand has been published)
                 if (prev >= 0) flag_release_add(A.k4a_done + prev / A.tiles);
                 prev = q;
-                ok = mma_gemm<PASSES, false>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, H, ring, ok);
                 ok = mma_gemm<PASSES, true>(sbase, tmem, sbase + Fwd::R, 0, tmem + 256u, H, ring, ok);
             }
             if (!ok) atomicExch(A.error, 14);
@@ -845,8 +847,10 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A, cons
             TS_DECL;
             TS();
             KT_FIRST();
-            xg.store(sbase);          // observation rows and b1 | b2 | W3 of this item: requested one item ago
-            a_ready(sbase);
+            if (q_last < 0) {         // first item of the CTA; later items were published at the end of the previous one
+                xg.store(sbase);      // observation rows and b1 | b2 | W3 of this item: requested one item ago
+                a_ready(sbase);
+            }
             epi_sync();        // biases / head weights visible to every epilogue thread
             TS();
             ok = wait_gemm(sbase, ring, ok);
@@ -1038,15 +1042,27 @@ __global__ void __launch_bounds__(NT_F, 1) tc_online_kernel(const TcArgs A, cons
             // dh1 = (dh2 W2^T) * relu'(h1)
             ok = wait_gemm(sbase, ring, ok);
             TS();
-#pragma unroll 1
-            for (int cc = 0; cc < 2; ++cc) {
-                const int c0 = e.part * 64 + cc * 32;
+            {   // The accumulator is read in two halves; as soon as the second half is in registers the TMEM columns and R are free,
+                // so the NEXT item's layer-1 operand is published first (its GEMM starts, and the proxy fence inside a_ready() --
+                // a MEMBAR.ALL.CTA -- does not wait for 32 fresh global stores per thread), and the second half of the dh1^T stores
+                // goes out in that GEMM's shadow.
                 float v[32];
+                const int c0 = e.part * 64;
                 tmem_ld32(tmem + e.lane_addr + (uint32_t)c0, v);
                 if (valid) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        A.dh1[sb * H + (size_t)(c0 + j) * B + gr] = ((mask1[cc] >> j) & 1u) ? v[j] : 0.f;
+                        A.dh1[sb * H + (size_t)(c0 + j) * B + gr] = ((mask1[0] >> j) & 1u) ? v[j] : 0.f;
+                }
+                tmem_ld32(tmem + e.lane_addr + (uint32_t)(c0 + 32), v);
+                if (qn < n_items) {
+                    xg.store(sbase);
+                    a_ready(sbase);
+                }
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        A.dh1[sb * H + (size_t)(c0 + 32 + j) * B + gr] = ((mask1[1] >> j) & 1u) ? v[j] : 0.f;
                 }
             }
             TS();

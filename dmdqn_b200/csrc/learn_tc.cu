@@ -219,8 +219,9 @@ __device__ __forceinline__ void flag_release_add(int* f) {
     asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(f) : "memory");
 }
 __device__ __forceinline__ bool flag_acquire_ge(const int* f, int want) {
-    // bounded by an iteration count (one register) rather than by the global timer: 2^23 polls of >= 256 ns are > 2 s
-    for (int i = 0; i < (1 << 23); ++i) {
+    // bounded by an iteration count (one register) rather than by the global timer: 2^21 polls of a ~256 ns sleep + an L2 round
+    // trip are 2-3 s, the same order as the mbarrier waits' bound
+    for (int i = 0; i < (1 << 21); ++i) {
         int v;
         asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
         if (v >= want) return true;
